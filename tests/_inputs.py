@@ -1,0 +1,94 @@
+"""Seeded synthetic inputs shared by the oracle tests, the GPU parity tests and the golden generator.
+
+`fa_inputs` / `seg_case` restate the generators in tests/golden/make_golden.py (which cannot be imported on
+the GPU box because it imports the reference); tests/test_oracle_*.py prove they agree by reproducing the
+golden outputs from these inputs.
+"""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def fa_inputs(shape, dist, seed):
+    rng = np.random.default_rng(seed)
+    x1 = rng.standard_normal(shape).astype(np.float32)
+    x2 = rng.standard_normal(shape).astype(np.float32)
+    if dist in ("relu", "dead"):
+        x1 = np.maximum(x1, 0.0)
+        x2 = np.maximum(x2, 0.0)
+    if dist == "dead":
+        x1[1, 0] = 0.0
+    return x1, x2
+
+
+def pos_inputs(s1, s2, seed):
+    rng = np.random.default_rng(seed)
+    x1 = np.maximum(rng.standard_normal(s1), 0).astype(np.float32)
+    x2 = np.maximum(rng.standard_normal(s2), 0).astype(np.float32)
+    return x1, x2
+
+
+def seg_case(kind, seed, shape=(2, 37, 53), nc=19, pred_dtype=np.int64, target_dtype=np.uint8):
+    rng = np.random.default_rng(seed)
+    target = rng.integers(0, nc, shape).astype(target_dtype)
+    ign = rng.random(shape) < 0.1
+    target[ign] = 255
+    rnd = rng.integers(0, nc, shape)
+    keep = rng.random(shape) < 0.7
+    pred = np.where(keep, np.where(ign, 0, target), rnd).astype(pred_dtype)
+    if kind == "all_ignored":
+        target[...] = 255
+    elif kind == "single_class":
+        target[...] = 3
+        pred[...] = 3
+    elif kind == "oor_target":
+        target[0, :5, :7] = 100
+        pred[0, 2, :4] = 100
+    elif kind == "oor_pred":
+        pred[0, :3, :] = nc + 4
+        if np.issubdtype(pred_dtype, np.signedinteger):
+            pred[1, :2, :] = -1
+    mask = target != 255
+    if kind == "explicit_mask":
+        mask = rng.random(shape) < 0.5
+    return pred, target, mask
+
+
+SEG_SEQS = [
+    ("mixed19", 19, [("plain", 1, (2, 37, 53), "int64", "uint8"), ("plain", 2, (1, 64, 96), "int64", "uint8"),
+                     ("oor_target", 3, (2, 37, 53), "int64", "uint8"), ("single_class", 4, (1, 16, 16), "int64", "uint8"),
+                     ("oor_pred", 5, (2, 21, 35), "int64", "uint8"), ("explicit_mask", 6, (2, 37, 53), "int64", "uint8")]),
+    ("with_all_ignored", 19, [("plain", 7, (1, 40, 40), "int64", "uint8"), ("all_ignored", 8, (1, 40, 40), "int64", "uint8"),
+                              ("plain", 9, (3, 33, 31), "int64", "uint8")]),
+    ("dtypes", 19, [("plain", 10, (2, 37, 53), "uint8", "uint8"), ("plain", 11, (2, 37, 53), "int32", "int64"),
+                    ("oor_pred", 12, (2, 37, 53), "int32", "int32"), ("plain", 13, (2, 37, 53), "int64", "int64")]),
+    ("nc6", 6, [("plain", 14, (2, 37, 53), "int64", "uint8")]),
+    ("only_all_ignored", 19, [("all_ignored", 15, (1, 8, 8), "int64", "uint8")]),
+]
+
+
+def cfg3_maps(num_maps, seed=54321, shape=(1024, 2048), nc=19):
+    """BASELINE config 3: uint8 targets with 10% ignore, int64 preds 70% correct."""
+    rng = np.random.default_rng(seed)
+    for _ in range(num_maps):
+        target = rng.integers(0, nc, shape, dtype=np.uint8)
+        ign = rng.random(shape, dtype=np.float32) < 0.1
+        target[ign] = 255
+        rnd = rng.integers(0, nc, shape, dtype=np.uint8)
+        keep = rng.random(shape, dtype=np.float32) < 0.7
+        pred = np.where(keep, np.where(ign, 0, target), rnd).astype(np.int64)
+        yield pred[None], target[None], (target != 255)[None]
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+
+
+def expand_pooled(gp, k, H, W):
+    """Golden gradients are stored on the pooled grid (constant per k x k window, zero on the dropped border)."""
+    B, C, h, w = gp.shape
+    out = np.zeros((B, C, H, W), dtype=gp.dtype)
+    out[:, :, : h * k, : w * k] = np.repeat(np.repeat(gp, k, 2), k, 3)
+    return out

@@ -1,0 +1,80 @@
+"""Pins oracle/fa_oracle.py against the golden vectors produced by the unmodified reference FALoss
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from _inputs import fa_inputs, pos_inputs, load_golden, expand_pooled
+from oracle import fa_oracle
+
+G = load_golden("fa_golden.npz")
+NAMES = [str(n) for n in G["names"]]
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.nan_to_num(a) - np.nan_to_num(b)) / max(np.linalg.norm(np.nan_to_num(b)), 1e-300)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_mode_matches_reference_fp64(name):
+    B, C, H, W, k, seed = (int(v) for v in G[f"{name}/meta"])
+    red = str(G[f"{name}/reduction"])
+    dist = str(G[f"{name}/dist"])
+    x1, x2 = fa_inputs((B, C, H, W), dist, seed)
+    go = None
+    if red == "none":
+        n = (W // k) ** 2
+        go = np.random.default_rng(seed + 1000).standard_normal((B, C, n * n)).astype(np.float32)
+    loss, d1, d2 = fa_oracle.fa_reference(x1, x2, k, red, grad_out=go)
+    gl = G[f"{name}/loss64"]
+    g1 = expand_pooled(G[f"{name}/g1_64"], k, H, W)
+    g2 = expand_pooled(G[f"{name}/g2_64"], k, H, W)
+    if dist == "dead":
+        assert np.isnan(loss) and np.isnan(gl)
+        assert np.array_equal(np.isnan(d1), np.isnan(g1))
+        assert np.array_equal(np.isnan(d2), np.isnan(g2))
+    else:
+        np.testing.assert_allclose(loss, gl, rtol=1e-12, atol=1e-14 if red == "none" else 0)
+    assert relerr(d1, g1) < 1e-10
+    assert relerr(d2, g2) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["cfg2_relu_6x1x64x128", "floor_relu_1x2x70x133", "tall_relu_1x1x128x64"])
+def test_sorted_closed_form_equals_bruteforce(name):
+    B, C, H, W, k, seed = (int(v) for v in G[f"{name}/meta"])
+    x1, x2 = fa_inputs((B, C, H, W), str(G[f"{name}/dist"]), seed)
+    a = fa_oracle.fa_reference(x1, x2, k, "mean")
+    b = fa_oracle.fa_reference(x1, x2, k, "mean", materialise_limit=0)     # forces the O(n log n) path
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+    assert relerr(a[1], b[1]) < 1e-12 and relerr(a[2], b[2]) < 1e-12
+
+
+def test_fp32_reference_is_within_north_star_tolerance_of_fp64():
+    """Context for the GPU tolerances: the reference's own fp32 run vs its fp64 run."""
+    for name in NAMES:
+        if str(G[f"{name}/dist"]) == "dead" or str(G[f"{name}/reduction"]) == "none":
+            continue
+        l64, l32 = float(G[f"{name}/loss64"]), float(G[f"{name}/loss32"])
+        assert abs(l32 - l64) / abs(l64) < 1e-4
+        assert relerr(G[f"{name}/g1_32"], G[f"{name}/g1_64"]) < 2e-2    # sign flips: see SURVEY section 7
+
+
+def test_shape_errors():
+    x = np.zeros((1, 1, 8, 8))
+    with pytest.raises(ValueError):
+        fa_oracle.fa_reference(x[0], x[0])
+    with pytest.raises(ValueError):
+        fa_oracle.fa_reference(x, np.zeros((1, 1, 8, 16)))
+
+
+P = load_golden("fa_position_golden.npz")
+
+
+@pytest.mark.parametrize("name", [str(n) for n in P["names"]])
+def test_position_mode_matches_torch_autograd(name):
+    B, C1, H, W, C2, k, seed = (int(v) for v in P[f"{name}/meta"])
+    x1, x2 = pos_inputs((B, C1, H, W), (B, C2, H, W), seed)
+    red = str(P[f"{name}/reduction"])
+    loss, d1, d2 = fa_oracle.fa_position(x1, x2, k, red, chunk=100)
+    np.testing.assert_allclose(loss, float(P[f"{name}/loss64"]), rtol=1e-12)
+    assert relerr(d1, P[f"{name}/g1_64"]) < 1e-10
+    assert relerr(d2, P[f"{name}/g2_64"]) < 1e-10
