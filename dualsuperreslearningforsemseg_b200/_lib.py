@@ -1,0 +1,84 @@
+"""ctypes binding of libdsrl_b200.so (the C-ABI declared in include/dsrl_b200.h).
+
+There is deliberately no fallback: if the library is missing, or a compute entry point is called without a
+B200-class device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libdsrl_b200.so")
+
+OK, ERR_BAD_SHAPE, ERR_BAD_DTYPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_BAD_ARG = 0, -1, -2, -3, -4, -5
+FA_REFERENCE, FA_POSITION = 0, 1
+REDUCE_NONE, REDUCE_MEAN, REDUCE_SUM = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+U8, I32, I64 = 0, 1, 2
+
+# every symbol include/dsrl_b200.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = (
+    "dsrl_version", "dsrl_last_error", "dsrl_launch_count",
+    "dsrl_fa_saved_bytes", "dsrl_fa_workspace_bytes", "dsrl_fa_forward", "dsrl_fa_backward",
+    "dsrl_seg_counts", "dsrl_seg_counts_from_logits",
+)
+
+
+class DsrlError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libdsrl_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i, sz, i64 = c.c_void_p, c.c_int, c.c_size_t, c.c_int64
+    lib.dsrl_version.restype = i
+    lib.dsrl_version.argtypes = []
+    lib.dsrl_last_error.restype = c.c_char_p
+    lib.dsrl_last_error.argtypes = []
+    lib.dsrl_launch_count.restype = c.c_uint64
+    lib.dsrl_launch_count.argtypes = []
+    lib.dsrl_fa_saved_bytes.restype = sz
+    lib.dsrl_fa_saved_bytes.argtypes = [i] * 7
+    lib.dsrl_fa_workspace_bytes.restype = sz
+    lib.dsrl_fa_workspace_bytes.argtypes = [i] * 7
+    lib.dsrl_fa_forward.restype = i
+    lib.dsrl_fa_forward.argtypes = [i, i, vp, vp, i, i, i, i, i, i, i, i, vp, vp, sz, vp, sz, vp]
+    lib.dsrl_fa_backward.restype = i
+    lib.dsrl_fa_backward.argtypes = [i, i, vp, vp, vp, sz, vp, vp, vp, i, i, i, i, i, i, i, vp, sz, vp]
+    lib.dsrl_seg_counts.restype = i
+    lib.dsrl_seg_counts.argtypes = [vp, i, vp, i, vp, i64, i64, i, i, vp, vp]
+    lib.dsrl_seg_counts_from_logits.restype = i
+    lib.dsrl_seg_counts_from_logits.argtypes = [vp, vp, i, vp, i64, i64, i64, i, i, vp, vp, vp]
+
+
+def lib():
+    """The loaded library; raises if it has not been built (run `python -m dualsuperreslearningforsemseg_b200.build`)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -m dualsuperreslearningforsemseg_b200.build` "
+                        "(needs nvcc).  There is no CPU or PyTorch fallback for this path.")
+                handle = ctypes.CDLL(LIB_PATH)
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != OK:
+        raise DsrlError(rc, lib().dsrl_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().dsrl_launch_count())

@@ -1,0 +1,61 @@
+// Diagnostics + process-wide state of libdsrl_b200.so.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dsrl {
+
+static thread_local char t_err[1024] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_last_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::once_flag g_dev_once;
+static int g_sm_count = 0, g_cc_major = 0, g_dev_status = DSRL_ERR_CUDA;
+static char g_dev_msg[256] = "";
+
+static void probe_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        snprintf(g_dev_msg, sizeof(g_dev_msg), "no CUDA device (%s); libdsrl_b200 has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g_cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (g_cc_major != 10) {
+        snprintf(g_dev_msg, sizeof(g_dev_msg), "device compute capability %d.x; this library is sm_100a only", g_cc_major);
+        return;
+    }
+    g_dev_status = DSRL_OK;
+}
+
+int require_device() {
+    std::call_once(g_dev_once, probe_device);
+    if (g_dev_status != DSRL_OK) set_last_error("%s", g_dev_msg);
+    return g_dev_status;
+}
+
+int device_sm_count() {
+    std::call_once(g_dev_once, probe_device);
+    return g_sm_count > 0 ? g_sm_count : 148;
+}
+
+}  // namespace dsrl
+
+extern "C" {
+int dsrl_version(void) { return DSRL_B200_VERSION; }
+const char *dsrl_last_error(void) { return dsrl::t_err; }
+uint64_t dsrl_launch_count(void) { return dsrl::g_launches.load(std::memory_order_relaxed); }
+}

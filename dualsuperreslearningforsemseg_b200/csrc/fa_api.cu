@@ -1,0 +1,73 @@
+// C-ABI entry points of the FA loss (argument validation + mode dispatch).  See include/dsrl_b200.h.
+#include "common.cuh"
+
+namespace dsrl {
+size_t fa_ref_saved_bytes(int B, int C, int H, int W, int k);
+size_t fa_ref_workspace_bytes(int B, int C, int H, int W, int k);
+int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W, int k, int reduction, int need_grad,
+                   float *loss_out, void *saved, size_t saved_bytes, void *ws, size_t ws_bytes, cudaStream_t st);
+int fa_ref_backward(const void *saved, size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C,
+                    int H, int W, int k, int reduction, void *ws, size_t ws_bytes, cudaStream_t st);
+
+size_t fa_pos_saved_bytes(int B, int C1, int C2, int H, int W, int k);
+size_t fa_pos_workspace_bytes(int B, int C1, int C2, int H, int W, int k);
+int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k,
+                   int reduction, int need_grad, float *loss_out, void *saved, size_t saved_bytes, void *ws,
+                   size_t ws_bytes, cudaStream_t st);
+int fa_pos_backward(int precision, const float *x1, const float *x2, const void *saved, size_t saved_bytes,
+                    const float *grad_out, float *dx1, float *dx2, int B, int C1, int C2, int H, int W, int k,
+                    int reduction, void *ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace dsrl
+
+using namespace dsrl;
+
+static int check_mode(int mode, int C1, int C2, int reduction) {
+    if (mode != DSRL_FA_REFERENCE && mode != DSRL_FA_POSITION) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA: unknown mode %d", mode);
+    if (reduction != DSRL_REDUCE_NONE && reduction != DSRL_REDUCE_MEAN && reduction != DSRL_REDUCE_SUM)
+        DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA: unknown reduction %d", reduction);
+    // FALoss.py:20 -- "Feature map inputs to FALoss.forward() should be of same size"
+    if (mode == DSRL_FA_REFERENCE && C1 != C2) DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(reference): inputs must have the same shape (C1=%d, C2=%d)", C1, C2);
+    if (mode == DSRL_FA_POSITION && reduction == DSRL_REDUCE_NONE)
+        DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): reduction='none' would materialise the N x N affinity; use mean or sum");
+    return DSRL_OK;
+}
+
+extern "C" size_t dsrl_fa_saved_bytes(int mode, int B, int C1, int C2, int H, int W, int k) {
+    if (mode == DSRL_FA_REFERENCE) return C1 == C2 ? fa_ref_saved_bytes(B, C1, H, W, k) : 0;
+    if (mode == DSRL_FA_POSITION) return fa_pos_saved_bytes(B, C1, C2, H, W, k);
+    return 0;
+}
+
+extern "C" size_t dsrl_fa_workspace_bytes(int mode, int B, int C1, int C2, int H, int W, int k) {
+    if (mode == DSRL_FA_REFERENCE) return C1 == C2 ? fa_ref_workspace_bytes(B, C1, H, W, k) : 0;
+    if (mode == DSRL_FA_POSITION) return fa_pos_workspace_bytes(B, C1, C2, H, W, k);
+    return 0;
+}
+
+extern "C" int dsrl_fa_forward(int mode, int precision, const float *x1, const float *x2, int B, int C1, int C2, int H,
+                               int W, int k, int reduction, int need_grad, float *loss_out, void *saved,
+                               size_t saved_bytes, void *workspace, size_t workspace_bytes, dsrl_stream_t stream) {
+    int rc = check_mode(mode, C1, C2, reduction);
+    if (rc) return rc;
+    if (!x1 || !x2 || !loss_out || !saved || !workspace) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA forward: null pointer");
+    if ((rc = require_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == DSRL_FA_REFERENCE)
+        return fa_ref_forward(x1, x2, B, C1, H, W, k, reduction, need_grad, loss_out, saved, saved_bytes, workspace, workspace_bytes, st);
+    return fa_pos_forward(precision, x1, x2, B, C1, C2, H, W, k, reduction, need_grad, loss_out, saved, saved_bytes, workspace, workspace_bytes, st);
+}
+
+extern "C" int dsrl_fa_backward(int mode, int precision, const float *x1, const float *x2, const void *saved,
+                                size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C1, int C2,
+                                int H, int W, int k, int reduction, void *workspace, size_t workspace_bytes,
+                                dsrl_stream_t stream) {
+    int rc = check_mode(mode, C1, C2, reduction);
+    if (rc) return rc;
+    if (!saved || !grad_out || !workspace) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA backward: null pointer");
+    if (!dx1 && !dx2) return DSRL_OK;
+    if ((rc = require_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == DSRL_FA_REFERENCE)
+        return fa_ref_backward(saved, saved_bytes, grad_out, dx1, dx2, B, C1, H, W, k, reduction, workspace, workspace_bytes, st);
+    return fa_pos_backward(precision, x1, x2, saved, saved_bytes, grad_out, dx1, dx2, B, C1, C2, H, W, k, reduction, workspace, workspace_bytes, st);
+}

@@ -1,0 +1,160 @@
+"""Host side of the segmentation-count kernel (K4): tensor plumbing around ``dsrl_seg_counts`` and the
+deferred, exact float64 finish shared by ``mIoU`` and ``Accuracy``."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+_DT = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64}
+IGNORE_DEFAULT = 255          # datasets/Cityscapes/settings.py IGNORE_CLASS_LABEL
+_last_nc = 19                  # datasets/Cityscapes/settings.py NUM_CLASSES; updated by every mIoU instance
+_cache = {"key": None, "nc": None, "rows": None}
+
+
+def row_len(nc: int) -> int:
+    return 3 * nc + 2
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dsrl-b200 metrics need a CUDA device: there is no CPU fallback on this path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_cuda(x, dev, labels: bool):
+    """numpy / CPU tensor / CUDA tensor -> contiguous CUDA tensor of a dtype the kernel reads natively."""
+    if isinstance(x, np.ndarray):
+        if x.dtype == np.bool_:
+            x = x.view(np.uint8)
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    elif not torch.is_tensor(x):
+        x = torch.as_tensor(np.asarray(x))
+    if x.dtype == torch.bool:
+        x = x.view(torch.uint8) if x.is_contiguous() else x.contiguous().view(torch.uint8)
+    if labels and x.dtype not in _DT:
+        if x.dtype in (torch.int8, torch.int16):
+            x = x.to(torch.int32)
+        else:
+            raise TypeError(f"label maps must be integer typed, got {x.dtype}")
+    if not labels and x.dtype != torch.uint8:
+        x = (x != 0).view(torch.uint8)
+    if not x.is_cuda:
+        x = x.to(dev, non_blocking=True)
+    return x.contiguous()
+
+
+def _key(*tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype) if t is not None else None for t in tensors)
+
+
+def counts_for_update(pred, target, mask, nc: int, updates_leading: bool = False, ignore_label: int = IGNORE_DEFAULT):
+    """Enqueue K4 for one ``update()`` (or U of them if ``updates_leading``) and return the device rows
+    ``[U, 3*nc+2]`` int64 without synchronising."""
+    shp = tuple(np.shape(pred)) if not torch.is_tensor(pred) else tuple(pred.shape)
+    tshp = tuple(np.shape(target)) if not torch.is_tensor(target) else tuple(target.shape)
+    want = 4 if updates_leading else 3
+    # same BUG CHECKs as mIoU.py:16-17 / Accuracy.py:14-15
+    assert shp == tshp, "BUG CHECK: 'pred' and 'target' must be of the same shape of (B, H, W)."
+    assert len(shp) == want, "BUG CHECK: 'target' and 'pred' must be (B, H, W) channel-order dimensions."
+    dev = pred.device if torch.is_tensor(pred) and pred.is_cuda else (
+        target.device if torch.is_tensor(target) and target.is_cuda else _device())
+    p = _as_cuda(pred, dev, True)
+    t = _as_cuda(target, dev, True)
+    m = _as_cuda(mask, dev, False) if mask is not None else None
+    if m is not None and tuple(m.shape) != shp:
+        m = m.expand(shp).contiguous()
+    U = shp[0] if updates_leading else 1
+    npix = int(np.prod(shp[1:] if updates_leading else shp, dtype=np.int64))
+    key = _key(p, t, m) + (U, ignore_label if m is None else None)
+    if _cache["key"] == key and _cache["nc"] == nc:
+        return _cache["rows"]
+    rows = torch.empty((U, row_len(nc)), dtype=torch.int64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dsrl_seg_counts(ctypes.c_void_p(p.data_ptr()), _DT[p.dtype], ctypes.c_void_p(t.data_ptr()),
+                                              _DT[t.dtype], ctypes.c_void_p(m.data_ptr()) if m is not None else None,
+                                              U, npix, nc, ignore_label, ctypes.c_void_p(rows.data_ptr()), stream))
+    # keep the inputs alive until the rows are consumed (the kernel is only enqueued) and remember the rows:
+    # the reference's callers pass the same arrays to Accuracy.update and mIoU.update back to back
+    # (train_or_resume.py:480-481, benchmark.py:76-77); the second call re-uses the first one's pass.
+    rows._dsrl_keepalive = (p, t, m)
+    _cache.update(key=key, nc=nc, rows=rows)
+    return rows
+
+
+def counts_from_logits(logits, target, mask, nc: int, ignore_label: int = IGNORE_DEFAULT, want_pred: bool = False):
+    """Fused argmax + counts for ONE update: logits (B, NC, H, W) fp32 CUDA, target (B, H, W)."""
+    if not (torch.is_tensor(logits) and logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 4):
+        raise TypeError("logits must be a 4-D float32 CUDA tensor (B, NC, H, W)")
+    B, C, H, W = logits.shape
+    assert C == nc, "BUG CHECK: logits channel count must equal num_classes."
+    assert tuple(target.shape) == (B, H, W), "BUG CHECK: 'pred' and 'target' must be of the same shape of (B, H, W)."
+    dev = logits.device
+    lg = logits.contiguous()
+    t = _as_cuda(target, dev, True)
+    m = _as_cuda(mask, dev, False) if mask is not None else None
+    rows = torch.empty((1, row_len(nc)), dtype=torch.int64, device=dev)
+    pred = torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_pred else None
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dsrl_seg_counts_from_logits(
+            ctypes.c_void_p(lg.data_ptr()), ctypes.c_void_p(t.data_ptr()), _DT[t.dtype],
+            ctypes.c_void_p(m.data_ptr()) if m is not None else None, 1, B, H * W, nc, ignore_label,
+            ctypes.c_void_p(rows.data_ptr()), ctypes.c_void_p(pred.data_ptr()) if pred is not None else None, stream))
+    rows._dsrl_keepalive = (lg, t, m)
+    return rows, pred
+
+
+class PendingRows:
+    """Device count rows not yet brought to the host.  One D2H + sync when the owner needs numbers."""
+
+    def __init__(self):
+        self.chunks = []
+
+    def add(self, rows):
+        self.chunks.append(rows)
+
+    def __len__(self):
+        return sum(int(c.shape[0]) for c in self.chunks)
+
+    def device_table(self):
+        if not self.chunks:
+            return None
+        return self.chunks[0] if len(self.chunks) == 1 else torch.cat(self.chunks, dim=0)
+
+    def replace(self, table):
+        self.chunks = [table] if table is not None else []
+
+    def drain(self) -> np.ndarray:
+        table = self.device_table()
+        self.chunks = []
+        if table is None:
+            return np.zeros((0, 0), dtype=np.int64)
+        return table.cpu().numpy()
+
+
+def sync_rows(pending: PendingRows, group=None, mode: str = "sum"):
+    """Multi-GPU exchange for the per-update rows.  ``sum``: every rank processed a shard of each
+    update's pixels (same number of updates everywhere) -> element-wise int64 all-reduce, bit-exact at any world
+    size.  ``gather``: ranks processed different updates -> all-gather, rank-major order."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    table = pending.device_table()
+    if table is None:
+        return
+    if mode == "sum":
+        table = table.clone()
+        dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
+    elif mode == "gather":
+        world = dist.get_world_size(group)
+        outs = [torch.empty_like(table) for _ in range(world)]
+        dist.all_gather(outs, table.contiguous(), group=group)
+        table = torch.cat(outs, dim=0)
+    else:
+        raise ValueError("mode must be 'sum' or 'gather'")
+    pending.replace(table)

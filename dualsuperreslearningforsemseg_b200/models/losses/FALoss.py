@@ -1,0 +1,141 @@
+"""Feature-Affinity loss -- B200 drop-in for the reference's ``models.losses.FALoss``.
+
+Mirrors ``models/losses/FALoss.py:5-34`` of the reference: same class name, base class
+(``torch.nn.modules.loss._Loss``), constructor ``(subsample_factor=8, size_average=None, reduce=None,
+reduction='mean')`` (the reference ignores ``size_average``/``reduce`` and so do we, FALoss.py:15), same
+``forward(feature_map1, feature_map2)`` contract (4-D, equal shapes, FALoss.py:19-20) and the same result:
+a 0-dim tensor for ``mean``/``sum``, ``(B, C, n*n)`` for ``none`` (n = (W // k)**2), differentiable w.r.t. both
+inputs.  Used at ``command_handlers/train_or_resume.py:118,437,444`` as ``w2 * FALoss()(a, b)`` inside
+``(CE + MSE + FA).backward()``.
+
+All arithmetic runs in hand-written sm_100a kernels behind the C-ABI of ``libdsrl_b200.so``
+(``include/dsrl_b200.h``); this file only owns tensors, the autograd node and error translation.  There is no
+PyTorch/CPU fallback: CPU tensors raise.
+
+Keyword-only extensions (defaults preserve the reference behaviour):
+  affinity='reference' | 'position'   'position' = the paper's N x N position affinity (not in the reference)
+  precision=None | 'fp32' | 'tf32' | 'bf16'   tensor-core operand precision for 'position'
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ... import _lib
+
+_RED = {"none": _lib.REDUCE_NONE, "mean": _lib.REDUCE_MEAN, "sum": _lib.REDUCE_SUM}
+_PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "bf16": _lib.PREC_BF16}
+_MODE = {"reference": _lib.FA_REFERENCE, "position": _lib.FA_POSITION}
+
+_size_cache = {}
+
+
+def _sizes(mode, B, C1, C2, H, W, k):
+    key = (mode, B, C1, C2, H, W, k)
+    v = _size_cache.get(key)
+    if v is None:
+        L = _lib.lib()
+        v = (int(L.dsrl_fa_saved_bytes(*key)), int(L.dsrl_fa_workspace_bytes(*key)))
+        _size_cache[key] = v
+    return v
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _FAFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, k, reduction, mode, precision):
+        B, C1, H, W = x1.shape
+        C2 = x2.shape[1]
+        x1c, x2c = x1.contiguous(), x2.contiguous()
+        saved_bytes, ws_bytes = _sizes(mode, B, C1, C2, H, W, k)
+        if saved_bytes == 0:
+            raise _lib.DsrlError(_lib.ERR_UNSUPPORTED,
+                                 f"FALoss: unsupported geometry B={B} C=({C1},{C2}) H={H} W={W} k={k}")
+        dev = x1.device
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if reduction == _lib.REDUCE_NONE:
+            n = (W // k) ** 2
+            out = torch.empty((B, C1, n * n), dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty((), dtype=torch.float32, device=dev)
+        need_grad = int(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().dsrl_fa_forward(mode, precision, _ptr(x1c), _ptr(x2c), B, C1, C2, H, W, k, reduction,
+                                                  need_grad, _ptr(out), _ptr(saved), saved_bytes, _ptr(ws), ws_bytes,
+                                                  stream))
+        ctx.geom = (B, C1, C2, H, W, k, reduction, mode, precision, saved_bytes, ws_bytes)
+        if mode == _lib.FA_POSITION:
+            ctx.save_for_backward(saved, x1c, x2c)
+        else:
+            ctx.save_for_backward(saved)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        B, C1, C2, H, W, k, reduction, mode, precision, saved_bytes, ws_bytes = ctx.geom
+        tensors = ctx.saved_tensors
+        saved = tensors[0]
+        x1c = tensors[1] if len(tensors) > 1 else None
+        x2c = tensors[2] if len(tensors) > 2 else None
+        dev = saved.device
+        go = grad_out.to(torch.float32).contiguous()
+        dx1 = torch.empty((B, C1, H, W), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dx2 = torch.empty((B, C2, H, W), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().dsrl_fa_backward(mode, precision, _ptr(x1c), _ptr(x2c), _ptr(saved), saved_bytes,
+                                                   _ptr(go), _ptr(dx1), _ptr(dx2), B, C1, C2, H, W, k, reduction,
+                                                   _ptr(ws), ws_bytes, stream))
+        return dx1, dx2, None, None, None, None
+
+
+class FALoss(torch.nn.modules.loss._Loss):
+    __constants__ = ['reduction']
+
+    def __init__(self, subsample_factor: int = 8, size_average=None, reduce=None, reduction: str = 'mean', *,
+                 affinity: str = 'reference', precision=None) -> None:
+        # the reference passes None for size_average/reduce whatever the caller gave (FALoss.py:15)
+        super().__init__(size_average=None, reduce=None, reduction=reduction)
+        if affinity not in _MODE:
+            raise ValueError(f"affinity must be 'reference' or 'position', got {affinity!r}")
+        if precision not in _PREC:
+            raise ValueError(f"precision must be one of {sorted(p for p in _PREC if p)}, got {precision!r}")
+        self.subsample_factor = subsample_factor
+        self.affinity = affinity
+        self.precision = precision
+
+    def extra_repr(self) -> str:
+        return f"subsample_factor={self.subsample_factor}, reduction={self.reduction!r}, affinity={self.affinity!r}"
+
+    def forward(self, feature_map1: torch.Tensor, feature_map2: torch.Tensor) -> torch.Tensor:
+        # same BUG CHECKs (and wording) as FALoss.py:19-20
+        torch._assert(feature_map1.dim() == 4 and feature_map2.dim() == 4,
+                      "BUG CHECK: Feature map inputs to FALoss.forward() must have 4 dimensions (B, C, H, W).")
+        if self.affinity == 'reference':
+            torch._assert(feature_map1.shape == feature_map2.shape,
+                          "BUG CHECK: Feature map inputs to FALoss.forward() should be of same size.")
+        else:
+            torch._assert(feature_map1.shape[0] == feature_map2.shape[0] and feature_map1.shape[2:] == feature_map2.shape[2:],
+                          "BUG CHECK: Feature map inputs to FALoss.forward() must agree in B, H and W.")
+        if self.reduction not in _RED:
+            raise ValueError(f"{self.reduction} is not a valid value for reduction")
+        if not (feature_map1.is_cuda and feature_map2.is_cuda):
+            raise RuntimeError("FALoss (dsrl-b200) runs only on CUDA tensors: there is no CPU fallback on this path")
+        if feature_map1.device != feature_map2.device:
+            raise RuntimeError("FALoss inputs must live on the same device")
+        if feature_map1.dtype != torch.float32 or feature_map2.dtype != torch.float32:
+            # the reference itself rejects half/bfloat16 here ("Low precision dtypes not supported", linalg.norm)
+            raise RuntimeError("FALoss (dsrl-b200) supports float32 feature maps only")
+        k = int(self.subsample_factor)
+        if feature_map1.shape[2] // k < 1 or feature_map1.shape[3] // k < 1:
+            raise RuntimeError("FALoss: feature map smaller than the pooling window")
+        return _FAFunction.apply(feature_map1, feature_map2, k, _RED[self.reduction], _MODE[self.affinity],
+                                 _PREC[self.precision])

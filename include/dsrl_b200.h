@@ -1,0 +1,116 @@
+/* dsrl_b200.h -- C-ABI of libdsrl_b200.so: the B200 (sm_100a) implementation of the DSRL hot path.
+ *
+ * The reference (sanje2v/DualSuperResLearningForSemSeg) is pure Python and has no FFI layer; the boundary
+ * this library sits behind is the pair of Python import surfaces the training/benchmark scripts use:
+ *
+ *   from models.losses import FALoss            (models/losses/FALoss.py:5-34; called at
+ *                                                command_handlers/train_or_resume.py:118,437,444)
+ *   from metrices import mIoU, Accuracy         (metrices/mIoU.py:5-41, metrices/Accuracy.py:4-30; called at
+ *                                                command_handlers/train_or_resume.py:389-390,476-481 and
+ *                                                command_handlers/benchmark.py:56-57,76-77)
+ *
+ * Each entry point below names the reference computation it replaces.  Conventions:
+ *   - plain C: pointers, sizes, ints.  No torch / C++ types cross the boundary.
+ *   - every data pointer is a DEVICE pointer to contiguous memory; `stream` is a cudaStream_t.  All work is
+ *     enqueued on that stream; no entry point synchronises, allocates or frees caller memory.
+ *   - return value: DSRL_OK (0) or a negative DSRL_ERR_*; dsrl_last_error() gives a thread-local message.
+ *   - re-entrant: the only global state is one-time, mutex-guarded kernel attribute / descriptor setup.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns DSRL_ERR_CUDA.
+ */
+#ifndef DSRL_B200_H
+#define DSRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSRL_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef void *dsrl_stream_t; /* cudaStream_t */
+
+enum dsrl_status {
+    DSRL_OK = 0,
+    DSRL_ERR_BAD_SHAPE = -1,   /* FALoss.py:19-20 / mIoU.py:16-17 shape contracts violated */
+    DSRL_ERR_BAD_DTYPE = -2,
+    DSRL_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve (size limits, mode/reduction combos) */
+    DSRL_ERR_CUDA = -4,
+    DSRL_ERR_BAD_ARG = -5      /* null pointer, workspace too small, unknown enum value */
+};
+
+enum dsrl_fa_mode {
+    DSRL_FA_REFERENCE = 0, /* what FALoss.py:8-34 computes: spectral norm, per-(b,c) w x w Gram, all-pairs L1 */
+    DSRL_FA_POSITION = 1   /* paper's N x N position affinity (opt-in; not in the reference) */
+};
+
+enum dsrl_reduction { DSRL_REDUCE_NONE = 0, DSRL_REDUCE_MEAN = 1, DSRL_REDUCE_SUM = 2 }; /* FALoss.py:32-34 */
+
+enum dsrl_precision {
+    DSRL_PREC_FP32 = 0,   /* CUDA-core FP32 FMA (reference mode always uses this) */
+    DSRL_PREC_TF32 = 1,   /* tcgen05 kind::tf32, FP32 accumulate in TMEM (position mode default) */
+    DSRL_PREC_BF16 = 2    /* tcgen05 kind::f16 with BF16 operands */
+};
+
+enum dsrl_dtype { DSRL_U8 = 0, DSRL_I32 = 1, DSRL_I64 = 2 };
+
+/* ---- diagnostics ------------------------------------------------------------------------------------- */
+int dsrl_version(void);
+const char *dsrl_last_error(void);
+/* Number of kernel launches (and memset nodes) this library has enqueued from the calling process since
+ * load; bench.py reports the delta over its timed region as `gpu_launches`. */
+uint64_t dsrl_launch_count(void);
+
+/* ---- FA loss (replaces FALoss.forward, FALoss.py:18-34, and its autograd backward) --------------------- */
+
+/* Bytes of the opaque `saved` blob forward() fills and backward() consumes, and of the scratch workspace
+ * both need.  C2 is only meaningful in position mode (reference mode requires C1 == C2, FALoss.py:20).
+ * Return 0 for an invalid / unsupported geometry. */
+size_t dsrl_fa_saved_bytes(int mode, int B, int C1, int C2, int H, int W, int k);
+size_t dsrl_fa_workspace_bytes(int mode, int B, int C1, int C2, int H, int W, int k);
+
+/* Forward.  x1, x2: (B, C, H, W) fp32.  k = subsample_factor (FALoss.py:14,23-24).
+ * loss_out: 1 float for mean/sum; (B, C, n*n) floats, n = (W/k)^2, for DSRL_REDUCE_NONE (FALoss.py:27-34).
+ * need_grad != 0 also prepares the gradient in `saved` (fused forward+backward work, one pass over the
+ * pairs).  For mean/sum the local (this rank's) sum of |.| terms is left as a double at saved[0..8) so that
+ * a multi-GPU caller can all-reduce it. */
+int dsrl_fa_forward(int mode, int precision, const float *x1, const float *x2, int B, int C1, int C2, int H,
+                    int W, int k, int reduction, int need_grad, float *loss_out, void *saved,
+                    size_t saved_bytes, void *workspace, size_t workspace_bytes, dsrl_stream_t stream);
+
+/* Backward.  grad_out: device pointer -- 1 float (mean/sum) or (B, C, n*n) floats (none).
+ * dx1 / dx2: (B, C, H, W) fp32 outputs, either may be NULL (input does not require grad). */
+int dsrl_fa_backward(int mode, int precision, const float *x1, const float *x2, const void *saved,
+                     size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C1, int C2,
+                     int H, int W, int k, int reduction, void *workspace, size_t workspace_bytes,
+                     dsrl_stream_t stream);
+
+/* ---- segmentation counts (replaces the three np.histogram passes of mIoU.update, mIoU.py:21-29, and the
+ *      two reductions of Accuracy.update, Accuracy.py:19-20) ---------------------------------------------- */
+
+/* Row layout of `counts`, one row per update:  [0,NC) area_pred  [NC,2NC) area_inter  [2NC,3NC) area_target
+ * [3NC] correct  [3NC+1] valid.  int64. */
+#define DSRL_SEG_ROW_LEN(num_classes) (3 * (num_classes) + 2)
+
+/* pred/target: num_updates consecutive maps of npix_per_update elements each (an `update()` call of the
+ * reference sees (B,H,W) = one map here).  mask: uint8/bool per pixel, or NULL to derive
+ * `target != ignore_label` in-kernel (what every reference call site passes: train_or_resume.py:479,
+ * benchmark.py:73).  counts: [num_updates][DSRL_SEG_ROW_LEN] int64, OVERWRITTEN. */
+int dsrl_seg_counts(const void *pred, int pred_dtype, const void *target, int target_dtype, const uint8_t *mask,
+                    int64_t num_updates, int64_t npix_per_update, int num_classes, int ignore_label,
+                    int64_t *counts, dsrl_stream_t stream);
+
+/* Fused argmax + counts (replaces `np.argmax(SSSR_output, axis=1)` at benchmark.py:69 /
+ * `t.argmax(SSSR_output, dim=1)` at train_or_resume.py:477 followed by the counts above).
+ * logits: (num_updates*batch, num_classes, H*W) fp32, NCHW; each update covers `batch` images of `hw` pixels.
+ * Tie-break = first maximum, NaN counts as maximum (numpy/torch argmax).  pred_out (int64, may be NULL)
+ * optionally receives the argmax map. */
+int dsrl_seg_counts_from_logits(const float *logits, const void *target, int target_dtype, const uint8_t *mask,
+                                int64_t num_updates, int64_t batch, int64_t hw, int num_classes,
+                                int ignore_label, int64_t *counts, int64_t *pred_out, dsrl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSRL_B200_H */
