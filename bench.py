@@ -1,0 +1,530 @@
+#!/usr/bin/env python
+"""bench.py -- measures the DSRL hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fa_train|seg_counts|fa_stress] [--impl reference]
+
+One JSON line on stdout (rank 0).  Workloads (BASELINE.json configs):
+
+  fa_train   configs[1]  FA loss fwd+bwd, reference semantics, batch 6 x (1, 64, 128) fp32 per GPU   [default]
+  seg_counts configs[2]  mIoU + accuracy counts, 19 classes, 500 label maps of 1024 x 2048 (int64/uint8/bool)
+  fa_stress  configs[3]  FA loss fwd+bwd, position semantics, 128 x 256 positions, C = 256, batch 8 (sharded)
+
+A "step" is one pass of the hot path over one batch of synthetic input.  `value` is measured with the inputs
+resident in HBM (CUDA events on the launching stream); `e2e` is the same metric through the public drop-in
+API (FALoss / mIoU / Accuracy) starting from pinned HOST buffers, with the H2D copies and the D2H read of the
+result inside the timed region.  The default run also measures the other workloads briefly and reports them
+under `extra` so one line carries the latency-bound FA number, the HBM-bound counts number and (when built) the
+tensor-bound position-mode number.
+
+`--impl reference` times the CPU port of the reference (oracle/) on the host cores instead -- the reference
+itself is Python and cannot travel to the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SEED = 54321  # the reference's RANDOM_SEED (settings.py:25)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------------------------
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks", 0x100: "display_clock", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.thread:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
+
+
+class L2Flusher:
+    """Evicts L2 between timed steps by overwriting a buffer larger than the 126 MB L2."""
+
+    def __init__(self, dev, mib=256):
+        self.buf = torch.empty(mib << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1)
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    return float(t.item())
+
+
+def timed_steps(step, steps, warmup, world, flush=None):
+    """Runs `warmup` + `steps` calls of step(); returns device milliseconds summed over the timed steps.
+    With `flush`, L2 is evicted before every step and each step gets its own event pair (the flush is not timed)."""
+    for _ in range(warmup):
+        if flush:
+            flush()
+        step()
+    barrier(world)
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier(world)
+        return e0.elapsed_time(e1)
+    evs = []
+    for _ in range(steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier(world)
+    return float(sum(a.elapsed_time(b) for a, b in evs))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload: fa_train (BASELINE configs[1])
+# ----------------------------------------------------------------------------------------------------------------
+FA_TRAIN_SHAPE = (6, 1, 64, 128)
+FA_K = 8
+
+
+def fa_pairs(shape, k):
+    B, C, H, W = shape
+    return B * C * (W // k) ** 4
+
+
+def fa_train_inputs():
+    from _inputs import fa_inputs
+    return fa_inputs(FA_TRAIN_SHAPE, "relu", SEED)
+
+
+def bench_fa_train(args, rank, world, dev, peaks):
+    from dualsuperreslearningforsemseg_b200.models.losses import FALoss
+    from dualsuperreslearningforsemseg_b200 import _lib
+    x1h, x2h = fa_train_inputs()
+    pairs = fa_pairs(FA_TRAIN_SHAPE, FA_K)
+    loss_fn = FALoss()
+    a = torch.from_numpy(x1h).to(dev).requires_grad_(True)
+    b = torch.from_numpy(x2h).to(dev).requires_grad_(True)
+
+    def eager_step():
+        a.grad = None
+        b.grad = None
+        loss = loss_fn(a, b)
+        loss.backward()
+        return loss
+
+    # device-resident number: the step (4 kernels) captured once in a CUDA graph and replayed -- the launch-bound
+    # inner loop is what a training step's graph would contain
+    for _ in range(3):
+        eager_step()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = eager_step()
+    launches_per_step = _lib.launch_count() - n0
+    flush = L2Flusher(dev)
+    with ClockSampler(dev.index) as clk:
+        ms = timed_steps(graph.replay, args.steps, args.warmup, world, flush=flush)
+        ms_hot = timed_steps(graph.replay, args.steps, args.warmup, world, flush=None)
+    ms = max_over_ranks(ms, world, dev)
+    ms_hot = max_over_ranks(ms_hot, world, dev)
+    loss_val = float(static_loss.item())
+
+    # end to end through the public API from pinned host buffers
+    p1 = torch.from_numpy(x1h).pin_memory()
+    p2 = torch.from_numpy(x2h).pin_memory()
+
+    def e2e_step():
+        u = p1.to(dev, non_blocking=True).requires_grad_(True)
+        v = p2.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_fn(u, v)
+        loss.backward()
+        return loss.item()          # D2H read of the step's result (synchronises)
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    step_ms = ms / args.steps
+    alg_bytes = 2 * 2 * int(np.prod(FA_TRAIN_SHAPE)) * 4          # read x1,x2 + write dx1,dx2
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    res = {
+        "metric": "fa_fwd_bwd_gpairs_per_s", "unit": "Gpairs/s",
+        "value": world * pairs / (step_ms * 1e-3) / 1e9,
+        "ms_per_step": step_ms,
+        "dtype": "f32",
+        "scaling": "weak",
+        "config": {"workload": "fa_train: BASELINE configs[1] -- FA loss fwd+bwd, reference semantics (FALoss.py:8-34), "
+                               "per-GPU batch 6 x (1,64,128) fp32, k=8 -> 393216 pairs per GPU",
+                   "shape": list(FA_TRAIN_SHAPE), "subsample_factor": FA_K, "pairs_per_gpu": pairs,
+                   "l2": "flushed before every step (256 MiB fill, outside the per-step event pair)",
+                   "launch": "CUDA graph replay of the 4-kernel step", "parallelism": f"dp{world} (batch shard, no data-path collective)",
+                   "ms_per_step_l2_warm": ms_hot / args.steps, "loss": loss_val},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic().get("fa_train"),
+                     "peak_source": peaks["source"],
+                     "note": "latency-bound micro-problem (6 CTAs of work, 0.79 MB algorithmic traffic per step): neither HBM nor "
+                             "tensor bound; see extra.seg_counts for the bandwidth-bound kernel"},
+        "e2e": {"value": world * pairs / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": "Gpairs/s",
+                "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(x1h.nbytes + x2h.nbytes), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(sum_over_ranks(launches_per_step * args.steps, world, dev)),
+        "clocks": clk.summary(),
+    }
+    return res
+
+
+def cpu_fa_train(budget_s=12.0, threads=None):
+    """The reference's CPU path, via the torch port in oracle/, on the host cores."""
+    from oracle import fa_torch_port
+    x1h, x2h = fa_train_inputs()
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    a, b = torch.from_numpy(x1h), torch.from_numpy(x2h)
+    for _ in range(3):
+        fa_torch_port.fwd_bwd(a, b, FA_K)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        fa_torch_port.fwd_bwd(a, b, FA_K)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 2000:
+            break
+    return {"value": fa_pairs(FA_TRAIN_SHAPE, FA_K) * n / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+            "ms_per_step": dt / n * 1e3,
+            "sample": f"{n} fwd+bwd calls of oracle/fa_torch_port.py (PyTorch-CPU port of FALoss.py:8-34) on the full configs[1] batch"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload: seg_counts (BASELINE configs[2])
+# ----------------------------------------------------------------------------------------------------------------
+SEG_NC, SEG_HW = 19, (1024, 2048)
+
+
+def seg_device_maps(num_maps, dev):
+    """Config 3 distribution generated on the device (10 % ignore, 70 % correct), int64 / uint8 / bool."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED)
+    shape = (num_maps, 1, *SEG_HW)
+    target = torch.randint(0, SEG_NC, shape, device=dev, generator=g, dtype=torch.uint8)
+    ign = torch.rand(shape, device=dev, generator=g) < 0.1
+    target.masked_fill_(ign, 255)
+    rnd = torch.randint(0, SEG_NC, shape, device=dev, generator=g, dtype=torch.uint8)
+    keep = torch.rand(shape, device=dev, generator=g) < 0.7
+    pred = torch.where(keep, torch.where(ign, torch.zeros_like(target), target), rnd).to(torch.int64)
+    del rnd, keep
+    mask = target != 255
+    return pred, target, mask
+
+
+def bench_seg_counts(args, rank, world, dev, peaks, num_maps=500, steps=None, warmup=None, e2e_maps=16):
+    from dualsuperreslearningforsemseg_b200.metrices import mIoU, Accuracy, _counts
+    from dualsuperreslearningforsemseg_b200 import _lib
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+    per_rank = num_maps // world + (1 if rank < num_maps % world else 0)     # shard the 500 updates across ranks
+    pred, target, mask = seg_device_maps(per_rank, dev)
+    npx = per_rank * SEG_HW[0] * SEG_HW[1]
+    total_px = num_maps * SEG_HW[0] * SEG_HW[1]
+
+    def step():
+        _counts._cache.update(key=None)
+        return _counts.counts_for_update(pred, target, mask, SEG_NC, updates_leading=True)
+
+    n0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - n0
+    with ClockSampler(dev.index) as clk:
+        ms = timed_steps(step, steps, max(3, warmup), world, flush=None)      # 10.5 GB of input >> L2
+    ms = max_over_ranks(ms, world, dev)
+    step_ms = ms / steps
+    # correctness spot check on the first map against the oracle (untimed)
+    from oracle import seg_oracle
+    rows = step().cpu().numpy()
+    ap, ai, at, c, v = seg_oracle.seg_counts(pred[0].cpu().numpy(), target[0].cpu().numpy(), mask[0].cpu().numpy(), SEG_NC)
+    assert np.array_equal(rows[0], np.concatenate([ap, ai, at, [c, v]])), "seg_counts bench output differs from the oracle"
+
+    # e2e: numpy host arrays -> mIoU.update + Accuracy.update (what the reference's loops call) -> percentages
+    e2e_maps = min(e2e_maps, per_rank)
+    hp = pred[:e2e_maps].cpu().pin_memory()
+    ht = target[:e2e_maps].cpu().pin_memory()
+    hm = mask[:e2e_maps].cpu().pin_memory()
+
+    def e2e_step():
+        m, a = mIoU(SEG_NC), Accuracy()
+        for i in range(e2e_maps):
+            dp, dt_, dm = hp[i].to(dev, non_blocking=True), ht[i].to(dev, non_blocking=True), hm[i].to(dev, non_blocking=True)
+            a.update(dp, dt_, dm)
+            m.update(dp, dt_, dm)
+        return m(), a()
+
+    for _ in range(2):
+        e2e_step()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = 3
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / e2e_steps
+    e2e_px = e2e_maps * SEG_HW[0] * SEG_HW[1]
+
+    bytes_per_px = 8 + 1 + 1
+    achieved = npx * bytes_per_px / (step_ms * 1e-3) / 1e9
+    return {
+        "metric": "seg_counts_gpx_per_s", "unit": "Gpx/s",
+        "value": total_px / (step_ms * 1e-3) / 1e9,
+        "ms_per_step": step_ms, "steps": steps, "dtype": "int64",
+        "scaling": "strong",
+        "config": {"workload": f"seg_counts: BASELINE configs[2] -- mIoU+accuracy counts, {SEG_NC} classes, {num_maps} maps of "
+                               f"{SEG_HW[0]}x{SEG_HW[1]} (pred int64, target uint8, mask bool = 10 B/px), one launch, per-update rows",
+                   "maps_per_gpu": per_rank, "l2": "inputs (10.5 GB) larger than L2, no flush",
+                   "parallelism": f"dp{world} (updates sharded; int64 rows all-gathered once per validation pass)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic().get("seg_counts"),
+                     "peak_source": peaks["source"], "algorithmic_bytes_per_launch": npx * bytes_per_px},
+        "e2e": {"value": world * e2e_px / (e2e_ms * 1e-3) / 1e9, "unit": "Gpx/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(e2e_px * bytes_per_px), "d2h_bytes_per_step": int(e2e_maps * (59 + 2) * 8),
+                "note": f"{e2e_maps} updates per step through mIoU.update + Accuracy.update from pinned host arrays (PCIe-bound)"},
+        "gpu_launches": int(sum_over_ranks(launches_per_step * steps, world, dev)),
+        "clocks": clk.summary(),
+    }
+
+
+def cpu_seg_counts(maps=2, threads=None):
+    from _inputs import cfg3_maps
+    from oracle import seg_oracle
+    data = list(cfg3_maps(maps, seed=SEED))
+    px = maps * SEG_HW[0] * SEG_HW[1]
+    t0 = time.perf_counter()
+    for p, t, m in data:
+        mo, ao = seg_oracle.MIoUOracle(SEG_NC), seg_oracle.AccuracyOracle()
+        mo.update(p, t, m)
+        ao.update(p, t, m)
+    dt = time.perf_counter() - t0
+    out = {"value": px / dt / 1e9, "unit": "Gpx/s", "cores": 1, "kind": "port",
+           "sample": f"{maps} of the 500 maps through oracle/seg_oracle.py (NumPy restatement of mIoU.py:21-35 + Accuracy.py:19-24, single thread like the reference)"}
+    threads = threads or os.cpu_count()
+    seg_oracle.seg_counts_c(*data[0], SEG_NC, threads=threads)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        for p, t, m in data:
+            seg_oracle.seg_counts_c(p, t, m, SEG_NC, threads=threads)
+    dtc = (time.perf_counter() - t0) / reps
+    out["c_openmp"] = {"value": px / dtc / 1e9, "unit": "Gpx/s", "cores": threads, "note": "oracle/seg_counts_ref.c, one fused pass"}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload: fa_stress (BASELINE configs[3]) -- position semantics, tcgen05 path
+# ----------------------------------------------------------------------------------------------------------------
+def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None):
+    from dualsuperreslearningforsemseg_b200 import _lib
+    if _lib.lib().dsrl_fa_saved_bytes(_lib.FA_POSITION, 1, 256, 256, 128, 256, 1) == 0:
+        return {"unavailable": "FA(position) tcgen05 path not built in this revision"}
+    raise NotImplementedError
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# main
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return None
+    if args.workload == "seg_counts":
+        maps = 2
+        t0 = time.perf_counter()
+        cpu = cpu_seg_counts(maps=maps)
+        res = {"metric": "seg_counts_gpx_per_s", "unit": "Gpx/s", "value": cpu["value"], "dtype": "int64",
+               "config": {"workload": "seg_counts: BASELINE configs[2] (bounded sample)"}, "scaling": "strong",
+               "ms_per_step": (time.perf_counter() - t0) * 1e3}
+    else:
+        threads = os.cpu_count()
+        from oracle import fa_torch_port
+        torch.set_num_threads(threads)
+        x1h, x2h = fa_train_inputs()
+        a, b = torch.from_numpy(x1h), torch.from_numpy(x2h)
+        for _ in range(max(3, args.warmup)):
+            fa_torch_port.fwd_bwd(a, b, FA_K)
+        steps = min(args.steps, 5000)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fa_torch_port.fwd_bwd(a, b, FA_K)
+        dt = time.perf_counter() - t0
+        pairs = fa_pairs(FA_TRAIN_SHAPE, FA_K)
+        cpu = {"value": pairs * steps / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+               "sample": f"{steps} fwd+bwd calls of oracle/fa_torch_port.py on the full configs[1] batch"}
+        res = {"metric": "fa_fwd_bwd_gpairs_per_s", "unit": "Gpairs/s", "value": cpu["value"], "dtype": "f32",
+               "config": {"workload": "fa_train: BASELINE configs[1] -- FA loss fwd+bwd, reference semantics, batch 6 x (1,64,128) fp32",
+                          "shape": list(FA_TRAIN_SHAPE), "subsample_factor": FA_K}, "scaling": "weak",
+               "ms_per_step": dt / steps * 1e3}
+    res.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                "vs_baseline": None, "data": "synthetic", "cpu_baseline": cpu,
+                "e2e": {"value": res["value"], "unit": res["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0})
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="fa_train", choices=["fa_train", "seg_counts", "fa_stress"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, local_rank, world = dist_env()
+
+    if args.impl == "reference":
+        res = run_reference_arm(args, rank, world)
+        if res is not None:
+            print(json.dumps(res), flush=True)
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    barrier(world)
+    peaks = load_peaks()
+
+    fn = {"fa_train": bench_fa_train, "seg_counts": bench_seg_counts, "fa_stress": bench_fa_stress}[args.workload]
+    res = fn(args, rank, world, dev, peaks)
+    extra = {}
+    if not args.no_extra:
+        if args.workload != "seg_counts":
+            try:
+                extra["seg_counts"] = bench_seg_counts(args, rank, world, dev, peaks, steps=5, warmup=3)
+            except Exception as e:  # noqa: BLE001 -- the primary line must still be printed
+                extra["seg_counts"] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+        if args.workload != "fa_stress":
+            try:
+                extra["fa_stress"] = bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3)
+            except Exception as e:  # noqa: BLE001
+                extra["fa_stress"] = {"error": repr(e)}
+        if rank == 0 and world == 1:
+            res["cpu_baseline"] = cpu_fa_train() if args.workload != "seg_counts" else cpu_seg_counts()
+            if "seg_counts" in extra and "error" not in extra["seg_counts"]:
+                extra["seg_counts"]["cpu_baseline"] = cpu_seg_counts()
+    if rank == 0:
+        out = {"metric": res.pop("metric"), "value": res.pop("value"), "unit": res.pop("unit"), "n_gpus": world,
+               "steps": res.pop("steps", args.steps), "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"),
+               "higher_is_better": True, "scaling": res.pop("scaling"), "vs_baseline": None, "dtype": res.pop("dtype"),
+               "data": "synthetic", **res}
+        if extra:
+            out["extra"] = extra
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -72,6 +72,8 @@ def counts_for_update(pred, target, mask, nc: int, updates_leading: bool = False
     key = _key(p, t, m) + (U, ignore_label if m is None else None)
     if _cache["key"] == key and _cache["nc"] == nc:
         return _cache["rows"]
+    if npix == 0 or U == 0:          # nothing to read: torch gives empty tensors a null data pointer
+        return torch.zeros((U, row_len(nc)), dtype=torch.int64, device=dev)
     rows = torch.empty((U, row_len(nc)), dtype=torch.int64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):

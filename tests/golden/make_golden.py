@@ -171,7 +171,7 @@ def seg_case(kind, seed, shape=(2, 37, 53), nc=19, pred_dtype=np.int64, target_d
         pred[0, 2, :4] = 100             # raw-equal out-of-range pair counts as 'correct' (Accuracy.py:19)
     elif kind == "oor_pred":
         pred[0, :3, :] = nc + 4
-        if np.issubdtype(pred_dtype, np.signedinteger):
+        if np.issubdtype(pred_dtype, np.signedinteger) and shape[0] > 1:
             pred[1, :2, :] = -1
     mask = target != 255
     if kind == "explicit_mask":

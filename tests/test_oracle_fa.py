@@ -78,3 +78,15 @@ def test_position_mode_matches_torch_autograd(name):
     np.testing.assert_allclose(loss, float(P[f"{name}/loss64"]), rtol=1e-12)
     assert relerr(d1, P[f"{name}/g1_64"]) < 1e-10
     assert relerr(d2, P[f"{name}/g2_64"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["cfg2_relu_6x1x64x128", "sum_relu_3x2x64x128", "floor_relu_1x2x70x133"])
+def test_torch_timing_port_matches_reference(name):
+    import torch
+    from oracle import fa_torch_port
+    B, C, H, W, k, seed = (int(v) for v in G[f"{name}/meta"])
+    x1, x2 = fa_inputs((B, C, H, W), str(G[f"{name}/dist"]), seed)
+    loss, d1, d2 = fa_torch_port.fwd_bwd(torch.from_numpy(x1).double(), torch.from_numpy(x2).double(), k, str(G[f"{name}/reduction"]))
+    np.testing.assert_allclose(float(loss), float(G[f"{name}/loss64"]), rtol=1e-12)
+    assert relerr(d1.numpy(), expand_pooled(G[f"{name}/g1_64"], k, H, W)) < 1e-10
+    assert relerr(d2.numpy(), expand_pooled(G[f"{name}/g2_64"], k, H, W)) < 1e-10
