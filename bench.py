@@ -194,23 +194,29 @@ def bench_fa_train(args, rank, world, dev, peaks):
     a = torch.from_numpy(x1h).to(dev).requires_grad_(True)
     b = torch.from_numpy(x2h).to(dev).requires_grad_(True)
 
-    def eager_step():
-        a.grad = None
-        b.grad = None
-        loss = loss_fn(a, b)
-        loss.backward()
-        return loss
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    plan = FAPlan(FA_TRAIN_SHAPE, subsample_factor=FA_K, device=dev)
+    a_c, b_c = a.detach(), b.detach()
+    go = torch.ones((), dtype=torch.float32, device=dev)         # upstream gradient w2 = 1.0 (settings.py:43)
 
-    # device-resident number: the step (4 kernels) captured once in a CUDA graph and replayed -- the launch-bound
-    # inner loop is what a training step's graph would contain
+    def raw_step():
+        return plan.forward_backward(a_c, b_c, go)
+
+    # device-resident number: the step's kernels (fused forward + backward) captured once in a CUDA graph and replayed
+    # -- this launch-bound inner loop is what a captured training step would contain.  Checked against autograd below.
     for _ in range(3):
-        eager_step()
+        raw_step()
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        static_loss = eager_step()
+        static_loss, sdx1, sdx2 = raw_step()
     launches_per_step = _lib.launch_count() - n0
+    graph.replay()
+    loss_ag = loss_fn(a, b)
+    loss_ag.backward()
+    torch.cuda.synchronize()
+    assert float(loss_ag) == float(static_loss) and torch.equal(a.grad, sdx1) and torch.equal(b.grad, sdx2), "graph path != autograd path"
     flush = L2Flusher(dev)
     with ClockSampler(dev.index) as clk:
         ms = timed_steps(graph.replay, args.steps, args.warmup, world, flush=flush)
@@ -254,7 +260,7 @@ def bench_fa_train(args, rank, world, dev, peaks):
                                "per-GPU batch 6 x (1,64,128) fp32, k=8 -> 393216 pairs per GPU",
                    "shape": list(FA_TRAIN_SHAPE), "subsample_factor": FA_K, "pairs_per_gpu": pairs,
                    "l2": "flushed before every step (256 MiB fill, outside the per-step event pair)",
-                   "launch": "CUDA graph replay of the 4-kernel step", "parallelism": f"dp{world} (batch shard, no data-path collective)",
+                   "launch": f"CUDA graph replay of the step's {launches_per_step} kernels (FAPlan: fused forward + backward)", "parallelism": f"dp{world} (batch shard, no data-path collective)",
                    "ms_per_step_l2_warm": ms_hot / args.steps, "loss": loss_val},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic().get("fa_train"),

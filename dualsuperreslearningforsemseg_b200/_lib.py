@@ -10,7 +10,7 @@ import os
 import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libdsrl_b200.so")
+LIB_PATH = os.environ.get("DSRL_B200_LIB") or os.path.join(PKG_DIR, "libdsrl_b200.so")
 
 OK, ERR_BAD_SHAPE, ERR_BAD_DTYPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_BAD_ARG = 0, -1, -2, -3, -4, -5
 FA_REFERENCE, FA_POSITION = 0, 1

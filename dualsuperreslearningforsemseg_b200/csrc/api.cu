@@ -52,6 +52,36 @@ int device_sm_count() {
     return g_sm_count > 0 ? g_sm_count : 148;
 }
 
+
+static std::mutex g_ticket_mu;
+static unsigned *g_ticket_pool[64] = {};
+static std::atomic<unsigned> g_ticket_next{0};
+constexpr unsigned kTicketSlots = 4096;
+
+unsigned *next_ticket_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        set_last_error("next_ticket_slot: cudaGetDevice failed");
+        return nullptr;
+    }
+    if (!g_ticket_pool[dev]) {
+        std::lock_guard<std::mutex> lk(g_ticket_mu);
+        if (!g_ticket_pool[dev]) {
+            unsigned *p = nullptr;
+            cudaError_t e = cudaMalloc(&p, kTicketSlots * sizeof(unsigned));
+            if (e == cudaSuccess) e = cudaMemset(p, 0, kTicketSlots * sizeof(unsigned));
+            if (e != cudaSuccess) {
+                set_last_error("ticket pool allocation failed (%s); if this happened inside a CUDA graph capture, run the "
+                               "call once eagerly first", cudaGetErrorString(e));
+                (void)cudaGetLastError();
+                return nullptr;
+            }
+            g_ticket_pool[dev] = p;
+        }
+    }
+    return g_ticket_pool[dev] + (g_ticket_next.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
+}
+
 }  // namespace dsrl
 
 extern "C" {

@@ -37,6 +37,15 @@ struct RefSaved {  // byte offsets into the opaque `saved` blob
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// c += sign(x - y) with sign(0) = 0 and sign(NaN) = 0, in three SASS instructions (two FSET producing 0 / -1 and
+// one IADD3): this is the inner loop of the all-pairs kernels, which are issue-bound.
+__device__ __forceinline__ void sign_acc(int &c, float x, float y) {
+    int gt, lt;
+    asm("set.gt.s32.f32 %0, %1, %2;" : "=r"(gt) : "f"(x), "f"(y));
+    asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(lt) : "f"(x), "f"(y));
+    c += lt - gt;   // gt, lt are 0 or -1
+}
+
 inline bool make_geom(int B, int C, int H, int W, int k, RefGeom &g) {
     if (B < 1 || C < 1 || H < 1 || W < 1 || k < 1) return false;
     g.B = B; g.C = C; g.H = H; g.W = W; g.k = k;
@@ -89,16 +98,18 @@ inline PairsPlan make_pairs_plan(const RefGeom &g) {
 // ---------------------------------------------------------------------------------------------------------------
 // prepare: pool, sigma/u1/v1, S
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kPowerMaxM = 32;  // short side up to which the squaring + power-iteration solver is used
 struct PrepSmem { size_t A, Wm, vec, scratch, total; int sepW; };
 inline PrepSmem make_prep_smem(const RefGeom &g, size_t limit) {
     PrepSmem s;
-    const size_t a_bytes = align_up((size_t)g.h * g.lda * 4, 16), w_bytes = align_up((size_t)g.m_pad * g.L * 4, 16);
-    const size_t tail = align_up((size_t)(g.h + g.w + g.m_pad) * 8, 16) + 40 * 8 + 16;
-    s.sepW = (a_bytes + w_bytes + tail) <= limit;
+    const size_t a_bytes = align_up((size_t)g.h * g.lda * 4, 16);
+    const size_t w_bytes = g.m <= kPowerMaxM ? align_up((size_t)2 * g.m * g.m * 4, 16) : align_up((size_t)g.m_pad * g.L * 4, 16);
+    const size_t tail = align_up((size_t)(g.h + g.w + g.m_pad + 32) * 8, 16) + 40 * 8 + 16;
+    s.sepW = g.m <= kPowerMaxM || (a_bytes + w_bytes + tail) <= limit;   // the power solver never aliases
     s.A = 0;
     s.Wm = s.sepW ? a_bytes : 0;
     s.vec = s.sepW ? a_bytes + w_bytes : (a_bytes > w_bytes ? a_bytes : w_bytes);
-    s.scratch = s.vec + align_up((size_t)(g.h + g.w + g.m_pad) * 8, 16);
+    s.scratch = s.vec + align_up((size_t)(g.h + g.w + g.m_pad + 32) * 8, 16);
     s.total = s.scratch + 40 * 8 + 16;
     return s;
 }
@@ -157,6 +168,238 @@ __device__ void jacobi_rows(float *Wm, int m, int m_pad, int L, int *flag) {
     __syncthreads();
 }
 
+
+// A group of whole warps inside a CTA that synchronises on its own named barrier (bar 0 + all threads == __syncthreads).
+struct Grp {
+    int tid, nt, bar;
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory"); }
+};
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, T *scratch /* >= 33 */, const Grp &g) {
+    const int lane = g.tid & 31, wid = g.tid >> 5, nw = g.nt >> 5;
+    v = warp_sum(v);
+    g.sync();
+    if (lane == 0) scratch[wid] = v;
+    g.sync();
+    if (wid == 0) {
+        T t = lane < nw ? scratch[lane] : T(0);
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    g.sync();
+    return scratch[32];
+}
+
+// Top singular triple of the m x L view V[i][c] = sA[i*rs + c*cs] (m <= kPowerMaxM is the short side).
+//  1) M = V V^T (fp32);  2) p squarings with trace normalisation -- M^(2^p) is numerically rank one unless the
+//  spectral gap is tiny;  3) fp64 power steps on V itself until sigma stalls (its error is second order in the
+//  vector error).  On exit xs (len m) and xl (len L) are unit vectors with V^T xs = sigma xl.
+__device__ double top_singular_power(const float *sA, int rs, int cs, int m, int L, float *M0, float *M1, double *xs,
+                                     double *xs2, double *xl, double *scratch, const Grp &grp) {
+    const int tid = grp.tid, nt = grp.nt, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    for (int o = tid; o < m * m; o += nt) {
+        const int i = o / m, j = o - i * m;
+        float s = 0.f;
+        for (int c = 0; c < L; ++c) s = fmaf(sA[i * rs + c * cs], sA[j * rs + c * cs], s);
+        M0[o] = s;
+    }
+    float *cur = M0, *nxt = M1;
+    const int p = m <= 16 ? 8 : 6;
+    for (int sq = 0; sq < p; ++sq) {
+        grp.sync();
+        float tr = 0.f;
+        for (int i = 0; i < m; ++i) tr += cur[i * m + i];
+        if (!(tr > 0.f)) break;                         // zero (or NaN) matrix: uniform exit
+        const float inv = 1.f / tr;
+        for (int o = tid; o < m * m; o += nt) {
+            const int i = o / m, j = o - i * m;
+            float s = 0.f;
+            for (int k = 0; k < m; ++k) s = fmaf(cur[i * m + k], cur[k * m + j], s);
+            nxt[o] = s * inv * inv;
+        }
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    grp.sync();
+    int best = 0;
+    for (int i = 1; i < m; ++i) if (cur[i * m + i] > cur[best * m + best]) best = i;
+    if (tid < m) xs[tid] = (double)cur[tid * m + best];
+    double sig = 0.0, sig_prev = -1.0;
+    for (int it = 0; it < 60; ++it) {
+        grp.sync();
+        double ns = 0.0;
+        for (int i = 0; i < m; ++i) ns += xs[i] * xs[i];
+        if (!(ns > 0.0)) { sig = 0.0; break; }
+        ns = 1.0 / sqrt(ns);
+        double part = 0.0;
+        for (int c = tid; c < L; c += nt) {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += (double)sA[i * rs + c * cs] * xs[i];
+            s *= ns;
+            xl[c] = s;
+            part += s * s;
+        }
+        const double nl2 = group_sum(part, scratch, grp);
+        if (!(nl2 > 0.0)) { sig = 0.0; break; }
+        const double nl = 1.0 / sqrt(nl2);
+        for (int i = wid; i < m; i += nw) {
+            double s = 0.0;
+            for (int c = lane; c < L; c += 32) s += (double)sA[i * rs + c * cs] * xl[c];
+            s = warp_sum(s);
+            if (lane == 0) xs2[i] = s * nl;
+        }
+        grp.sync();
+        double s2 = 0.0;
+        for (int i = 0; i < m; ++i) s2 += xs2[i] * xs2[i];
+        sig = sqrt(s2);
+        double *t = xs; xs = xs2; xs2 = t;
+        if (it >= 1 && fabs(sig - sig_prev) <= 1e-11 * sig) break;
+        sig_prev = sig;
+    }
+    grp.sync();
+    // final consistent pair: us = xs/|xs|, xl = V^T us, sigma = |xl|
+    double ns = 0.0;
+    for (int i = 0; i < m; ++i) ns += xs[i] * xs[i];
+    ns = ns > 0.0 ? 1.0 / sqrt(ns) : 0.0;
+    double part = 0.0;
+    for (int c = tid; c < L; c += nt) {
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) s += (double)sA[i * rs + c * cs] * xs[i];
+        s *= ns;
+        xl[c] = s;
+        part += s * s;
+    }
+    const double sigma2 = group_sum(part, scratch, grp);
+    const double sigma = sqrt(sigma2), inv = sigma > 0.0 ? 1.0 / sigma : 0.0;
+    for (int c = tid; c < L; c += nt) xl[c] *= inv;
+    grp.sync();
+    if (tid < m) xs2[tid] = xs[tid] * ns;               // unit short vector lands in xs2 ...
+    grp.sync();
+    if (tid < m) xs[tid] = xs2[tid];                    // ... and in xs (whichever buffer the caller reads)
+    grp.sync();
+    return sigma;
+}
+
+// Warp-level variant for the fused small-shape kernel (m <= 16, L <= 32): the same algorithm run by ONE warp with
+// the vectors in registers / a few shared doubles and only __syncwarp between steps.  M0 must already hold V V^T.
+// On exit xs[0..m) / xl[0..L) (shared) are the unit vectors; returns sigma.  Call from one full warp.
+// Code size matters here (the fused kernel runs once per launch on a cold instruction cache): loops are kept
+// rolled and the fp64 rsqrt lives in one non-inlined helper.
+__device__ __noinline__ double wsum_d(double v) {      // one copy of the 10-shuffle butterfly instead of one per call site
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __noinline__ double group_sum_d(double v, double *scratch, int gtid, int gnt, int bar) {
+    const Grp g{gtid, gnt, bar};
+    const int lane = gtid & 31, wid = gtid >> 5, nw = gnt >> 5;
+    v = wsum_d(v);
+    g.sync();
+    if (lane == 0) scratch[wid] = v;
+    g.sync();
+    if (wid == 0) {
+        double t = lane < nw ? scratch[lane] : 0.0;
+        t = wsum_d(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    g.sync();
+    return scratch[32];
+}
+
+__device__ __noinline__ float top_singular_warp(const float *sA, int rs, int cs, int m, int L, float *M0, float *M1,
+                                                float *xs, float *xl) {
+    // fp32 throughout: sigma only needs ~1e-6 relative (the loss tolerance is 1e-4, the reference itself is fp32) and
+    // this single-warp dependent chain is the critical path of the whole forward -- fp64 shuffles/rsqrt tripled it.
+    const int lane = threadIdx.x & 31;
+    const int qi = 32 / m, qj = 32 - qi * m, i0 = lane / m, j0 = lane - i0 * m;   // (i, j) of entry o advance by (qi, qj) per 32
+    float *cur = M0, *nxt = M1;
+#pragma unroll 1
+    for (int sq = 0; sq < 6; ++sq) {
+        float tr = lane < m ? cur[lane * m + lane] : 0.f;
+        tr = warp_sum(tr);
+        if (!(tr > 0.f)) break;
+        const float inv = __frcp_rn(tr);
+        int i = i0, j = j0;
+#pragma unroll 1
+        for (int o = lane; o < m * m; o += 32) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k + 1 < m; k += 2) {
+                s0 = fmaf(cur[i * m + k], cur[k * m + j], s0);
+                s1 = fmaf(cur[i * m + k + 1], cur[(k + 1) * m + j], s1);
+            }
+            if (m & 1) s0 = fmaf(cur[i * m + m - 1], cur[(m - 1) * m + j], s0);
+            nxt[o] = (s0 + s1) * inv * inv;
+            i += qi; j += qj;
+            if (j >= m) { j -= m; ++i; }
+        }
+        __syncwarp();
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    // start: column of the largest diagonal entry
+    float dg = lane < m ? cur[lane * m + lane] : -1.f;
+    int best = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, dg, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (od > dg || (od == dg && ob < best)) { dg = od; best = ob; }
+    }
+    float x = lane < m ? cur[lane * m + best] : 0.f;              // short vector: lane i holds xs[i]
+    // Power steps on V itself.  The stopping rule is on the VECTOR (max component change <= 1e-6): the error of
+    // sigma is second order in the vector error, so a stalled sigma says nothing about u1/v1, and the rank-one term
+    // of the gradient needs them to ~1e-5 (inputs without a spectral gap, e.g. randn, otherwise miss the tolerance).
+#pragma unroll 1
+    for (int it = 0; it < 96; ++it) {
+        float nx = warp_sum(x * x);
+        x *= nx > 0.f ? rsqrtf(nx) : 0.f;
+        if (lane < m) xs[lane] = x;
+        __syncwarp();
+        float y0 = 0.f, y1 = 0.f;                                   // long vector: lane c holds xl[c]
+        if (lane < L) {
+#pragma unroll 4
+            for (int i = 0; i + 1 < m; i += 2) { y0 = fmaf(sA[i * rs + lane * cs], xs[i], y0); y1 = fmaf(sA[(i + 1) * rs + lane * cs], xs[i + 1], y1); }
+            if (m & 1) y0 = fmaf(sA[(m - 1) * rs + lane * cs], xs[m - 1], y0);
+        }
+        float y = y0 + y1;
+        const float ny = warp_sum(y * y);
+        y *= ny > 0.f ? rsqrtf(ny) : 0.f;
+        if (lane < L) xl[lane] = y;
+        __syncwarp();
+        float z0 = 0.f, z1 = 0.f;
+        if (lane < m) {
+#pragma unroll 4
+            for (int c = 0; c + 1 < L; c += 2) { z0 = fmaf(sA[lane * rs + c * cs], xl[c], z0); z1 = fmaf(sA[lane * rs + (c + 1) * cs], xl[c + 1], z1); }
+            if (L & 1) z0 = fmaf(sA[lane * rs + (L - 1) * cs], xl[L - 1], z0);
+        }
+        const float z = z0 + z1;
+        const float s2 = warp_sum(z * z);                           // sigma^2 estimate
+        float d = fabsf(z * (s2 > 0.f ? rsqrtf(s2) : 0.f) - x);     // change of the unit short vector
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+        x = z;
+        __syncwarp();
+        if (!(d > 1e-6f)) break;                                    // also leaves on NaN
+    }
+    // consistent final pair: us = x/|x|, xl = V^T us, sigma = |xl|
+    {
+        const float nx = warp_sum(x * x);
+        x *= nx > 0.f ? rsqrtf(nx) : 0.f;
+    }
+    if (lane < m) xs[lane] = x;
+    __syncwarp();
+    float y0 = 0.f, y1 = 0.f;
+    if (lane < L) {
+#pragma unroll 4
+        for (int i = 0; i + 1 < m; i += 2) { y0 = fmaf(sA[i * rs + lane * cs], xs[i], y0); y1 = fmaf(sA[(i + 1) * rs + lane * cs], xs[i + 1], y1); }
+        if (m & 1) y0 = fmaf(sA[(m - 1) * rs + lane * cs], xs[m - 1], y0);
+    }
+    const float y = y0 + y1, s2 = warp_sum(y * y);
+    const float sigma = sqrtf(s2);
+    if (lane < L) xl[lane] = s2 > 0.f ? y / sigma : 0.f;
+    __syncwarp();
+    return sigma;
+}
+
 __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g, RefSaved so,
                                unsigned char *__restrict__ saved, PrepSmem ps) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -177,65 +420,76 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
     int *gcnt = reinterpret_cast<int *>(saved + so.cnt) + slot * g.n;
 
     // 1. pool (FALoss.py:23-24)
+    const bool small = g.m <= kPowerMaxM;
     const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     for (int cell = tid; cell < h * w; cell += nt) {
         const int py = cell / w, px = cell - py * w;
         const float v = pool_cell(x, g.W, g.k, py, px, vec4);
         gP[cell] = v;
         if (ps.sepW) sA[py * lda + px] = v;
-        if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v;
+        if (!small) { if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v; }
     }
     for (int i = tid; i < g.n; i += nt) gcnt[i] = 0;
     __syncthreads();
 
-    // 2. top singular triple: Jacobi in fp32, then one power step in fp64 (error in sigma is second order)
-    jacobi_rows(sW, g.m, g.m_pad, g.L, flag);
-    {
-        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-        for (int r = wid; r < g.m; r += nw) {
-            double s = 0.0;
-            for (int c = lane; c < g.L; c += 32) { const double t = sW[(size_t)r * g.L + c]; s += t * t; }
-            s = warp_sum(s);
-            if (lane == 0) nrm[r] = s;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int best = 0;
-            for (int r = 1; r < g.m; ++r) if (nrm[r] > nrm[best]) best = r;
-            *flag = best;
-        }
-        __syncthreads();
-    }
-    const int top = *flag;
-    const double top_inv = nrm[top] > 0.0 ? 1.0 / sqrt(nrm[top]) : 0.0;
-    // start vector: v0 (length w) if rows were rows of P, u0 (length h) if they were columns
-    double *start = g.transposed ? du : dv;
-    for (int c = tid; c < g.L; c += nt) start[c] = (double)sW[(size_t)top * g.L + c] * top_inv;
-    __syncthreads();
-    if (!ps.sepW) {  // the Jacobi work area aliased the pooled matrix: reload it from what this CTA wrote
-        for (int cell = tid; cell < h * w; cell += nt) { const int py = cell / w; sA[py * lda + (cell - py * w)] = gP[cell]; }
-        __syncthreads();
-    }
-    auto mul_A = [&]() {   // du = A dv
-        for (int y = tid; y < h; y += nt) { double s = 0.0; for (int c = 0; c < w; ++c) s += (double)sA[y * lda + c] * dv[c]; du[y] = s; }
-        __syncthreads();
-    };
-    auto mul_At = [&]() {  // dv = A^T du
-        for (int c = tid; c < w; c += nt) { double s = 0.0; for (int y = 0; y < h; ++y) s += (double)sA[y * lda + c] * du[y]; dv[c] = s; }
-        __syncthreads();
-    };
-    auto normalise = [&](double *vec, int len) -> double {
-        double s = 0.0;
-        for (int i = tid; i < len; i += nt) s += vec[i] * vec[i];
-        s = block_sum(s, scratch);
-        const double nr = sqrt(s), inv = nr > 0.0 ? 1.0 / nr : 0.0;
-        for (int i = tid; i < len; i += nt) vec[i] *= inv;
-        __syncthreads();
-        return nr;
-    };
+    // 2. top singular triple (sigma, u1, v1)
     double sigma;
-    if (!g.transposed) { mul_A(); normalise(du, h); mul_At(); sigma = normalise(dv, w); }
-    else               { mul_At(); normalise(dv, w); mul_A(); sigma = normalise(du, h); }
+    if (small) {
+        float *M0 = sW, *M1 = sW + g.m * g.m;
+        double *xs2a = nrm + g.m_pad;                               // [32] spare short vector
+        // the solver ping-pongs two short buffers; both end up holding the unit short vector
+        const Grp all{tid, nt, 0};
+        if (!g.transposed) sigma = top_singular_power(sA, lda, 1, g.m, g.L, M0, M1, du, xs2a, dv, scratch, all);
+        else               sigma = top_singular_power(sA, 1, lda, g.m, g.L, M0, M1, dv, xs2a, du, scratch, all);
+    } else {
+        // one-sided Jacobi in fp32, then one power step in fp64 (error in sigma is second order)
+        jacobi_rows(sW, g.m, g.m_pad, g.L, flag);
+        {
+            const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+            for (int r = wid; r < g.m; r += nw) {
+                double s = 0.0;
+                for (int c = lane; c < g.L; c += 32) { const double t = sW[(size_t)r * g.L + c]; s += t * t; }
+                s = warp_sum(s);
+                if (lane == 0) nrm[r] = s;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int best = 0;
+                for (int r = 1; r < g.m; ++r) if (nrm[r] > nrm[best]) best = r;
+                *flag = best;
+            }
+            __syncthreads();
+        }
+        const int top = *flag;
+        const double top_inv = nrm[top] > 0.0 ? 1.0 / sqrt(nrm[top]) : 0.0;
+        // start vector: v0 (length w) if rows were rows of P, u0 (length h) if they were columns
+        double *start = g.transposed ? du : dv;
+        for (int c = tid; c < g.L; c += nt) start[c] = (double)sW[(size_t)top * g.L + c] * top_inv;
+        __syncthreads();
+        if (!ps.sepW) {  // the Jacobi work area aliased the pooled matrix: reload it from what this CTA wrote
+            for (int cell = tid; cell < h * w; cell += nt) { const int py = cell / w; sA[py * lda + (cell - py * w)] = gP[cell]; }
+            __syncthreads();
+        }
+        auto mul_A = [&]() {   // du = A dv
+            for (int y = tid; y < h; y += nt) { double s = 0.0; for (int c = 0; c < w; ++c) s += (double)sA[y * lda + c] * dv[c]; du[y] = s; }
+            __syncthreads();
+        };
+        auto mul_At = [&]() {  // dv = A^T du
+            for (int c = tid; c < w; c += nt) { double s = 0.0; for (int y = 0; y < h; ++y) s += (double)sA[y * lda + c] * du[y]; dv[c] = s; }
+            __syncthreads();
+        };
+        auto normalise = [&](double *vec, int len) -> double {
+            double s = 0.0;
+            for (int i = tid; i < len; i += nt) s += vec[i] * vec[i];
+            s = block_sum(s, scratch);
+            const double nr = sqrt(s), inv = nr > 0.0 ? 1.0 / nr : 0.0;
+            for (int i = tid; i < len; i += nt) vec[i] *= inv;
+            __syncthreads();
+            return nr;
+        };
+        if (!g.transposed) { mul_A(); normalise(du, h); mul_At(); sigma = normalise(dv, w); }
+        else               { mul_At(); normalise(dv, w); mul_A(); sigma = normalise(du, h); }
+    }
     const float sigf = (float)sigma;
     float *gu = reinterpret_cast<float *>(saved + so.u) + slot * h;
     float *gv = reinterpret_cast<float *>(saved + so.v) + slot * w;
@@ -313,10 +567,10 @@ __global__ void __launch_bounds__(kPairsBlock) fa_ref_pairs(RefGeom g, RefSaved 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float x = xv[r];
-                c[r] += (x > y.x) - (x < y.x);
-                c[r] += (x > y.y) - (x < y.y);
-                c[r] += (x > y.z) - (x < y.z);
-                c[r] += (x > y.w) - (x < y.w);
+                sign_acc(c[r], x, y.x);
+                sign_acc(c[r], x, y.y);
+                sign_acc(c[r], x, y.z);
+                sign_acc(c[r], x, y.w);
                 if (pass == 0) { acc[r] += fabsf(x - y.x); acc[r] += fabsf(x - y.y); acc[r] += fabsf(x - y.z); acc[r] += fabsf(x - y.w); }
             }
         }
@@ -324,7 +578,7 @@ __global__ void __launch_bounds__(kPairsBlock) fa_ref_pairs(RefGeom g, RefSaved 
             const float y = sy[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                c[r] += (xv[r] > y) - (xv[r] < y);
+                sign_acc(c[r], xv[r], y);
                 if (pass == 0) acc[r] += fabsf(xv[r] - y);
             }
         }
@@ -498,6 +752,197 @@ __global__ void fa_ref_none_pairs(RefGeom g, RefSaved so, const unsigned char *_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fused small-shape forward: everything for one (b, c) in ONE CTA (the reference model's training shapes:
+// pooled map h <= 32, w <= 16, n = w*w <= 256).  Two 256-thread groups handle the two branches concurrently on
+// their own named barriers (pool -> sigma,u1,v1 -> S), then group g runs all-pairs pass g, then each group
+// produces its branch's pooled gradient.  The loss is finished by the last CTA to arrive (self-resetting
+// atomicInc ticket), so forward is a single launch with no memset and a deterministic summation order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFusedMaxW = 16, kFusedMaxH = 32, kFusedLda = kFusedMaxW + 1;
+struct FusedBranch {
+    float P[kFusedMaxH * kFusedLda];   // pooled map
+    float A[kFusedMaxH * kFusedLda];   // P / sigma
+    float M[2 * kFusedMaxW * kFusedMaxW];
+    float S[kFusedMaxW * kFusedMaxW];
+    int cnt[kFusedMaxW * kFusedMaxW];
+    float Gs[kFusedMaxW * kFusedLda];
+    float xs[32], xl[32];
+    double scratch[34];
+};
+inline bool fused_ok(const RefGeom &g) { return g.w <= kFusedMaxW && g.h <= kFusedMaxH; }
+
+__device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, int W, int k, bool vec4) {
+    float s = 0.f;
+    if (vec4) {
+#pragma unroll 1
+        for (int dy = 0; dy < k; ++dy) {
+            const float4 *r = reinterpret_cast<const float4 *>(base + (size_t)dy * W);
+#pragma unroll 2
+            for (int q = 0; q < (k >> 2); ++q) { const float4 v = __ldg(r + q); s += v.x; s += v.y; s += v.z; s += v.w; }
+        }
+    } else {
+#pragma unroll 1
+        for (int dy = 0; dy < k; ++dy)
+#pragma unroll 1
+            for (int dx = 0; dx < k; ++dx) s += __ldg(base + (size_t)dy * W + dx);
+    }
+    return s / (float)(k * k);
+}
+
+__global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g,
+                                                          RefSaved so, unsigned char *__restrict__ saved,
+                                                          double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                                          float g_scale, double loss_div, float *__restrict__ loss_out,
+                                                          int need_grad) {
+    __shared__ FusedBranch sb[2];
+    __shared__ double red[34];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, br = tid >> 8, ht = tid & 255;
+    const Grp grp{ht, 256, 1 + br};
+    FusedBranch &fb = sb[br];
+    const int bc = blockIdx.x, h = g.h, w = g.w, n = g.n, lda = kFusedLda, hw = h * w;
+    // every per-thread index decomposition is done once: ht = qw*w + rw (cell / S entry), ht + 256 = second cell
+    const int qw = ht / w, rw = ht - qw * w;
+    const int qw2 = (ht + 256) / w, rw2 = (ht + 256) - qw2 * w;
+    const bool c0 = ht < hw, c1 = ht + 256 < hw;
+    const int a0 = qw * lda + rw, a1 = qw2 * lda + rw2;           // padded smem offsets of the thread's cells
+
+#ifdef DSRL_FUSED_TIMING
+    long long *tm = reinterpret_cast<long long *>(partials + 64);
+#define TSTAMP(i) do { if (bc == 0 && tid == 0) tm[i] = clock64(); } while (0)
+#else
+#define TSTAMP(i)
+#endif
+    TSTAMP(0);
+    // 1. pool (FALoss.py:23-24)
+    const float *x = (br ? x2 : x1) + (size_t)bc * g.H * g.W;
+    const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (c0) fb.P[a0] = pool_cell_rolled(x + (size_t)qw * g.k * g.W + (size_t)rw * g.k, g.W, g.k, vec4);
+    if (c1) fb.P[a1] = pool_cell_rolled(x + (size_t)qw2 * g.k * g.W + (size_t)rw2 * g.k, g.W, g.k, vec4);
+    grp.sync();
+
+    TSTAMP(1);
+    // 2. sigma, u1, v1 (FALoss.py:10): M = V V^T by the whole group (m*m <= 256 entries), then one warp solves
+    const int rs = g.transposed ? 1 : lda, cs = g.transposed ? lda : 1, m = g.m, L = g.L;
+    if (ht < m * m) {
+        const int i = ht / m, j = ht - i * m;
+        float s = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < L; ++c) s = fmaf(fb.P[i * rs + c * cs], fb.P[j * rs + c * cs], s);
+        fb.M[ht] = s;
+    }
+    grp.sync();
+    TSTAMP(2);
+    if (ht < 32) {
+        const double sg = top_singular_warp(fb.P, rs, cs, m, L, fb.M, fb.M + m * m, fb.xs, fb.xl);
+        if (ht == 0) fb.scratch[33] = sg;
+    }
+    grp.sync();
+    TSTAMP(3);
+#ifdef DSRL_FUSED_TIMING
+    if (bc == 0 && tid == 0) { for (int q = 0; q < 10; ++q) reinterpret_cast<double *>(partials + 80)[q] = (double)fb.xs[31 - q]; }
+#endif
+    const double sigma = fb.scratch[33];
+    const float *du = g.transposed ? fb.xl : fb.xs, *dv = g.transposed ? fb.xs : fb.xl;
+    const float sigf = (float)sigma;
+
+    // 3. S = A^^T A^ (FALoss.py:10-11); sigma == 0 -> 0/0 = NaN like the reference
+    if (c0) fb.A[a0] = fb.P[a0] / sigf;
+    if (c1) fb.A[a1] = fb.P[a1] / sigf;
+    grp.sync();
+    if (ht < n) {
+        float s = 0.f;
+#pragma unroll 4
+        for (int y = 0; y < h; ++y) s = fmaf(fb.A[y * lda + qw], fb.A[y * lda + rw], s);
+        fb.S[ht] = s;
+    }
+    __syncthreads();
+
+    TSTAMP(4);
+    // 4. all pairs (FALoss.py:27-34): group `br` owns the values of branch `br` and streams the other branch
+    double local = 0.0;
+    if (ht < n && (br == 0 || need_grad)) {
+        const float *Y = sb[1 - br].S;
+        const float xv = fb.S[ht];
+        int c = 0;
+        float acc = 0.f;
+        if (br == 0) {
+#pragma unroll 2
+            for (int j = 0; j < n; j += 4) {            // n = w*w; the tail is handled below when w is odd
+                if (j + 4 > n) break;
+                const float4 y = *reinterpret_cast<const float4 *>(Y + j);
+                sign_acc(c, xv, y.x); sign_acc(c, xv, y.y); sign_acc(c, xv, y.z); sign_acc(c, xv, y.w);
+                acc += fabsf(xv - y.x); acc += fabsf(xv - y.y); acc += fabsf(xv - y.z); acc += fabsf(xv - y.w);
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < n; j += 4) {
+                if (j + 4 > n) break;
+                const float4 y = *reinterpret_cast<const float4 *>(Y + j);
+                sign_acc(c, xv, y.x); sign_acc(c, xv, y.y); sign_acc(c, xv, y.z); sign_acc(c, xv, y.w);
+            }
+        }
+#pragma unroll 1
+        for (int j = n & ~3; j < n; ++j) {
+            const float y = Y[j];
+            sign_acc(c, xv, y);
+            if (br == 0) acc += fabsf(xv - y);
+        }
+        fb.cnt[ht] = c;
+        local = (double)acc;
+    }
+    TSTAMP(5);
+    if (br == 0) {
+        const double tot = group_sum_d(local, fb.scratch, ht, 256, 1 + br);
+        if (ht == 0) {
+            partials[bc] = tot;
+            __threadfence();
+            const unsigned old = atomicInc(ticket, gridDim.x - 1);     // wraps to 0 after the last CTA: self-resetting
+            is_last = (old == gridDim.x - 1);
+        }
+    }
+
+    TSTAMP(6);
+    // 5. pooled gradient for unit upstream gradient
+    if (need_grad) {
+        grp.sync();
+        if (ht < n) fb.Gs[qw * lda + rw] = (float)(fb.cnt[ht] + fb.cnt[rw * w + qw]) * g_scale;     // G + G^T
+        grp.sync();
+        float gh0 = 0.f, gh1 = 0.f;
+        if (c0) {
+#pragma unroll 4
+            for (int xp = 0; xp < w; ++xp) gh0 = fmaf(fb.A[qw * lda + xp], fb.Gs[xp * lda + rw], gh0);
+        }
+        if (c1) {
+#pragma unroll 4
+            for (int xp = 0; xp < w; ++xp) gh1 = fmaf(fb.A[qw2 * lda + xp], fb.Gs[xp * lda + rw2], gh1);
+        }
+        double inner = (c0 ? (double)gh0 * (double)fb.P[a0] : 0.0) + (c1 ? (double)gh1 * (double)fb.P[a1] : 0.0);
+        inner = group_sum_d(inner, fb.scratch, ht, 256, 1 + br);
+        const float coef = (float)(inner / (sigma * sigma));
+        float *gdA = reinterpret_cast<float *>(saved + so.dA) + ((size_t)br * g.BC + bc) * hw;
+        if (c0) gdA[ht] = gh0 / sigf - coef * du[qw] * dv[rw];
+        if (c1) gdA[ht + 256] = gh1 / sigf - coef * du[qw2] * dv[rw2];
+    }
+
+    TSTAMP(7);
+    // 6. loss finish by the last CTA (fixed summation order -> deterministic)
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+#pragma unroll 1
+        for (int i = tid; i < (int)gridDim.x; i += 512) s += __ldcg(partials + i);
+        s = group_sum_d(s, red, tid, 512, 0);
+        if (tid == 0) {
+            *reinterpret_cast<double *>(saved) = s;
+            *loss_out = (float)(s / loss_div);
+        }
+    }
+    TSTAMP(8);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 constexpr size_t kSmemLimit = 220 * 1024;
@@ -560,6 +1005,16 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
     if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(reference): saved blob too small (%zu < %zu)", saved_bytes, so.total);
     if (ws_bytes < fa_ref_workspace_bytes(B, C, H, W, k)) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(reference): workspace too small");
     unsigned char *saved = static_cast<unsigned char *>(saved_v);
+
+    if (reduction != DSRL_REDUCE_NONE && fused_ok(g)) {
+        unsigned *ticket = next_ticket_slot();
+        if (!ticket) return DSRL_ERR_CUDA;
+        const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
+        fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
+                                                  loss_out, need_grad);
+        DSRL_LAUNCH_CHECK();
+        return DSRL_OK;
+    }
 
     PrepSmem ps = make_prep_smem(g, kSmemLimit);
     if (ps.total > kSmemLimit) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(reference): pooled map %dx%d too large for shared memory", g.h, g.w);

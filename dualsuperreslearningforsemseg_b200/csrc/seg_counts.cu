@@ -10,8 +10,10 @@
 //  * one CTA per tile of <= 65536 consecutive pixels of ONE update (per-update rows are what the reference's
 //    "mean over update() calls" needs, mIoU.py:35,40), so 500 updates cost one launch;
 //  * 128-bit streaming loads (ld.global.nc.L1::no_allocate), 4 independent vectors in flight per thread;
-//  * NO atomics in the pixel loop: every thread owns a private column of 8-bit counters in shared memory
-//    (<= 130 pixels per thread per tile, so they cannot overflow).  Two increments per pixel:
+//  * NO atomics in the pixel loop: every thread owns private 8-bit counters in shared memory (<= 130 pixels
+//    per thread per tile, so they cannot overflow), four rows packed per 32-bit word at word index
+//    (row/4)*BLOCK + tid -- the bank is the lane id, so the updates are bank-conflict free for ANY label
+//    distribution.  Two increments per pixel:
 //        row1 = mask ? 2*(pred in range ? pred : NC) + (pred == target) : dump
 //        row2 = target in range ? K2 + target : dump
 //    This is contention-free for any label distribution (a spatially coherent label map makes a warp-private
@@ -22,6 +24,12 @@
 namespace dsrl {
 namespace {
 
+#ifndef DSRL_SEG_MINB
+#define DSRL_SEG_MINB 4   /* measured on B200 (profiles/r01_seg_counts_sweep.md): 4 CTAs x 512 threads, 32 regs */
+#endif
+#ifndef DSRL_SEG_UNROLL
+#define DSRL_SEG_UNROLL 1
+#endif
 constexpr int kPxPerThread = 128;  // vector-body pixels per thread per tile (+ <= 2 head/tail) -- must stay < 254
 
 template <typename T, int N>
@@ -63,31 +71,44 @@ struct RowMap {
     int rows;   // dump + 1
 };
 
-__device__ __forceinline__ void count_pixel(uint8_t *col, int stride, const RowMap &rm, long long p, long long t, bool m) {
-    const bool eq = (p == t);
-    const bool pin = (p >= 0) && (p < rm.nc);
-    const bool tin = (t >= 0) && (t < rm.nc);
-    const int r1 = m ? (((pin ? (int)p : rm.nc) << 1) | (int)eq) : rm.dump;
-    const int r2 = tin ? rm.k2 + (int)t : rm.dump;
-    col[r1 * stride] += 1;
-    col[r2 * stride] += 1;
+template <int BLOCK>
+__device__ __forceinline__ void bump(uint8_t *mine, unsigned r) {
+    // byte (r & 3) of word (r >> 2) * BLOCK + tid
+    uint8_t *c = mine + (((r & ~3u) * BLOCK) | (r & 3u));
+    *c = (uint8_t)(*c + 1);
 }
 
-// Sums every counter row over the block's columns and adds the derived outputs to the update's global row.
 template <int BLOCK>
-__device__ __forceinline__ void flush_tile(const uint8_t *sm, int stride, int *rowsum, const RowMap &rm,
-                                           unsigned long long *out_row) {
+__device__ __forceinline__ void count_pixel(uint8_t *mine, const RowMap &rm, long long p, long long t, bool m) {
+    const bool eq = (p == t);
+    const bool pin = (unsigned long long)p < (unsigned long long)rm.nc;
+    const bool tin = (unsigned long long)t < (unsigned long long)rm.nc;
+    const unsigned r1 = m ? (((pin ? (unsigned)p : (unsigned)rm.nc) << 1) | (unsigned)eq) : (unsigned)rm.dump;
+    const unsigned r2 = tin ? (unsigned)rm.k2 + (unsigned)t : (unsigned)rm.dump;
+    bump<BLOCK>(mine, r1);
+    bump<BLOCK>(mine, r2);
+}
+
+// Sums every counter row over the block's threads and adds the derived outputs to the update's global row.
+template <int BLOCK>
+__device__ __forceinline__ void flush_tile(const uint8_t *sm, int *rowsum, const RowMap &rm, unsigned long long *out_row) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int NW = BLOCK / 32;
-    constexpr int BYTES_PER_LANE = BLOCK / 32;  // 16 (BLOCK=512), 8 (256), 4 (128)
+    const unsigned *words = reinterpret_cast<const unsigned *>(sm);
+    const int nq = (rm.rows + 3) >> 2;
     __syncthreads();
-    for (int r = wid; r < rm.rows; r += NW) {
-        const uint8_t *row = sm + (size_t)r * stride + lane * BYTES_PER_LANE;
-        int s = 0;
+    for (int q = wid; q < nq; q += NW) {
+        unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-        for (int q = 0; q < BYTES_PER_LANE / 4; ++q) s = (int)__dp4a(*reinterpret_cast<const unsigned *>(row + 4 * q), 0x01010101u, (unsigned)s);
-        s = warp_sum(s);
-        if (lane == 0) rowsum[r] = s;
+        for (int j = 0; j < BLOCK / 32; ++j) {
+            const unsigned w = words[q * BLOCK + j * 32 + lane];
+            s0 = __dp4a(w, 0x00000001u, s0);
+            s1 = __dp4a(w, 0x00000100u, s1);
+            s2 = __dp4a(w, 0x00010000u, s2);
+            s3 = __dp4a(w, 0x01000000u, s3);
+        }
+        s0 = warp_sum((int)s0); s1 = warp_sum((int)s1); s2 = warp_sum((int)s2); s3 = warp_sum((int)s3);
+        if (lane == 0) { rowsum[4 * q] = s0; rowsum[4 * q + 1] = s1; rowsum[4 * q + 2] = s2; rowsum[4 * q + 3] = s3; }
     }
     __syncthreads();
     const int nc = rm.nc;
@@ -114,12 +135,11 @@ __device__ __forceinline__ void zero_counters(uint8_t *sm, int bytes) {
 
 // ---- labels in, counts out ---------------------------------------------------------------------------------
 template <typename PT, typename TT, bool HAS_MASK, int VEC, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) seg_counts_kernel(const PT *__restrict__ pred, const TT *__restrict__ target,
+__global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? DSRL_SEG_MINB : 4) seg_counts_kernel(const PT *__restrict__ pred, const TT *__restrict__ target,
                                                            const uint8_t *__restrict__ mask, long long npix,
                                                            int nc, int ignore_label, int tiles_per_update,
                                                            unsigned long long *__restrict__ counts) {
     constexpr long long TILE = (long long)BLOCK * kPxPerThread;
-    constexpr int STRIDE = BLOCK + 16;
     extern __shared__ __align__(16) uint8_t sm[];
     const long long u = blockIdx.x / tiles_per_update;
     const int tt = blockIdx.x % tiles_per_update;
@@ -129,52 +149,54 @@ __global__ void __launch_bounds__(BLOCK) seg_counts_kernel(const PT *__restrict_
     if (lo >= hi) return;
 
     RowMap rm{nc, 2 * (nc + 1), 2 * (nc + 1) + nc, 2 * (nc + 1) + nc + 1};
-    int *rowsum = reinterpret_cast<int *>(sm + (size_t)rm.rows * STRIDE);
-    zero_counters<BLOCK>(sm, rm.rows * STRIDE);
-    uint8_t *col = sm + threadIdx.x;
+    const int counter_bytes = ((rm.rows + 3) >> 2) * BLOCK * 4;
+    int *rowsum = reinterpret_cast<int *>(sm + counter_bytes);
+    zero_counters<BLOCK>(sm, counter_bytes);
+    uint8_t *mine = sm + threadIdx.x * 4;
 
     auto one = [&](long long g) {
         const long long p = (long long)pred[g], t = (long long)target[g];
         const bool m = HAS_MASK ? (mask[g] != 0) : (t != (long long)ignore_label);
-        count_pixel(col, STRIDE, rm, p, t, m);
+        count_pixel<BLOCK>(mine, rm, p, t, m);
     };
 
     // scalar head / tail so the vector body is aligned in all three streams
     const long long lo_al = min(hi, (lo + VEC - 1) / VEC * VEC);
-    const long long nv = (hi - lo_al) / VEC;
-    const long long hi_al = lo_al + nv * VEC;
+    const int nv = (int)((hi - lo_al) / VEC);             // <= TILE / VEC: 32-bit indexing inside the tile
+    const long long hi_al = lo_al + (long long)nv * VEC;
     if (lo + threadIdx.x < lo_al) one(lo + threadIdx.x);
     if (hi_al + threadIdx.x < hi) one(hi_al + threadIdx.x);
 
-    constexpr int UNROLL = VEC >= 8 ? 1 : (VEC == 4 ? 2 : 4);  // ~64 B of loads in flight per thread
-    for (long long v0 = threadIdx.x; v0 < nv; v0 += (long long)UNROLL * BLOCK) {
+    const PT *__restrict__ pb = pred + lo_al;
+    const TT *__restrict__ tb = target + lo_al;
+    const uint8_t *__restrict__ mb = HAS_MASK ? mask + lo_al : nullptr;
+    constexpr int UNROLL = VEC >= 8 ? 1 : (VEC == 4 ? 2 : DSRL_SEG_UNROLL);  // ~64-80 B of loads in flight per thread
+    for (int v0 = threadIdx.x; v0 < nv; v0 += UNROLL * BLOCK) {
         Pack<PT, VEC> pp[UNROLL];
         Pack<TT, VEC> tp[UNROLL];
         Pack<uint8_t, VEC> mp[UNROLL];
 #pragma unroll
         for (int j = 0; j < UNROLL; ++j) {
-            const long long v = v0 + (long long)j * BLOCK;
+            const int v = v0 + j * BLOCK;
             if (v < nv) {
-                const long long g = lo_al + v * VEC;
-                pp[j] = load_pack<PT, VEC>(pred + g);
-                tp[j] = load_pack<TT, VEC>(target + g);
-                if (HAS_MASK) mp[j] = load_pack<uint8_t, VEC>(mask + g);
+                pp[j] = load_pack<PT, VEC>(pb + v * VEC);
+                tp[j] = load_pack<TT, VEC>(tb + v * VEC);
+                if (HAS_MASK) mp[j] = load_pack<uint8_t, VEC>(mb + v * VEC);
             }
         }
 #pragma unroll
         for (int j = 0; j < UNROLL; ++j) {
-            const long long v = v0 + (long long)j * BLOCK;
-            if (v < nv) {
+            if (v0 + j * BLOCK < nv) {
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
                     const long long p = (long long)pp[j].v[q], t = (long long)tp[j].v[q];
                     const bool m = HAS_MASK ? (mp[j].v[q] != 0) : (t != (long long)ignore_label);
-                    count_pixel(col, STRIDE, rm, p, t, m);
+                    count_pixel<BLOCK>(mine, rm, p, t, m);
                 }
             }
         }
     }
-    flush_tile<BLOCK>(sm, STRIDE, rowsum, rm, counts + (size_t)u * (3 * nc + 2));
+    flush_tile<BLOCK>(sm, rowsum, rm, counts + (size_t)u * (3 * nc + 2));
 }
 
 // ---- logits in (fused argmax), counts out --------------------------------------------------------------------
@@ -186,7 +208,6 @@ __global__ void __launch_bounds__(BLOCK) seg_counts_logits_kernel(const float *_
                                                                   unsigned long long *__restrict__ counts,
                                                                   long long *__restrict__ pred_out) {
     constexpr long long TILE = (long long)BLOCK * kPxPerThread;
-    constexpr int STRIDE = BLOCK + 16;
     extern __shared__ __align__(16) uint8_t sm[];
     const long long img = blockIdx.x / tiles_per_image;  // global image index = u*batch + i
     const int tt = blockIdx.x % tiles_per_image;
@@ -195,9 +216,10 @@ __global__ void __launch_bounds__(BLOCK) seg_counts_logits_kernel(const float *_
     if (lo >= hi) return;
 
     RowMap rm{nc, 2 * (nc + 1), 2 * (nc + 1) + nc, 2 * (nc + 1) + nc + 1};
-    int *rowsum = reinterpret_cast<int *>(sm + (size_t)rm.rows * STRIDE);
-    zero_counters<BLOCK>(sm, rm.rows * STRIDE);
-    uint8_t *col = sm + threadIdx.x;
+    const int counter_bytes = ((rm.rows + 3) >> 2) * BLOCK * 4;
+    int *rowsum = reinterpret_cast<int *>(sm + counter_bytes);
+    zero_counters<BLOCK>(sm, counter_bytes);
+    uint8_t *mine = sm + threadIdx.x * 4;
 
     const float *lg = logits + img * nc * hw;
     const TT *tg = target + img * hw;
@@ -233,11 +255,11 @@ __global__ void __launch_bounds__(BLOCK) seg_counts_logits_kernel(const float *_
         for (int q = 0; q < VEC; ++q) {
             const long long t = (long long)tp.v[q];
             const bool m = HAS_MASK ? (mp.v[q] != 0) : (t != (long long)ignore_label);
-            count_pixel(col, STRIDE, rm, (long long)idx[q], t, m);
+            count_pixel<BLOCK>(mine, rm, (long long)idx[q], t, m);
             if (po) po[g + q] = idx[q];
         }
     }
-    flush_tile<BLOCK>(sm, STRIDE, rowsum, rm, counts + (size_t)u * (3 * nc + 2));
+    flush_tile<BLOCK>(sm, rowsum, rm, counts + (size_t)u * (3 * nc + 2));
 }
 
 // ---- host dispatch -----------------------------------------------------------------------------------------
@@ -254,7 +276,7 @@ int launch_counts(const void *pred, const void *target, const uint8_t *mask, int
                   int nc, int ignore_label, int64_t *counts, cudaStream_t st) {
     constexpr long long TILE = (long long)BLOCK * kPxPerThread;
     const int rows = 3 * nc + 3;
-    const size_t smem = (size_t)rows * (BLOCK + 16) + (size_t)rows * sizeof(int);
+    const size_t smem = (size_t)((rows + 3) / 4) * BLOCK * 4 + (size_t)(rows + 4) * sizeof(int);
     auto kern = seg_counts_kernel<PT, TT, HAS_MASK, VEC, BLOCK>;
     int rc = prepare_smem(kern, smem);
     if (rc) return rc;
@@ -310,7 +332,7 @@ int launch_logits(const float *logits, const void *target, const uint8_t *mask, 
                   int64_t hw, int nc, int ignore_label, int64_t *counts, int64_t *pred_out, cudaStream_t st) {
     constexpr long long TILE = (long long)BLOCK * kPxPerThread;
     const int rows = 3 * nc + 3;
-    const size_t smem = (size_t)rows * (BLOCK + 16) + (size_t)rows * sizeof(int);
+    const size_t smem = (size_t)((rows + 3) / 4) * BLOCK * 4 + (size_t)(rows + 4) * sizeof(int);
     const long long tiles_per_image = (hw + TILE - 1) / TILE;
     const long long grid = tiles_per_image * batch * num_updates;
     if (grid > 0x7fffffffLL) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "seg_counts_from_logits: too many tiles (%lld)", grid);
