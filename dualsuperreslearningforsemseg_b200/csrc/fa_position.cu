@@ -1,13 +1,610 @@
-// FA loss, POSITION semantics (placeholder until the tcgen05 tile engine lands).
+// FA loss, POSITION semantics (the paper's N x N position affinity; opt-in), sm_100a.
+//
+//   F  = avgpool_k(X) viewed as (C, N), N = h*w                    (pool step as FALoss.py:23-24)
+//   Fh = F / max(||F_i||_2 over channels, 1e-12)                   per position i
+//   S  = Fh^T Fh  (N x N)                                          (the contraction of FALoss.py:11 on a (C, N) view)
+//   L  = reduce_{i,j} | S1 - S2 |_{ij},  diagonal forced to 0      (mean over B*N*N, or sum)
+//
+// The N x N affinity never exists in memory.  With Fcat = [Fh1 ; Fh2] (C1+C2 channels per position) the difference
+// is ONE contraction,  D = S1 - S2 = Fcat^T diag(+1..+1,-1..-1) Fcat,  so a 128 x 128 tile of D is accumulated
+// directly in tensor memory by tcgen05.mma (kind::tf32, the branch-2 channel chunks issued with the negate-A bit),
+// and the gradient  dL/dFcat_i = (2/Z) sum_j sign(D_ij) Fcat_j  is a second contraction whose A operand -- the sign
+// tile -- is written back into the SAME tensor-memory columns by the epilogue warps and consumed from there
+// (A-from-TMEM), like P = softmax(S) in an attention kernel.
+//
+// Kernels:
+//   fa_pos_pack     pool + per-position L2 normalise, TF32 rounding, two layouts:
+//                     Fpm (B, Npad, Kc) position-major  -> K-major operand tiles of the D contraction
+//                     Fcm (B, Kc, Npad) channel-major   -> K-major B tiles of the gradient contraction
+//   fa_pos_tiles    one CTA per (128-row tile i, channel group, sample): warp 0 = TMA producer, warp 1 = MMA issuer,
+//                   warps 2..5 = epilogue (|D| sum, sign tile, final normalisation Jacobian).  TMEM: columns
+//                   [0,256) gradient accumulator, [256,512) two D / sign tiles (double buffered).
+//   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace dsrl {
-size_t fa_pos_saved_bytes(int, int, int, int, int, int) { return 0; }
-size_t fa_pos_workspace_bytes(int, int, int, int, int, int) { return 0; }
-int fa_pos_forward(int, const float *, const float *, int, int, int, int, int, int, int, int, float *, void *, size_t, void *, size_t, cudaStream_t) {
-    DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): not built yet");
+namespace {
+
+using namespace tc;
+
+constexpr int kTile = 128;          // positions per tile (MMA M and N)
+constexpr int kChunk = 32;          // fp32 elements per 128-byte swizzle row = K extent of one operand box
+constexpr int kSlotBytes = kTile * kChunk * 4;   // 16 KB: one TMA box / one pipeline slot
+constexpr int kThreads = 192;
+constexpr int kMaxGroupCh = 256;    // gradient accumulator columns per CTA
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColD = 256;     // first column of the two D / sign tiles
+constexpr size_t kSmemBudget = 227 * 1024;
+constexpr size_t kSmemAux = 1024;   // barriers, TMEM pointer, reduction scratch
+
+struct PosGeom {
+    int B, C1, C2, H, W, k, h, w, N, Npad, C1p, C2p, Kc, G;
+    int gbeg[2], gcnt[2];   // channel range of group g on the concatenated channel axis
+    int tiles, nkc;         // Npad / 128, Kc / 32
+    int split;              // 1: 3xTF32 -- operands carried as hi + lo TF32 parts, D = hi*hi + hi*lo + lo*hi
+    int q_resident, stages;
+    size_t smem_bytes;
+};
+
+struct PosWs { size_t Fpm, Fcm, nrm, partials, total; };
+struct PosSaved { size_t dP, total; };
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, PosGeom &g) {
+    if (B < 1 || C1 < 1 || C2 < 1 || H < 1 || W < 1 || k < 1) return false;
+    g.B = B; g.C1 = C1; g.C2 = C2; g.H = H; g.W = W; g.k = k;
+    g.h = H / k; g.w = W / k;
+    if (g.h < 1 || g.w < 1) return false;
+    const long long N = (long long)g.h * g.w;
+    if (N > (1 << 20)) return false;
+    g.N = (int)N;
+    g.Npad = (int)align_up((size_t)N, kTile);
+    g.C1p = (int)align_up((size_t)C1, kChunk);
+    g.C2p = (int)align_up((size_t)C2, kChunk);
+    if (g.C1p > kMaxGroupCh || g.C2p > kMaxGroupCh) return false;
+    g.Kc = g.C1p + g.C2p;
+    if (g.Kc <= kMaxGroupCh) { g.G = 1; g.gbeg[0] = 0; g.gcnt[0] = g.Kc; g.gbeg[1] = 0; g.gcnt[1] = 0; }
+    else { g.G = 2; g.gbeg[0] = 0; g.gcnt[0] = g.C1p; g.gbeg[1] = g.C1p; g.gcnt[1] = g.C2p; }
+    g.tiles = g.Npad / kTile;
+    g.nkc = g.Kc / kChunk;
+    if ((long long)B * g.Npad > 0x7fffffffLL / 2 || (long long)B * g.Kc + kTile > 0x7fffffffLL / 2) return false;
+    const int avail = (int)((kSmemBudget - 1024 - kSmemAux) / kSlotBytes);   // 1024: alignment slack of the dynamic base
+    g.split = split ? 1 : 0;
+    const int qslots = g.nkc * (1 + g.split);
+    g.q_resident = qslots <= 8;
+    g.stages = avail - (g.q_resident ? qslots : 0);
+    if (g.stages > 12) g.stages = 12;
+    g.smem_bytes = 1024 + (size_t)((g.q_resident ? qslots : 0) + g.stages) * kSlotBytes + kSmemAux;
+    return true;
 }
-int fa_pos_backward(int, const float *, const float *, const void *, size_t, const float *, float *, float *, int, int, int, int, int, int, int, void *, size_t, cudaStream_t) {
-    DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): not built yet");
+
+inline PosWs make_ws(const PosGeom &g) {
+    PosWs w;
+    size_t off = 0;
+    w.Fpm = off;      off = align_up(off + (size_t)(1 + g.split) * g.B * g.Npad * g.Kc * 4, 1024);   // hi rows, then lo rows
+    w.Fcm = off;      off = align_up(off + ((size_t)g.B * g.Kc + kTile) * g.Npad * 4, 1024);   // + one box of slack rows
+    w.nrm = off;      off = align_up(off + (size_t)g.B * 2 * g.Npad * 4, 256);
+    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * 8, 256);
+    w.total = off;
+    return w;
 }
+
+inline PosSaved make_saved(const PosGeom &g) {
+    PosSaved s;
+    s.dP = 256;   // [0,8) double: local sum of |D|
+    s.total = s.dP + (size_t)g.B * g.Kc * g.Npad * 4;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pack: pool, normalise over channels, round to TF32, write both operand layouts
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1, const float *__restrict__ x2, PosGeom g,
+                                                  float *__restrict__ Fpm, float *__restrict__ Fcm, float *__restrict__ nrm) {
+    extern __shared__ float T[];                     // [Kc][33] pooled values of a 32-position strip
+    __shared__ float s_inv[2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, p0 = blockIdx.x * 32, p = p0 + lane;
+    const bool valid = p < g.N;
+    const int py = valid ? p / g.w : 0, px = valid ? p - py * g.w : 0;
+    const float inv_kk = 1.f / (float)(g.k * g.k);
+
+    for (int c = warp; c < g.Kc; c += 8) {
+        const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
+        float v = 0.f;
+        if (valid && cc < Cr) {
+            const float *x = (br ? x2 : x1) + (((size_t)b * Cr + cc) * g.H + (size_t)py * g.k) * g.W + (size_t)px * g.k;
+            float s = 0.f;
+            for (int dy = 0; dy < g.k; ++dy)
+                for (int dx = 0; dx < g.k; ++dx) s += __ldg(x + (size_t)dy * g.W + dx);
+            v = s * inv_kk;
+        }
+        T[c * 33 + lane] = v;
+    }
+    __syncthreads();
+    if (warp < 2) {                                   // per-position L2 norm over the channels of branch `warp`
+        const int c0 = warp ? g.C1p : 0, c1 = warp ? g.Kc : g.C1p;
+        float s = 0.f;
+        for (int c = c0; c < c1; ++c) { const float t = T[c * 33 + lane]; s = fmaf(t, t, s); }
+        const float n = sqrtf(s);
+        s_inv[warp][lane] = 1.f / fmaxf(n, 1e-12f);
+        nrm[((size_t)b * 2 + warp) * g.Npad + p] = n;
+    }
+    __syncthreads();
+    for (int c = warp; c < g.Kc; c += 8) {            // channel-major rows: 128 contiguous bytes per warp store
+        const int br = c >= g.C1p;
+        Fcm[((size_t)b * g.Kc + c) * g.Npad + p] = round_tf32(T[c * 33 + lane] * s_inv[br][lane]);
+    }
+    for (int q = warp; q < 32; q += 8) {              // position-major rows: Kc contiguous floats per position
+        float *dst = Fpm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
+        float *dst_lo = dst + (size_t)g.B * g.Npad * g.Kc;
+        for (int c = lane; c < g.Kc; c += 32) {
+            const float f = T[c * 33 + q] * s_inv[c >= g.C1p][q], hi = round_tf32(f);
+            dst[c] = hi;
+            if (g.split) dst_lo[c] = round_tf32(f - hi);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the tile engine
+// ---------------------------------------------------------------------------------------------------------------
+struct PosArgs {
+    const float *Fpm;
+    const float *nrm;
+    float *dP;
+    double *partials;
+    unsigned *ticket;
+    double *sum_out;
+    float *loss_out;
+    double loss_div;
+    float grad_scale;   // 2 / Z
+};
+
+template <bool kGrad>
+__global__ void __launch_bounds__(kThreads, 1)
+fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ CUtensorMap tm_cm, const PosGeom g, const PosArgs a) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t raw = smem_u32(smraw);
+    unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);     // 1024-byte aligned: swizzle-128B tiles
+    const int S = g.stages, split = g.split, nq = g.q_resident ? g.nkc * (1 + g.split) : 0;
+    unsigned char *qreg = sm;
+    unsigned char *ring = sm + (size_t)nq * kSlotBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kSlotBytes);
+    uint64_t *empty = full + S;
+    uint64_t *q_full = empty + S;
+    uint64_t *d_full = q_full + 1;      // [2] D tile complete in TMEM            (MMA -> epilogue)
+    uint64_t *p_full = d_full + 2;      // [2] kGrad: sign tile written (epilogue -> MMA); else: D tile drained
+    uint64_t *o_full = p_full + 2;      //     gradient accumulator complete      (MMA -> epilogue)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
+    double *red = reinterpret_cast<double *>(o_full + 2);               // [8]
+    int *flag = reinterpret_cast<int *>(red + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int itile = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
+    const int T = g.tiles, nkc = g.nkc;
+    const int j0 = kGrad ? 0 : itile;              // forward-only uses the symmetry D_ij = D_ji: tiles j >= i, weight 2
+    const int nt = T - j0;
+    const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], nbox = (gN + kTile - 1) / kTile;
+    const int row_q = b * g.Npad + itile * kTile, lo_rows = g.B * g.Npad;     // lo parts live lo_rows below the hi parts
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_pm);
+        prefetch_tmap(&tm_cm);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 128); }
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            if (nq) {
+                mbar_arrive_expect_tx(q_full, (uint32_t)nq * kSlotBytes);
+                for (int kc = 0; kc < nq; ++kc)
+                    tma_load_2d(qreg + (size_t)kc * kSlotBytes, &tm_pm, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
+            }
+            int slot = 0;
+            uint32_t ph = 0;
+            auto fill = [&](const CUtensorMap *tm, int c0, int c1) {
+                mbar_wait(&empty[slot], ph ^ 1, 1);
+                mbar_arrive_expect_tx(&full[slot], kSlotBytes);
+                tma_load_2d(ring + (size_t)slot * kSlotBytes, tm, &full[slot], c0, c1);
+                if (++slot == S) { slot = 0; ph ^= 1; }
+            };
+            auto load_k = [&](int j) {      // operand boxes of D(i, j): [Q_i chunk,] K_j chunk per 32 channels
+                const int row_k = b * g.Npad + j * kTile;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    if (!nq) {
+                        fill(&tm_pm, kc * kChunk, row_q);
+                        if (split) fill(&tm_pm, kc * kChunk, row_q + lo_rows);
+                    }
+                    fill(&tm_pm, kc * kChunk, row_k);
+                    if (split) fill(&tm_pm, kc * kChunk, row_k + lo_rows);
+                }
+            };
+            auto load_v = [&](int j) {      // B boxes of the gradient contraction: (channels x 32 positions of tile j)
+                for (int jc = 0; jc < kTile / kChunk; ++jc)
+                    for (int bx = 0; bx < nbox; ++bx) fill(&tm_cm, j * kTile + jc * kChunk, b * g.Kc + gbeg + bx * kTile);
+            };
+            if (kGrad) {
+                load_k(0);
+                for (int j = 0; j < T; ++j) {
+                    if (j + 1 < T) load_k(j + 1);
+                    load_v(j);
+                }
+            } else {
+                for (int jj = 0; jj < nt; ++jj) load_k(j0 + jj);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (one thread) =====================================
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t ph = 0;
+            const uint32_t ring_addr = smem_u32(ring), q_addr = smem_u32(qreg);
+            auto take = [&](int &s_out) -> uint32_t {
+                mbar_wait(&full[slot], ph, 2);
+                s_out = slot;
+                const uint32_t addr = ring_addr + (uint32_t)slot * kSlotBytes;
+                if (++slot == S) { slot = 0; ph ^= 1; }
+                return addr;
+            };
+            const uint32_t id_pos = idesc_tf32(kTile, kTile, false), id_neg = idesc_tf32(kTile, kTile, true);
+            auto gemm_d = [&](int jj) {     // D(i, j0+jj) -> TMEM columns kColD + (jj&1)*128
+                const int buf = jj & 1;
+                const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
+                if (!kGrad) mbar_wait(&p_full[buf], ((jj >> 1) & 1) ^ 1, 4);      // epilogue drained the tile that used this buffer
+                for (int kc = 0; kc < nkc; ++kc) {
+                    int sa = -1, sa_lo = -1, sb, sb_lo = -1;
+                    uint32_t a_addr, a_lo = 0, b_lo = 0;
+                    if (nq) {
+                        a_addr = q_addr + (uint32_t)kc * kSlotBytes;
+                        a_lo = q_addr + (uint32_t)(nkc + kc) * kSlotBytes;
+                    } else {
+                        a_addr = take(sa);
+                        if (split) a_lo = take(sa_lo);
+                    }
+                    const uint32_t b_addr = take(sb);
+                    if (split) b_lo = take(sb_lo);
+                    fence_after_sync();
+                    const uint32_t id = kc * kChunk >= g.C1p ? id_neg : id_pos;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_tf32_ss(dcol, smem_desc_sw128(a_addr + ks * 32), smem_desc_sw128(b_addr + ks * 32), id, (kc | ks) != 0);
+                    if (split) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_tf32_ss(dcol, smem_desc_sw128(a_addr + ks * 32), smem_desc_sw128(b_lo + ks * 32), id, 1);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_tf32_ss(dcol, smem_desc_sw128(a_lo + ks * 32), smem_desc_sw128(b_addr + ks * 32), id, 1);
+                    }
+                    umma_commit(&empty[sb]);
+                    if (sb_lo >= 0) umma_commit(&empty[sb_lo]);
+                    if (sa >= 0) umma_commit(&empty[sa]);
+                    if (sa_lo >= 0) umma_commit(&empty[sa_lo]);
+                }
+                umma_commit(&d_full[buf]);
+            };
+            auto gemm_g = [&](int jj) {     // O(i, :) += sign(D(i, j)) * Fcat_j   (A = sign tile in TMEM)
+                const int buf = jj & 1;
+                const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
+                mbar_wait(&p_full[buf], (jj >> 1) & 1, 5);
+                fence_after_sync();
+                for (int jc = 0; jc < kTile / kChunk; ++jc)
+                    for (int bx = 0; bx < nbox; ++bx) {
+                        int sb;
+                        const uint32_t b_addr = take(sb);
+                        fence_after_sync();
+                        const int rows = min(kTile, gN - bx * kTile);
+                        const uint32_t id = idesc_tf32(kTile, rows, false);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8),
+                                        smem_desc_sw128(b_addr + ks * 32), id, (jj | jc | ks) != 0);
+                        umma_commit(&empty[sb]);
+                    }
+            };
+            if (nq) mbar_wait(q_full, 0, 6);
+            if (kGrad) {
+                gemm_d(0);
+                for (int j = 0; j < T; ++j) {
+                    if (j + 1 < T) gemm_d(j + 1);      // keeps the tensor pipe busy while the epilogue turns D(j) into signs
+                    gemm_g(j);
+                }
+                umma_commit(o_full);
+            } else {
+                for (int jj = 0; jj < nt; ++jj) gemm_d(jj);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================== epilogue warps =====================================
+        const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        double acc = 0.0;
+        for (int jj = 0; jj < nt; ++jj) {
+            const int buf = jj & 1, j = j0 + jj;
+            mbar_wait(&d_full[buf], (jj >> 1) & 1, 3);
+            fence_after_sync();
+            const bool diag = j == itile;
+            float tsum = 0.f;
+#pragma unroll 1
+            for (int cg = 0; cg < 4; ++cg) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32);
+                tmem_ld32(taddr, v);
+                tmem_ld_wait();
+                if (diag && cg == q) {                               // S_ii = 1 in both branches: a structural tie
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = __uint_as_float(v[e]);
+                    tsum += fabsf(x);
+                    if (kGrad) v[e] = (v[e] & 0x80000000u) | (x != 0.f ? 0x3f800000u : 0u);     // sign(x) as a TF32 value
+                }
+                if (kGrad) tmem_st32(taddr, v);
+            }
+            if (kGrad) tmem_st_wait();
+            fence_before_sync();
+            mbar_arrive(&p_full[buf]);
+            acc += (double)tsum * ((kGrad || diag) ? 1.0 : 2.0);
+        }
+
+        if (kGrad) {
+            // normalisation Jacobian of the gradient accumulator, stored channel-major (coalesced along positions)
+            mbar_wait(o_full, 0, 7);
+            fence_after_sync();
+            const int row = itile * kTile + r;
+            const float *frow = a.Fpm + ((size_t)b * g.Npad + row) * g.Kc;
+            for (int br = 0; br < 2; ++br) {
+                const int cb = br ? g.C1p : 0, ce = br ? g.Kc : g.C1p;         // channel range of the branch
+                if (cb < gbeg || ce > gbeg + gN) continue;                     // not in this CTA's group
+                const float n = a.nrm[((size_t)b * 2 + br) * g.Npad + row];
+                const float sgn = br ? -a.grad_scale : a.grad_scale;           // dL/dFh2 = -2 Fh2 Sigma
+                float proj = 0.f;
+                for (int c0 = cb; c0 < ce; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
+                        proj = fmaf(f.x, __uint_as_float(v[e4 * 4 + 0]), proj);
+                        proj = fmaf(f.y, __uint_as_float(v[e4 * 4 + 1]), proj);
+                        proj = fmaf(f.z, __uint_as_float(v[e4 * 4 + 2]), proj);
+                        proj = fmaf(f.w, __uint_as_float(v[e4 * 4 + 3]), proj);
+                    }
+                }
+                const bool dead = !(n > 1e-12f);                                // F/eps branch of the clamp: no projection
+                const float scale = sgn / fmaxf(n, 1e-12f);
+                if (dead) proj = 0.f;
+                for (int c0 = cb; c0 < ce; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
+                    tmem_ld_wait();
+                    float *dst = a.dP + ((size_t)b * g.Kc + c0) * g.Npad + row;
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
+                        dst[(size_t)(e4 * 4 + 0) * g.Npad] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale;
+                        dst[(size_t)(e4 * 4 + 1) * g.Npad] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale;
+                        dst[(size_t)(e4 * 4 + 2) * g.Npad] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale;
+                        dst[(size_t)(e4 * 4 + 3) * g.Npad] = (__uint_as_float(v[e4 * 4 + 3]) - f.w * proj) * scale;
+                    }
+                }
+            }
+        }
+
+        // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
+        if (grp == 0) {
+            const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
+            double tot = warp_sum(acc);
+            if (lane == 0) red[et >> 5] = tot;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+                a.partials[(size_t)b * T + itile] = red[0] + red[1] + red[2] + red[3];
+                __threadfence();
+                const unsigned nparts = gridDim.x * gridDim.z;
+                *flag = atomicInc(a.ticket, nparts - 1) == nparts - 1;      // self-resetting
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*flag) {
+                __threadfence();
+                const int nparts = (int)(gridDim.x * gridDim.z);
+                double s = 0.0;
+                for (int i = et; i < nparts; i += 128) s += __ldcg(a.partials + i);
+                s = warp_sum(s);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (lane == 0) red[4 + (et >> 5)] = s;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const double all = red[4] + red[5] + red[6] + red[7];
+                    *a.sum_out = all;
+                    *a.loss_out = (float)(all / a.loss_div);
+                }
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward proper
+// ---------------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void fa_pos_unpool(PosGeom g, const float *__restrict__ dP, const float *__restrict__ grad_out,
+                              float *__restrict__ dx1, float *__restrict__ dx2) {
+    const float scale = __ldg(grad_out) / (float)(g.k * g.k);
+    const int wv = g.W / VEC;
+    const long long n1 = (long long)g.B * g.C1 * g.H * wv, n2 = (long long)g.B * g.C2 * g.H * wv;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += (long long)gridDim.x * blockDim.x) {
+        const int br = idx >= n1;
+        float *dx = br ? dx2 : dx1;
+        if (!dx) continue;
+        long long rr = br ? idx - n1 : idx;
+        const int Cr = br ? g.C2 : g.C1;
+        const int xv = (int)(rr % wv); rr /= wv;
+        const int y = (int)(rr % g.H); rr /= g.H;
+        const int c = (int)(rr % Cr);
+        const int b = (int)(rr / Cr);
+        const int py = y / g.k;
+        const float *src = dP + ((size_t)b * g.Kc + (br ? g.C1p : 0) + c) * g.Npad + (size_t)py * g.w;
+        float out[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            const int px = (xv * VEC + q) / g.k;
+            out[q] = (py < g.h && px < g.w) ? src[px] * scale : 0.f;
+        }
+        float *dst = dx + (((size_t)b * Cr + c) * g.H + y) * g.W + (size_t)xv * VEC;
+        if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+        else dst[0] = out[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+std::once_flag g_encode_once;
+EncodeTiledFn g_encode = nullptr;
+
+EncodeTiledFn encode_fn() {
+    std::call_once(g_encode_once, [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+        (void)cudaGetLastError();
+    });
+    return g_encode;
+}
+
+// rows x cols fp32 matrix, row-major; box = 128 rows x 32 columns, 128-byte swizzle
+int make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) DSRL_FAIL(DSRL_ERR_CUDA, "FA(position): cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)kTile};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DSRL_FAIL(DSRL_ERR_CUDA, "FA(position): cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return DSRL_OK;
+}
+
+template <typename K>
+int opt_in_smem(K kern, size_t bytes) {
+    if (bytes > 48 * 1024) DSRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DSRL_OK;
+}
+
+}  // namespace
+
+size_t fa_pos_saved_bytes(int B, int C1, int C2, int H, int W, int k) {
+    PosGeom g;
+    if (!make_geom(B, C1, C2, H, W, k, 0, g)) return 0;
+    return make_saved(g).total;
+}
+
+size_t fa_pos_workspace_bytes(int B, int C1, int C2, int H, int W, int k) {
+    PosGeom g;
+    if (!make_geom(B, C1, C2, H, W, k, 1, g)) return 0;     // sized for the 3xTF32 layout (the query has no precision)
+    return make_ws(g).total;
+}
+
+int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
+                   int need_grad, float *loss_out, void *saved_v, size_t saved_bytes, void *ws_v, size_t ws_bytes, cudaStream_t st) {
+    if (precision != DSRL_PREC_TF32 && precision != DSRL_PREC_FP32)
+        DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass) or FP32 (3xTF32 split)");
+    PosGeom g;
+    if (!make_geom(B, C1, C2, H, W, k, precision == DSRL_PREC_FP32, g))
+        DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry B=%d C=(%d,%d) H=%d W=%d k=%d (channels per branch <= 256)", B, C1, C2, H, W, k);
+    const PosWs wo = make_ws(g);
+    const PosSaved so = make_saved(g);
+    if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(position): saved blob too small (%zu < %zu)", saved_bytes, so.total);
+    if (ws_bytes < wo.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(position): workspace too small (%zu < %zu)", ws_bytes, wo.total);
+    if ((reinterpret_cast<uintptr_t>(ws_v) & 15) || (reinterpret_cast<uintptr_t>(saved_v) & 15))
+        DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(position): workspace / saved must be 16-byte aligned");
+    unsigned char *ws = static_cast<unsigned char *>(ws_v), *saved = static_cast<unsigned char *>(saved_v);
+    float *Fpm = reinterpret_cast<float *>(ws + wo.Fpm), *Fcm = reinterpret_cast<float *>(ws + wo.Fcm);
+    float *nrm = reinterpret_cast<float *>(ws + wo.nrm);
+
+    const size_t pack_smem = (size_t)g.Kc * 33 * 4;
+    int rc = opt_in_smem(fa_pos_pack, pack_smem);
+    if (rc) return rc;
+    fa_pos_pack<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, Fpm, Fcm, nrm);
+    DSRL_LAUNCH_CHECK();
+
+    CUtensorMap tm_pm, tm_cm;
+    if ((rc = make_map(&tm_pm, Fpm, (uint64_t)(1 + g.split) * B * g.Npad, (uint64_t)g.Kc))) return rc;
+    if ((rc = make_map(&tm_cm, Fcm, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad))) return rc;
+
+    unsigned *ticket = next_ticket_slot();
+    if (!ticket) return DSRL_ERR_CUDA;
+    PosArgs a;
+    a.Fpm = Fpm; a.nrm = nrm;
+    a.dP = reinterpret_cast<float *>(saved + so.dP);
+    a.partials = reinterpret_cast<double *>(ws + wo.partials);
+    a.ticket = ticket;
+    a.sum_out = reinterpret_cast<double *>(saved);
+    a.loss_out = loss_out;
+    const double Z = reduction == DSRL_REDUCE_MEAN ? (double)B * (double)g.N * (double)g.N : 1.0;
+    a.loss_div = Z;
+    a.grad_scale = (float)(2.0 / Z);
+    if (need_grad) {
+        if ((rc = opt_in_smem(fa_pos_tiles<true>, g.smem_bytes))) return rc;
+        fa_pos_tiles<true><<<dim3(g.tiles, g.G, B), kThreads, g.smem_bytes, st>>>(tm_pm, tm_cm, g, a);
+    } else {
+        if ((rc = opt_in_smem(fa_pos_tiles<false>, g.smem_bytes))) return rc;
+        fa_pos_tiles<false><<<dim3(g.tiles, 1, B), kThreads, g.smem_bytes, st>>>(tm_pm, tm_cm, g, a);
+    }
+    DSRL_LAUNCH_CHECK();
+    return DSRL_OK;
+}
+
+int fa_pos_backward(int precision, const float *, const float *, const void *saved_v, size_t saved_bytes, const float *grad_out,
+                    float *dx1, float *dx2, int B, int C1, int C2, int H, int W, int k, int, void *, size_t, cudaStream_t st) {
+    (void)precision;
+    PosGeom g;
+    if (!make_geom(B, C1, C2, H, W, k, 0, g)) DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry");
+    const PosSaved so = make_saved(g);
+    if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(position): saved blob too small");
+    const float *dP = reinterpret_cast<const float *>(static_cast<const unsigned char *>(saved_v) + so.dP);
+    const bool v4 = (W % 4 == 0) && (!dx1 || (reinterpret_cast<uintptr_t>(dx1) & 15) == 0) &&
+                    (!dx2 || (reinterpret_cast<uintptr_t>(dx2) & 15) == 0);
+    const long long total = (long long)B * (C1 + C2) * H * (W / (v4 ? 4 : 1));
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)device_sm_count() * 16);
+    if (v4) fa_pos_unpool<4><<<blocks, threads, 0, st>>>(g, dP, grad_out, dx1, dx2);
+    else fa_pos_unpool<1><<<blocks, threads, 0, st>>>(g, dP, grad_out, dx1, dx2);
+    DSRL_LAUNCH_CHECK();
+    return DSRL_OK;
+}
+
 }  // namespace dsrl

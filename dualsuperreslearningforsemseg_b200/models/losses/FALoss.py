@@ -127,6 +127,9 @@ class FALoss(torch.nn.modules.loss._Loss):
                           "BUG CHECK: Feature map inputs to FALoss.forward() must agree in B, H and W.")
         if self.reduction not in _RED:
             raise ValueError(f"{self.reduction} is not a valid value for reduction")
+        if self.affinity == 'position' and self.reduction == 'none':
+            raise _lib.DsrlError(_lib.ERR_UNSUPPORTED, "FALoss(affinity='position'): reduction='none' would materialise "
+                                                       "the N x N affinity; use 'mean' or 'sum'")
         if not (feature_map1.is_cuda and feature_map2.is_cuda):
             raise RuntimeError("FALoss (dsrl-b200) runs only on CUDA tensors: there is no CPU fallback on this path")
         if feature_map1.device != feature_map2.device:

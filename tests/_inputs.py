@@ -30,6 +30,28 @@ def pos_inputs(s1, s2, seed):
     return x1, x2
 
 
+def pos_margin_inputs(B, C1, C2, H, W, seed):
+    """Position-mode inputs whose affinity difference S1 - S2 stays away from zero everywhere off the diagonal.
+
+    Each branch has two groups of positions (different groupings per branch) with a shared base vector per group plus
+    noise; branch 1 is tight (cos ~0.95 inside a group, ~0.2 across), branch 2 loose (~0.75 / ~0.5), so S1 - S2 is
+    about +0.2, +0.45, -0.55 or -0.3.  The gradient contains sign(S1 - S2): with a margin no rounding can flip a
+    sign, and kernel-vs-oracle gradient differences measure the arithmetic rather than the discontinuity."""
+    rng = np.random.default_rng(seed)
+    N = H * W
+    pos = np.arange(N)
+
+    def branch(C, a, sigma, groups):
+        base = np.full((2, C), a, dtype=np.float64)
+        base[0, : C // 2] += 1.0
+        base[1, C // 2:] += 1.0
+        rms = np.sqrt((base ** 2).mean(axis=1))[groups]                       # (N,)
+        x = base[groups].T[None] + sigma * rms[None, None, :] * rng.standard_normal((B, C, N))
+        return x.reshape(B, C, H, W).astype(np.float32)
+
+    return branch(C1, 0.1, 0.23, (pos // 3) % 2), branch(C2, 0.4, 0.58, (pos // 5) % 2)
+
+
 def seg_case(kind, seed, shape=(2, 37, 53), nc=19, pred_dtype=np.int64, target_dtype=np.uint8):
     rng = np.random.default_rng(seed)
     target = rng.integers(0, nc, shape).astype(target_dtype)
