@@ -90,7 +90,7 @@ inline PosWs make_ws(const PosGeom &g) {
     w.Fpm = off;      off = align_up(off + (size_t)(1 + g.split) * g.B * g.Npad * g.Kc * 4, 1024);   // hi rows, then lo rows
     w.Fcm = off;      off = align_up(off + ((size_t)g.B * g.Kc + kTile) * g.Npad * 4, 1024);   // + one box of slack rows
     w.nrm = off;      off = align_up(off + (size_t)g.B * 2 * g.Npad * 4, 256);
-    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * 8, 256);
+    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * 8 + 16384, 256);   // + debug timing area
     w.total = off;
     return w;
 }
@@ -167,13 +167,22 @@ struct PosArgs {
     float grad_scale;   // 2 / Z
 };
 
-template <bool kGrad>
+#ifdef DSRL_POS_TIMING
+#define TWAIT(acc, stmt) do { const long long _t = clock64(); stmt; acc += clock64() - _t; } while (0)
+#else
+#define TWAIT(acc, stmt) do { stmt; } while (0)
+#endif
+
+// kGrad:     also accumulate the gradient contraction (otherwise loss only, tiles j >= i by symmetry)
+// kSplit:    3xTF32 -- D = hi*hi + hi*lo + lo*hi with the lo parts as extra operand boxes
+// kResident: the CTA's own operand rows Q_i stay in shared memory for all tiles (otherwise streamed with K_j)
+template <bool kGrad, bool kSplit, bool kResident>
 __global__ void __launch_bounds__(kThreads, 1)
 fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ CUtensorMap tm_cm, const PosGeom g, const PosArgs a) {
     extern __shared__ unsigned char smraw[];
     const uint32_t raw = smem_u32(smraw);
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);     // 1024-byte aligned: swizzle-128B tiles
-    const int S = g.stages, split = g.split, nq = g.q_resident ? g.nkc * (1 + g.split) : 0;
+    const int S = g.stages, nkc = g.nkc, nq = kResident ? nkc * (kSplit ? 2 : 1) : 0;
     unsigned char *qreg = sm;
     unsigned char *ring = sm + (size_t)nq * kSlotBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kSlotBytes);
@@ -188,7 +197,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int itile = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
-    const int T = g.tiles, nkc = g.nkc;
+    const int T = g.tiles;
     const int j0 = kGrad ? 0 : itile;              // forward-only uses the symmetry D_ij = D_ji: tiles j >= i, weight 2
     const int nt = T - j0;
     const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], nbox = (gN + kTile - 1) / kTile;
@@ -209,138 +218,175 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
+    // Producer and issuer walk the ring in the same order.  Both run their loops with the whole warp (uniform control
+    // flow, operands in uniform registers); one elected lane issues the TMA / MMA / commit instructions.
+    int slot = 0;
+    uint32_t ph = 0;
+#define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
+
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
-            if (nq) {
+        long long w_empty = 0;
+        const long long t_begin = clock64();
+        if (kResident) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, (uint32_t)nq * kSlotBytes);
                 for (int kc = 0; kc < nq; ++kc)
                     tma_load_2d(qreg + (size_t)kc * kSlotBytes, &tm_pm, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
             }
-            int slot = 0;
-            uint32_t ph = 0;
-            auto fill = [&](const CUtensorMap *tm, int c0, int c1) {
-                mbar_wait(&empty[slot], ph ^ 1, 1);
-                mbar_arrive_expect_tx(&full[slot], kSlotBytes);
-                tma_load_2d(ring + (size_t)slot * kSlotBytes, tm, &full[slot], c0, c1);
-                if (++slot == S) { slot = 0; ph ^= 1; }
-            };
-            auto load_k = [&](int j) {      // operand boxes of D(i, j): [Q_i chunk,] K_j chunk per 32 channels
-                const int row_k = b * g.Npad + j * kTile;
-                for (int kc = 0; kc < nkc; ++kc) {
-                    if (!nq) {
-                        fill(&tm_pm, kc * kChunk, row_q);
-                        if (split) fill(&tm_pm, kc * kChunk, row_q + lo_rows);
-                    }
-                    fill(&tm_pm, kc * kChunk, row_k);
-                    if (split) fill(&tm_pm, kc * kChunk, row_k + lo_rows);
-                }
-            };
-            auto load_v = [&](int j) {      // B boxes of the gradient contraction: (channels x 32 positions of tile j)
-                for (int jc = 0; jc < kTile / kChunk; ++jc)
-                    for (int bx = 0; bx < nbox; ++bx) fill(&tm_cm, j * kTile + jc * kChunk, b * g.Kc + gbeg + bx * kTile);
-            };
-            if (kGrad) {
-                load_k(0);
-                for (int j = 0; j < T; ++j) {
-                    if (j + 1 < T) load_k(j + 1);
-                    load_v(j);
-                }
-            } else {
-                for (int jj = 0; jj < nt; ++jj) load_k(j0 + jj);
-            }
+            __syncwarp();
         }
-        __syncwarp();
+#define RING_FILL(tm, c0, c1)                                                              \
+        do {                                                                               \
+            TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 1));                            \
+            if (elect_one()) {                                                             \
+                mbar_arrive_expect_tx(&full[slot], kSlotBytes);                            \
+                tma_load_2d(ring + (size_t)slot * kSlotBytes, tm, &full[slot], c0, c1);    \
+            }                                                                              \
+            __syncwarp();                                                                  \
+            RING_ADVANCE();                                                                \
+        } while (0)
+        // operand boxes of D(i, j): per 32 channels [Q_i hi, Q_i lo,] K_j hi [, K_j lo]
+        auto load_k = [&](int j) {
+            const int row_k = b * g.Npad + j * kTile;
+            for (int kc = 0; kc < nkc; ++kc) {
+                if (!kResident) {
+                    RING_FILL(&tm_pm, kc * kChunk, row_q);
+                    if (kSplit) RING_FILL(&tm_pm, kc * kChunk, row_q + lo_rows);
+                }
+                RING_FILL(&tm_pm, kc * kChunk, row_k);
+                if (kSplit) RING_FILL(&tm_pm, kc * kChunk, row_k + lo_rows);
+            }
+        };
+        // B boxes of the gradient contraction: (<= 128 channels) x (32 positions of tile j)
+        auto load_v = [&](int j) {
+            for (int jc = 0; jc < kTile / kChunk; ++jc)
+                for (int bx = 0; bx < nbox; ++bx) RING_FILL(&tm_cm, j * kTile + jc * kChunk, b * g.Kc + gbeg + bx * kTile);
+        };
+        if (kGrad) {
+            load_k(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) load_k(j + 1);
+                load_v(j);
+            }
+        } else {
+            for (int jj = 0; jj < nt; ++jj) load_k(j0 + jj);
+        }
+#undef RING_FILL
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
+            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            tm[0] = clock64() - t_begin; tm[1] = w_empty;
+        }
+#else
+        (void)t_begin; (void)w_empty;
+#endif
     } else if (warp == 1) {
-        // ===================================== MMA issuer (one thread) =====================================
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t ph = 0;
-            const uint32_t ring_addr = smem_u32(ring), q_addr = smem_u32(qreg);
-            auto take = [&](int &s_out) -> uint32_t {
-                mbar_wait(&full[slot], ph, 2);
-                s_out = slot;
-                const uint32_t addr = ring_addr + (uint32_t)slot * kSlotBytes;
-                if (++slot == S) { slot = 0; ph ^= 1; }
-                return addr;
-            };
-            const uint32_t id_pos = idesc_tf32(kTile, kTile, false), id_neg = idesc_tf32(kTile, kTile, true);
-            auto gemm_d = [&](int jj) {     // D(i, j0+jj) -> TMEM columns kColD + (jj&1)*128
-                const int buf = jj & 1;
-                const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
-                if (!kGrad) mbar_wait(&p_full[buf], ((jj >> 1) & 1) ^ 1, 4);      // epilogue drained the tile that used this buffer
-                for (int kc = 0; kc < nkc; ++kc) {
-                    int sa = -1, sa_lo = -1, sb, sb_lo = -1;
-                    uint32_t a_addr, a_lo = 0, b_lo = 0;
-                    if (nq) {
-                        a_addr = q_addr + (uint32_t)kc * kSlotBytes;
-                        a_lo = q_addr + (uint32_t)(nkc + kc) * kSlotBytes;
-                    } else {
-                        a_addr = take(sa);
-                        if (split) a_lo = take(sa_lo);
-                    }
-                    const uint32_t b_addr = take(sb);
-                    if (split) b_lo = take(sb_lo);
-                    fence_after_sync();
-                    const uint32_t id = kc * kChunk >= g.C1p ? id_neg : id_pos;
+        // ===================================== MMA issuer =====================================
+        long long w_full = 0, w_p = 0, w_drain = 0;
+        const long long t_begin = clock64();
+        constexpr uint64_t kSlotDesc = kSlotBytes >> 4;                 // descriptor start-address units (16 bytes)
+        const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
+        const uint32_t id_pos = idesc_tf32(kTile, kTile, false), id_neg = idesc_tf32(kTile, kTile, true);
+        const uint32_t id_last = idesc_tf32(kTile, gN - (nbox - 1) * kTile, false);     // last channel box may be narrower
+        const int kc_neg = g.C1p / kChunk;                               // first chunk of branch 2 (subtracted)
+#define RING_TAKE(desc_out, slot_out)                                                      \
+        do {                                                                               \
+            TWAIT(w_full, mbar_wait(&full[slot], ph, 2));                                  \
+            desc_out = ring_desc + (uint64_t)slot * kSlotDesc;                             \
+            slot_out = slot;                                                               \
+            RING_ADVANCE();                                                                \
+        } while (0)
+        // D(i, j0+jj) -> TMEM columns kColD + (jj&1)*128
+        auto gemm_d = [&](int jj) {
+            const int buf = jj & 1;
+            const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
+            if (!kGrad) TWAIT(w_drain, mbar_wait(&p_full[buf], ((jj >> 1) & 1) ^ 1, 4));    // epilogue drained this buffer
+            for (int kc = 0; kc < nkc; ++kc) {
+                uint64_t a_hi, a_lo = 0, b_hi, b_lo = 0;
+                int sa = 0, sal = 0, sb = 0, sbl = 0;
+                if (kResident) {
+                    a_hi = q_desc + (uint64_t)kc * kSlotDesc;
+                    a_lo = q_desc + (uint64_t)(nkc + kc) * kSlotDesc;
+                } else {
+                    RING_TAKE(a_hi, sa);
+                    if (kSplit) RING_TAKE(a_lo, sal);
+                }
+                RING_TAKE(b_hi, sb);
+                if (kSplit) RING_TAKE(b_lo, sbl);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_tf32_ss(dcol, smem_desc_sw128(a_addr + ks * 32), smem_desc_sw128(b_addr + ks * 32), id, (kc | ks) != 0);
-                    if (split) {
+                    for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(dcol, a_hi + 2 * ks, b_hi + 2 * ks, id, (kc | ks) != 0);
+                    if (kSplit) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_tf32_ss(dcol, smem_desc_sw128(a_addr + ks * 32), smem_desc_sw128(b_lo + ks * 32), id, 1);
+                        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(dcol, a_hi + 2 * ks, b_lo + 2 * ks, id, 1);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_tf32_ss(dcol, smem_desc_sw128(a_lo + ks * 32), smem_desc_sw128(b_addr + ks * 32), id, 1);
+                        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(dcol, a_lo + 2 * ks, b_hi + 2 * ks, id, 1);
                     }
                     umma_commit(&empty[sb]);
-                    if (sb_lo >= 0) umma_commit(&empty[sb_lo]);
-                    if (sa >= 0) umma_commit(&empty[sa]);
-                    if (sa_lo >= 0) umma_commit(&empty[sa_lo]);
+                    if (kSplit) umma_commit(&empty[sbl]);
+                    if (!kResident) {
+                        umma_commit(&empty[sa]);
+                        if (kSplit) umma_commit(&empty[sal]);
+                    }
+                    if (kc == nkc - 1) umma_commit(&d_full[buf]);
                 }
-                umma_commit(&d_full[buf]);
-            };
-            auto gemm_g = [&](int jj) {     // O(i, :) += sign(D(i, j)) * Fcat_j   (A = sign tile in TMEM)
-                const int buf = jj & 1;
-                const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
-                mbar_wait(&p_full[buf], (jj >> 1) & 1, 5);
-                fence_after_sync();
-                for (int jc = 0; jc < kTile / kChunk; ++jc)
-                    for (int bx = 0; bx < nbox; ++bx) {
-                        int sb;
-                        const uint32_t b_addr = take(sb);
-                        fence_after_sync();
-                        const int rows = min(kTile, gN - bx * kTile);
-                        const uint32_t id = idesc_tf32(kTile, rows, false);
+                __syncwarp();
+            }
+        };
+        // O(i, :) += sign(D(i, j)) * Fcat_j     (A = the sign tile the epilogue left in the D columns)
+        auto gemm_g = [&](int jj, bool last) {
+            const int buf = jj & 1;
+            const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
+            TWAIT(w_p, mbar_wait(&p_full[buf], (jj >> 1) & 1, 5));
+            for (int jc = 0; jc < kTile / kChunk; ++jc)
+                for (int bx = 0; bx < nbox; ++bx) {
+                    uint64_t bd;
+                    int sb;
+                    RING_TAKE(bd, sb);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t id = bx == nbox - 1 ? id_last : id_pos;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8),
-                                        smem_desc_sw128(b_addr + ks * 32), id, (jj | jc | ks) != 0);
+                            mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8), bd + 2 * ks, id, (jj | jc | ks) != 0);
                         umma_commit(&empty[sb]);
+                        if (last && jc == kTile / kChunk - 1 && bx == nbox - 1) umma_commit(o_full);
                     }
-            };
-            if (nq) mbar_wait(q_full, 0, 6);
-            if (kGrad) {
-                gemm_d(0);
-                for (int j = 0; j < T; ++j) {
-                    if (j + 1 < T) gemm_d(j + 1);      // keeps the tensor pipe busy while the epilogue turns D(j) into signs
-                    gemm_g(j);
+                    __syncwarp();
                 }
-                umma_commit(o_full);
-            } else {
-                for (int jj = 0; jj < nt; ++jj) gemm_d(jj);
+        };
+        if (kResident) mbar_wait(q_full, 0, 6);
+        if (kGrad) {
+            gemm_d(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) gemm_d(j + 1);      // keeps the tensor pipe busy while the epilogue turns D(j) into signs
+                gemm_g(j, j == T - 1);
             }
+        } else {
+            for (int jj = 0; jj < nt; ++jj) gemm_d(jj);
         }
-        __syncwarp();
+#undef RING_TAKE
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
+            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            tm[2] = clock64() - t_begin; tm[3] = w_full; tm[4] = w_p; tm[5] = w_drain;
+        }
+#else
+        (void)t_begin; (void)w_full; (void)w_p; (void)w_drain;
+#endif
     } else {
         // ===================================== epilogue warps =====================================
         const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         double acc = 0.0;
+        long long w_d = 0;
+        const long long t_begin = clock64();
         for (int jj = 0; jj < nt; ++jj) {
             const int buf = jj & 1, j = j0 + jj;
-            mbar_wait(&d_full[buf], (jj >> 1) & 1, 3);
+            TWAIT(w_d, mbar_wait(&d_full[buf], (jj >> 1) & 1, 3));
             fence_after_sync();
             const bool diag = j == itile;
             float tsum = 0.f;
@@ -367,6 +413,14 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             mbar_arrive(&p_full[buf]);
             acc += (double)tsum * ((kGrad || diag) ? 1.0 : 2.0);
         }
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            tm[6] = clock64() - t_begin; tm[7] = w_d;
+        }
+#else
+        (void)t_begin; (void)w_d;
+#endif
 
         if (kGrad) {
             // normalisation Jacobian of the gradient accumulator, stored channel-major (coalesced along positions)
@@ -443,6 +497,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             }
         }
     }
+#undef RING_ADVANCE
 
     fence_before_sync();
     __syncthreads();
@@ -577,13 +632,24 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)B * (double)g.N * (double)g.N : 1.0;
     a.loss_div = Z;
     a.grad_scale = (float)(2.0 / Z);
-    if (need_grad) {
-        if ((rc = opt_in_smem(fa_pos_tiles<true>, g.smem_bytes))) return rc;
-        fa_pos_tiles<true><<<dim3(g.tiles, g.G, B), kThreads, g.smem_bytes, st>>>(tm_pm, tm_cm, g, a);
-    } else {
-        if ((rc = opt_in_smem(fa_pos_tiles<false>, g.smem_bytes))) return rc;
-        fa_pos_tiles<false><<<dim3(g.tiles, 1, B), kThreads, g.smem_bytes, st>>>(tm_pm, tm_cm, g, a);
+    const dim3 grid(g.tiles, need_grad ? g.G : 1, B);
+#define LAUNCH_TILES(GR, SP, RS)                                                                          \
+    do {                                                                                                  \
+        if ((rc = opt_in_smem(fa_pos_tiles<GR, SP, RS>, g.smem_bytes))) return rc;                        \
+        fa_pos_tiles<GR, SP, RS><<<grid, kThreads, g.smem_bytes, st>>>(tm_pm, tm_cm, g, a);               \
+    } while (0)
+    const int variant = (need_grad ? 4 : 0) | (g.split ? 2 : 0) | (g.q_resident ? 1 : 0);
+    switch (variant) {
+        case 0: LAUNCH_TILES(false, false, false); break;
+        case 1: LAUNCH_TILES(false, false, true); break;
+        case 2: LAUNCH_TILES(false, true, false); break;
+        case 3: LAUNCH_TILES(false, true, true); break;
+        case 4: LAUNCH_TILES(true, false, false); break;
+        case 5: LAUNCH_TILES(true, false, true); break;
+        case 6: LAUNCH_TILES(true, true, false); break;
+        default: LAUNCH_TILES(true, true, true); break;
     }
+#undef LAUNCH_TILES
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
 }
