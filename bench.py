@@ -5,9 +5,11 @@
 
 One JSON line on stdout (rank 0).  Workloads (BASELINE.json configs):
 
-  fa_train   configs[1]  FA loss fwd+bwd, reference semantics, batch 6 x (1, 64, 128) fp32 per GPU   [default]
+  fa_stress  configs[3]  FA loss fwd+bwd, position semantics, 128 x 256 positions, C = 256, batch 8 (sharded)   [default:
+                         the configuration the metric's "tensor-pipe % of peak" is quoted on and the one BASELINE.json
+                         shards over 1/2/4/8 GPUs]
+  fa_train   configs[1]  FA loss fwd+bwd, reference semantics, batch 6 x (1, 64, 128) fp32 per GPU
   seg_counts configs[2]  mIoU + accuracy counts, 19 classes, 500 label maps of 1024 x 2048 (int64/uint8/bool)
-  fa_stress  configs[3]  FA loss fwd+bwd, position semantics, 128 x 256 positions, C = 256, batch 8 (sharded)
 
 A "step" is one pass of the hot path over one batch of synthetic input.  `value` is measured with the inputs
 resident in HBM (CUDA events on the launching stream); `e2e` is the same metric through the public drop-in
@@ -421,21 +423,170 @@ def cpu_seg_counts(maps=2, threads=None):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# workload: fa_stress (BASELINE configs[3]) -- position semantics, tcgen05 path
+# workload: fa_stress (BASELINE configs[3]) -- position semantics, tcgen05 tile engine
 # ----------------------------------------------------------------------------------------------------------------
-def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None):
+STRESS_B, STRESS_HW, STRESS_K = 8, (128, 256), 1      # "128x256 feature positions ... batch 8, sharded over 1/2/4/8 B200"
+STRESS_C = 256                                        # channels per branch (decoder width, DSRL.py:115)
+
+
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 GEMM, 8192^3, best of 10 -- the same recipe MEASURED_PEAKS.json used for bf16 (it has no TF32 entry)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        x = torch.randn((n, n), device=dev)
+        y = torch.randn((n, n), device=dev)
+        for _ in range(3):
+            x @ y
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            x @ y
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def stress_inputs(b_local, C, dev, seed):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    shape = (b_local, C, *STRESS_HW)
+    return (torch.relu(torch.randn(shape, device=dev, generator=g)), torch.relu(torch.randn(shape, device=dev, generator=g)))
+
+
+def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=None, precision=None, light=False):
     from dualsuperreslearningforsemseg_b200 import _lib
-    if _lib.lib().dsrl_fa_saved_bytes(_lib.FA_POSITION, 1, 256, 256, 128, 256, 1) == 0:
-        return {"unavailable": "FA(position) tcgen05 path not built in this revision"}
-    raise NotImplementedError
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    from dualsuperreslearningforsemseg_b200.models.losses import FALoss
+    from dualsuperreslearningforsemseg_b200.distributed import shard_slice
+    steps = steps or args.steps
+    warmup = max(3, warmup or args.warmup)
+    C = C or STRESS_C
+    sl = shard_slice(STRESS_B, rank, world)                      # batch shard: samples are independent (SURVEY 8e)
+    b_local = sl.stop - sl.start
+    if b_local == 0:
+        raise SystemExit("fa_stress needs at least one sample per rank (--gpus <= 8)")
+    H, W = STRESS_HW
+    N = H * W
+    x1, x2 = stress_inputs(b_local, C, dev, SEED + rank)
+    plan = FAPlan((b_local, C, H, W), subsample_factor=STRESS_K, affinity="position", precision=precision, device=dev)
+    go = torch.ones((), dtype=torch.float32, device=dev)
+
+    def step():
+        return plan.forward_backward(x1, x2, go)
+
+    n0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - n0
+    # L2: one step streams 2 x 268 MB of features per 128-row tile pass (>> 126 MB L2) and ends by writing 0.5 GB of
+    # gradients, so no step starts with a warm L2; no explicit flush.
+    with ClockSampler(dev.index) as clk:
+        ms = timed_steps(step, steps, warmup, world, flush=None)
+    ms = max_over_ranks(ms, world, dev)
+    step_ms = ms / steps
+    loss_local = float(plan.loss.item())
+    pairs_total = STRESS_B * N * N
+    alg_flops_rank = 12.0 * b_local * C * N * N                   # SURVEY 8d: fwd 4CN^2 + recompute 4CN^2 + two gradient GEMMs 4CN^2
+    kc = 2 * ((C + 31) // 32 * 32)
+    exec_flops_rank = (2.0 * kc * (2 if kc > 256 else 1) + 2.0 * kc) * b_local * N * N   # D (twice when two channel groups) + gradient
+    achieved = alg_flops_rank / (step_ms * 1e-3) / 1e12
+
+    res = {
+        "metric": "fa_fwd_bwd_gpairs_per_s", "unit": "Gpairs/s",
+        "value": pairs_total / (step_ms * 1e-3) / 1e9,
+        "ms_per_step": step_ms, "steps": steps, "dtype": "tf32" if precision in (None, "tf32") else "3xtf32",
+        "scaling": "strong",
+        "config": {"workload": f"fa_stress: BASELINE configs[3] -- FA loss fwd+bwd, position semantics (N x N affinity never materialised), "
+                               f"{H}x{W} positions (N={N}), batch {STRESS_B} sharded over {world} GPU(s), C={C} per branch, subsample_factor={STRESS_K}",
+                   "shape_per_gpu": [b_local, C, H, W], "pairs_total": pairs_total,
+                   "precision": "one tcgen05 kind::tf32 pass, FP32 accumulate in TMEM" if precision in (None, "tf32") else "3xTF32 split",
+                   "l2": "working set per step (1.6 GB per sample) larger than L2, no flush",
+                   "parallelism": f"dp{world} (batch shard, no data-path collective; scalar loss all-reduced for reporting only)",
+                   "loss_rank0": loss_local},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic().get("fa_stress"),
+                     "peak_source": peaks["source"] + " dense bf16 burst; the kernel runs kind::tf32, whose hardware rate is half of bf16",
+                     "algorithmic_flops_per_step_per_gpu": alg_flops_rank, "executed_tensor_flops_per_step_per_gpu": exec_flops_rank,
+                     "executed_tflops": exec_flops_rank / (step_ms * 1e-3) / 1e12,
+                     "kernel": "fa_pos_tiles (timed together with fa_pos_pack + fa_pos_unpool: one step = 3 launches)"},
+        "gpu_launches": int(sum_over_ranks(launches_per_step * steps, world, dev)),
+        "clocks": clk.summary(),
+    }
+    if not light:
+        tf32_peak = measure_tf32_peak(dev)
+        res["roofline"]["tf32_peak_measured"] = tf32_peak
+        res["roofline"]["frac_of_tf32_peak"] = achieved / tf32_peak
+        res["roofline"]["executed_frac_of_tf32_peak"] = res["roofline"]["executed_tflops"] / tf32_peak
+
+    # end to end through the drop-in FALoss from pinned host buffers (H2D of both feature maps + D2H of the loss)
+    loss_fn = FALoss(subsample_factor=STRESS_K, affinity="position", precision=precision)
+    p1, p2 = x1.cpu().pin_memory(), x2.cpu().pin_memory()
+
+    def e2e_step():
+        u = p1.to(dev, non_blocking=True).requires_grad_(True)
+        v = p2.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_fn(u, v)
+        loss.backward()
+        return loss.item()
+
+    e2e_steps = 2 if light else max(2, min(steps, 5))
+    for _ in range(2):
+        e2e_step()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / e2e_steps
+    res["e2e"] = {"value": pairs_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
+                  "h2d_bytes_per_step": int(p1.numel() * 4 + p2.numel() * 4), "d2h_bytes_per_step": 4,
+                  "note": "FALoss(affinity='position') forward + backward on tensors copied from pinned host memory each step; PCIe-bound"}
+    del p1, p2
+    return res
+
+
+def cpu_fa_stress(budget_s=15.0, threads=None, C=None, rows=256):
+    """Bounded sample of configs[3] on the host: PyTorch-CPU fp32 port, a block of `rows` affinity rows of one sample."""
+    from oracle import fa_position_torch_port as tp
+    C = C or STRESS_C
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    g = torch.Generator()
+    g.manual_seed(SEED)
+    x1 = torch.relu(torch.randn((1, C, *STRESS_HW), generator=g))
+    x2 = torch.relu(torch.randn((1, C, *STRESS_HW), generator=g))
+    N = STRESS_HW[0] * STRESS_HW[1]
+    tp.fwd_bwd_rows(x1, x2, STRESS_K, 0, rows)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        r0 = (n * rows) % N
+        tp.fwd_bwd_rows(x1, x2, STRESS_K, r0, r0 + rows)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 200:
+            break
+    return {"value": rows * N * n / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port", "ms_per_step": dt / n * 1e3,
+            "sample": f"{n} fwd+bwd calls of oracle/fa_position_torch_port.py (PyTorch-CPU fp32: normalize, Gram matmul, l1_loss, autograd), "
+                      f"each over a block of {rows} of the {N} affinity rows of one configs[3] sample (C={C}); pairs = rows x N per call"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # main
 # ----------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the CPU port of the reference path for the same workload, on the host cores, rank 0 only.
+    Each step is a bounded sample of the workload (stated in cpu_baseline.sample)."""
     if rank != 0:
         return None
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
     if args.workload == "seg_counts":
         maps = 2
         t0 = time.perf_counter()
@@ -443,10 +594,8 @@ def run_reference_arm(args, rank, world):
         res = {"metric": "seg_counts_gpx_per_s", "unit": "Gpx/s", "value": cpu["value"], "dtype": "int64",
                "config": {"workload": "seg_counts: BASELINE configs[2] (bounded sample)"}, "scaling": "strong",
                "ms_per_step": (time.perf_counter() - t0) * 1e3}
-    else:
-        threads = os.cpu_count()
+    elif args.workload == "fa_train":
         from oracle import fa_torch_port
-        torch.set_num_threads(threads)
         x1h, x2h = fa_train_inputs()
         a, b = torch.from_numpy(x1h), torch.from_numpy(x2h)
         for _ in range(max(3, args.warmup)):
@@ -463,6 +612,30 @@ def run_reference_arm(args, rank, world):
                "config": {"workload": "fa_train: BASELINE configs[1] -- FA loss fwd+bwd, reference semantics, batch 6 x (1,64,128) fp32",
                           "shape": list(FA_TRAIN_SHAPE), "subsample_factor": FA_K}, "scaling": "weak",
                "ms_per_step": dt / steps * 1e3}
+    else:
+        from oracle import fa_position_torch_port as tp
+        rows = 256
+        H, W = STRESS_HW
+        N = H * W
+        g = torch.Generator()
+        g.manual_seed(SEED)
+        x1 = torch.relu(torch.randn((1, STRESS_C, H, W), generator=g))
+        x2 = torch.relu(torch.randn((1, STRESS_C, H, W), generator=g))
+        for _ in range(min(3, max(1, args.warmup))):
+            tp.fwd_bwd_rows(x1, x2, STRESS_K, 0, rows)
+        steps = min(args.steps, 100)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            r0 = (i * rows) % N
+            tp.fwd_bwd_rows(x1, x2, STRESS_K, r0, r0 + rows)
+        dt = time.perf_counter() - t0
+        cpu = {"value": rows * N * steps / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+               "sample": f"{steps} steps, each fwd+bwd of oracle/fa_position_torch_port.py (PyTorch-CPU fp32) over a block of {rows} of the {N} "
+                         f"affinity rows of one configs[3] sample (C={STRESS_C}); pairs = rows x N per step"}
+        res = {"metric": "fa_fwd_bwd_gpairs_per_s", "unit": "Gpairs/s", "value": cpu["value"], "dtype": "f32",
+               "config": {"workload": f"fa_stress: BASELINE configs[3] -- FA loss fwd+bwd, position semantics, {H}x{W} positions, batch {STRESS_B}, "
+                                      f"C={STRESS_C} per branch (bounded sample: {rows}-row blocks of one sample)"},
+               "scaling": "strong", "ms_per_step": dt / steps * 1e3}
     res.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                 "vs_baseline": None, "data": "synthetic", "cpu_baseline": cpu,
                 "e2e": {"value": res["value"], "unit": res["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -473,10 +646,10 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fa_train", choices=["fa_train", "seg_counts", "fa_stress"])
+    ap.add_argument("--workload", default="fa_stress", choices=["fa_train", "seg_counts", "fa_stress"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -502,23 +675,30 @@ def main():
 
     fn = {"fa_train": bench_fa_train, "seg_counts": bench_seg_counts, "fa_stress": bench_fa_stress}[args.workload]
     res = fn(args, rank, world, dev, peaks)
+    torch.cuda.empty_cache()
     extra = {}
     if not args.no_extra:
-        if args.workload != "seg_counts":
+        def attempt(name, thunk):
             try:
-                extra["seg_counts"] = bench_seg_counts(args, rank, world, dev, peaks, steps=5, warmup=3)
+                extra[name] = thunk()
             except Exception as e:  # noqa: BLE001 -- the primary line must still be printed
-                extra["seg_counts"] = {"error": repr(e)}
+                extra[name] = {"error": repr(e)}
             torch.cuda.empty_cache()
+        if args.workload != "fa_train":
+            attempt("fa_train", lambda: bench_fa_train(argparse.Namespace(steps=200, warmup=10), rank, world, dev, peaks))
+        if args.workload != "seg_counts":
+            attempt("seg_counts", lambda: bench_seg_counts(args, rank, world, dev, peaks, steps=5, warmup=3))
         if args.workload != "fa_stress":
-            try:
-                extra["fa_stress"] = bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3)
-            except Exception as e:  # noqa: BLE001
-                extra["fa_stress"] = {"error": repr(e)}
+            attempt("fa_stress", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, light=True))
+        else:
+            attempt("fa_stress_c128", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=5, warmup=3, C=128, light=True))
+            attempt("fa_stress_c256_3xtf32", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, precision="fp32", light=True))
         if rank == 0 and world == 1:
-            res["cpu_baseline"] = cpu_fa_train() if args.workload != "seg_counts" else cpu_seg_counts()
-            if "seg_counts" in extra and "error" not in extra["seg_counts"]:
-                extra["seg_counts"]["cpu_baseline"] = cpu_seg_counts()
+            cpu_fn = {"fa_train": cpu_fa_train, "seg_counts": cpu_seg_counts, "fa_stress": cpu_fa_stress}
+            res["cpu_baseline"] = cpu_fn[args.workload]()
+            for name in ("fa_train", "seg_counts"):
+                if name in extra and "error" not in extra[name]:
+                    extra[name]["cpu_baseline"] = cpu_fn[name]()
     if rank == 0:
         out = {"metric": res.pop("metric"), "value": res.pop("value"), "unit": res.pop("unit"), "n_gpus": world,
                "steps": res.pop("steps", args.steps), "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"),

@@ -34,7 +34,8 @@ using namespace tc;
 
 constexpr int kTile = 128;          // positions per tile (MMA M and N)
 constexpr int kChunk = 32;          // fp32 elements per 128-byte swizzle row = K extent of one operand box
-constexpr int kSlotBytes = kTile * kChunk * 4;   // 16 KB: one TMA box / one pipeline slot
+constexpr int kBoxBytes = kTile * kChunk * 4;    // 16 KB: one TMA box (128 rows x 32 fp32, 128-byte swizzle)
+constexpr int kStageBytes = 2 * kBoxBytes;       // a pipeline stage holds up to two boxes behind one full/empty barrier pair
 constexpr int kThreads = 192;
 constexpr int kMaxGroupCh = 256;    // gradient accumulator columns per CTA
 constexpr uint32_t kTmemCols = 512;
@@ -74,13 +75,13 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     g.tiles = g.Npad / kTile;
     g.nkc = g.Kc / kChunk;
     if ((long long)B * g.Npad > 0x7fffffffLL / 2 || (long long)B * g.Kc + kTile > 0x7fffffffLL / 2) return false;
-    const int avail = (int)((kSmemBudget - 1024 - kSmemAux) / kSlotBytes);   // 1024: alignment slack of the dynamic base
+    const int avail = (int)((kSmemBudget - 1024 - kSmemAux) / kBoxBytes);    // 1024: alignment slack of the dynamic base
     g.split = split ? 1 : 0;
-    const int qslots = g.nkc * (1 + g.split);
-    g.q_resident = qslots <= 8;
-    g.stages = avail - (g.q_resident ? qslots : 0);
-    if (g.stages > 12) g.stages = 12;
-    g.smem_bytes = 1024 + (size_t)((g.q_resident ? qslots : 0) + g.stages) * kSlotBytes + kSmemAux;
+    const int qboxes = g.nkc * (1 + g.split);
+    g.q_resident = qboxes <= 8;
+    g.stages = (avail - (g.q_resident ? qboxes : 0)) / 2;
+    if (g.stages > 6) g.stages = 6;
+    g.smem_bytes = 1024 + (size_t)(g.q_resident ? qboxes : 0) * kBoxBytes + (size_t)g.stages * kStageBytes + kSmemAux;
     return true;
 }
 
@@ -184,8 +185,8 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);     // 1024-byte aligned: swizzle-128B tiles
     const int S = g.stages, nkc = g.nkc, nq = kResident ? nkc * (kSplit ? 2 : 1) : 0;
     unsigned char *qreg = sm;
-    unsigned char *ring = sm + (size_t)nq * kSlotBytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kSlotBytes);
+    unsigned char *ring = sm + (size_t)nq * kBoxBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
     uint64_t *empty = full + S;
     uint64_t *q_full = empty + S;
     uint64_t *d_full = q_full + 1;      // [2] D tile complete in TMEM            (MMA -> epilogue)
@@ -218,8 +219,9 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    // Producer and issuer walk the ring in the same order.  Both run their loops with the whole warp (uniform control
-    // flow, operands in uniform registers); one elected lane issues the TMA / MMA / commit instructions.
+    // Producer and issuer walk the ring of stages in the same order.  Both run their loops with the whole warp
+    // (uniform control flow, operands in uniform registers); one elected lane issues the TMA / MMA / commit
+    // instructions.  A stage carries one or two 16 KB boxes, so every barrier round trip feeds 4-12 MMAs.
     int slot = 0;
     uint32_t ph = 0;
 #define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
@@ -230,38 +232,50 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         const long long t_begin = clock64();
         if (kResident) {
             if (elect_one()) {
-                mbar_arrive_expect_tx(q_full, (uint32_t)nq * kSlotBytes);
+                mbar_arrive_expect_tx(q_full, (uint32_t)nq * kBoxBytes);
                 for (int kc = 0; kc < nq; ++kc)
-                    tma_load_2d(qreg + (size_t)kc * kSlotBytes, &tm_pm, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
+                    tma_load_2d(qreg + (size_t)kc * kBoxBytes, &tm_pm, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
             }
             __syncwarp();
         }
-#define RING_FILL(tm, c0, c1)                                                              \
-        do {                                                                               \
-            TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 1));                            \
-            if (elect_one()) {                                                             \
-                mbar_arrive_expect_tx(&full[slot], kSlotBytes);                            \
-                tma_load_2d(ring + (size_t)slot * kSlotBytes, tm, &full[slot], c0, c1);    \
-            }                                                                              \
-            __syncwarp();                                                                  \
-            RING_ADVANCE();                                                                \
+        // fills the current stage with box A and (if two) box B
+#define RING_FILL(tmA, a0, a1, two, tmB, b0, b1)                                                         \
+        do {                                                                                             \
+            TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 1));                                          \
+            if (elect_one()) {                                                                           \
+                unsigned char *dst = ring + (size_t)slot * kStageBytes;                                  \
+                mbar_arrive_expect_tx(&full[slot], (two) ? kStageBytes : kBoxBytes);                     \
+                tma_load_2d(dst, tmA, &full[slot], a0, a1);                                              \
+                if (two) tma_load_2d(dst + kBoxBytes, tmB, &full[slot], b0, b1);                         \
+            }                                                                                            \
+            __syncwarp();                                                                                \
+            RING_ADVANCE();                                                                              \
         } while (0)
-        // operand boxes of D(i, j): per 32 channels [Q_i hi, Q_i lo,] K_j hi [, K_j lo]
+        // operand boxes of D(i, j)
         auto load_k = [&](int j) {
             const int row_k = b * g.Npad + j * kTile;
-            for (int kc = 0; kc < nkc; ++kc) {
-                if (!kResident) {
-                    RING_FILL(&tm_pm, kc * kChunk, row_q);
-                    if (kSplit) RING_FILL(&tm_pm, kc * kChunk, row_q + lo_rows);
+            if (kResident && !kSplit) {            // two channel chunks of K_j per stage
+                for (int kc = 0; kc < nkc; kc += 2)
+                    RING_FILL(&tm_pm, kc * kChunk, row_k, kc + 1 < nkc, &tm_pm, (kc + 1) * kChunk, row_k);
+            } else if (kResident) {                // K_j hi + lo of one chunk
+                for (int kc = 0; kc < nkc; ++kc) RING_FILL(&tm_pm, kc * kChunk, row_k, true, &tm_pm, kc * kChunk, row_k + lo_rows);
+            } else if (!kSplit) {                  // Q_i + K_j of one chunk
+                for (int kc = 0; kc < nkc; ++kc) RING_FILL(&tm_pm, kc * kChunk, row_q, true, &tm_pm, kc * kChunk, row_k);
+            } else {                               // (Q_i hi, lo) then (K_j hi, lo)
+                for (int kc = 0; kc < nkc; ++kc) {
+                    RING_FILL(&tm_pm, kc * kChunk, row_q, true, &tm_pm, kc * kChunk, row_q + lo_rows);
+                    RING_FILL(&tm_pm, kc * kChunk, row_k, true, &tm_pm, kc * kChunk, row_k + lo_rows);
                 }
-                RING_FILL(&tm_pm, kc * kChunk, row_k);
-                if (kSplit) RING_FILL(&tm_pm, kc * kChunk, row_k + lo_rows);
             }
         };
-        // B boxes of the gradient contraction: (<= 128 channels) x (32 positions of tile j)
+        // B boxes of the gradient contraction, flattened over (32-position chunk jc, 128-channel box bx), two per stage
         auto load_v = [&](int j) {
-            for (int jc = 0; jc < kTile / kChunk; ++jc)
-                for (int bx = 0; bx < nbox; ++bx) RING_FILL(&tm_cm, j * kTile + jc * kChunk, b * g.Kc + gbeg + bx * kTile);
+            const int nb = (kTile / kChunk) * nbox;
+            for (int i = 0; i < nb; i += 2) {
+                const int jc0 = i / nbox, bx0 = i - jc0 * nbox, jc1 = (i + 1) / nbox, bx1 = (i + 1) - jc1 * nbox;
+                RING_FILL(&tm_cm, j * kTile + jc0 * kChunk, b * g.Kc + gbeg + bx0 * kTile, true,
+                          &tm_cm, j * kTile + jc1 * kChunk, b * g.Kc + gbeg + bx1 * kTile);
+            }
         };
         if (kGrad) {
             load_k(0);
@@ -285,55 +299,90 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         // ===================================== MMA issuer =====================================
         long long w_full = 0, w_p = 0, w_drain = 0;
         const long long t_begin = clock64();
-        constexpr uint64_t kSlotDesc = kSlotBytes >> 4;                 // descriptor start-address units (16 bytes)
+        constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kStageDesc = kStageBytes >> 4;    // in descriptor address units (16 B)
         const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
         const uint32_t id_pos = idesc_tf32(kTile, kTile, false), id_neg = idesc_tf32(kTile, kTile, true);
-        const uint32_t id_last = idesc_tf32(kTile, gN - (nbox - 1) * kTile, false);     // last channel box may be narrower
-        const int kc_neg = g.C1p / kChunk;                               // first chunk of branch 2 (subtracted)
+        const int last_rows = gN - (nbox - 1) * kTile;                                   // last channel box may be narrower
+        const uint32_t id_last = idesc_tf32(kTile, last_rows, false), id_wide = idesc_tf32(kTile, 2 * kTile, false);
+        const int kc_neg = g.C1p / kChunk;                                               // first chunk of branch 2 (subtracted)
 #define RING_TAKE(desc_out, slot_out)                                                      \
         do {                                                                               \
             TWAIT(w_full, mbar_wait(&full[slot], ph, 2));                                  \
-            desc_out = ring_desc + (uint64_t)slot * kSlotDesc;                             \
+            desc_out = ring_desc + (uint64_t)slot * kStageDesc;                            \
             slot_out = slot;                                                               \
             RING_ADVANCE();                                                                \
+        } while (0)
+#define MMA4_SS(dcol, ad, bd, id, acc0)                                                    \
+        do {                                                                               \
+            mma_tf32_ss(dcol, (ad), (bd), id, acc0);                                       \
+            mma_tf32_ss(dcol, (ad) + 2, (bd) + 2, id, 1);                                  \
+            mma_tf32_ss(dcol, (ad) + 4, (bd) + 4, id, 1);                                  \
+            mma_tf32_ss(dcol, (ad) + 6, (bd) + 6, id, 1);                                  \
         } while (0)
         // D(i, j0+jj) -> TMEM columns kColD + (jj&1)*128
         auto gemm_d = [&](int jj) {
             const int buf = jj & 1;
             const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
             if (!kGrad) TWAIT(w_drain, mbar_wait(&p_full[buf], ((jj >> 1) & 1) ^ 1, 4));    // epilogue drained this buffer
-            for (int kc = 0; kc < nkc; ++kc) {
-                uint64_t a_hi, a_lo = 0, b_hi, b_lo = 0;
-                int sa = 0, sal = 0, sb = 0, sbl = 0;
-                if (kResident) {
-                    a_hi = q_desc + (uint64_t)kc * kSlotDesc;
-                    a_lo = q_desc + (uint64_t)(nkc + kc) * kSlotDesc;
-                } else {
-                    RING_TAKE(a_hi, sa);
-                    if (kSplit) RING_TAKE(a_lo, sal);
-                }
-                RING_TAKE(b_hi, sb);
-                if (kSplit) RING_TAKE(b_lo, sbl);
-                fence_after_sync();
-                if (elect_one()) {
-                    const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(dcol, a_hi + 2 * ks, b_hi + 2 * ks, id, (kc | ks) != 0);
-                    if (kSplit) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(dcol, a_hi + 2 * ks, b_lo + 2 * ks, id, 1);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) mma_tf32_ss(dcol, a_lo + 2 * ks, b_hi + 2 * ks, id, 1);
+            if (kResident && !kSplit) {
+                for (int kc = 0; kc < nkc; kc += 2) {
+                    uint64_t bd; int sb;
+                    RING_TAKE(bd, sb);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t ad = q_desc + (uint64_t)kc * kBoxDesc;
+                        MMA4_SS(dcol, ad, bd, (kc >= kc_neg ? id_neg : id_pos), kc != 0);
+                        if (kc + 1 < nkc) MMA4_SS(dcol, ad + kBoxDesc, bd + kBoxDesc, (kc + 1 >= kc_neg ? id_neg : id_pos), 1);
+                        umma_commit(&empty[sb]);
+                        if (kc + 2 >= nkc) umma_commit(&d_full[buf]);
                     }
-                    umma_commit(&empty[sb]);
-                    if (kSplit) umma_commit(&empty[sbl]);
-                    if (!kResident) {
-                        umma_commit(&empty[sa]);
-                        if (kSplit) umma_commit(&empty[sal]);
-                    }
-                    if (kc == nkc - 1) umma_commit(&d_full[buf]);
+                    __syncwarp();
                 }
-                __syncwarp();
+            } else if (kResident) {
+                for (int kc = 0; kc < nkc; ++kc) {
+                    uint64_t bd; int sb;
+                    RING_TAKE(bd, sb);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t a_hi = q_desc + (uint64_t)kc * kBoxDesc, a_lo = q_desc + (uint64_t)(nkc + kc) * kBoxDesc;
+                        const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
+                        MMA4_SS(dcol, a_hi, bd, id, kc != 0);
+                        MMA4_SS(dcol, a_hi, bd + kBoxDesc, id, 1);
+                        MMA4_SS(dcol, a_lo, bd, id, 1);
+                        umma_commit(&empty[sb]);
+                        if (kc == nkc - 1) umma_commit(&d_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            } else if (!kSplit) {
+                for (int kc = 0; kc < nkc; ++kc) {
+                    uint64_t sd; int ss;
+                    RING_TAKE(sd, ss);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        MMA4_SS(dcol, sd, sd + kBoxDesc, (kc >= kc_neg ? id_neg : id_pos), kc != 0);
+                        umma_commit(&empty[ss]);
+                        if (kc == nkc - 1) umma_commit(&d_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            } else {
+                for (int kc = 0; kc < nkc; ++kc) {
+                    uint64_t qd, kd; int sq, sk;
+                    RING_TAKE(qd, sq);
+                    RING_TAKE(kd, sk);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
+                        MMA4_SS(dcol, qd, kd, id, kc != 0);
+                        MMA4_SS(dcol, qd, kd + kBoxDesc, id, 1);
+                        MMA4_SS(dcol, qd + kBoxDesc, kd, id, 1);
+                        umma_commit(&empty[sq]);
+                        umma_commit(&empty[sk]);
+                        if (kc == nkc - 1) umma_commit(&d_full[buf]);
+                    }
+                    __syncwarp();
+                }
             }
         };
         // O(i, :) += sign(D(i, j)) * Fcat_j     (A = the sign tile the epilogue left in the D columns)
@@ -341,22 +390,33 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             const int buf = jj & 1;
             const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
             TWAIT(w_p, mbar_wait(&p_full[buf], (jj >> 1) & 1, 5));
-            for (int jc = 0; jc < kTile / kChunk; ++jc)
-                for (int bx = 0; bx < nbox; ++bx) {
-                    uint64_t bd;
-                    int sb;
-                    RING_TAKE(bd, sb);
-                    fence_after_sync();
-                    if (elect_one()) {
-                        const uint32_t id = bx == nbox - 1 ? id_last : id_pos;
+            const int nb = (kTile / kChunk) * nbox;
+            for (int i = 0; i < nb; i += 2) {
+                uint64_t bd; int sb;
+                RING_TAKE(bd, sb);
+                fence_after_sync();
+                if (elect_one()) {
+                    if (nbox == 2 && last_rows == kTile) {
+                        // both boxes belong to the same 32 positions: one N = 256 instruction per K step
+                        const uint32_t acol = pcol + (uint32_t)((i >> 1) * kChunk);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8), bd + 2 * ks, id, (jj | jc | ks) != 0);
-                        umma_commit(&empty[sb]);
-                        if (last && jc == kTile / kChunk - 1 && bx == nbox - 1) umma_commit(o_full);
+                        for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(tmem, acol + ks * 8, bd + 2 * ks, id_wide, (jj | i | ks) != 0);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int jc = (i + h) / nbox, bx = (i + h) - jc * nbox;
+                            const uint32_t id = bx == nbox - 1 ? id_last : id_pos;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8),
+                                            bd + (uint64_t)h * kBoxDesc + 2 * ks, id, (jj | jc | ks) != 0);
+                        }
                     }
-                    __syncwarp();
+                    umma_commit(&empty[sb]);
+                    if (last && i + 2 >= nb) umma_commit(o_full);
                 }
+                __syncwarp();
+            }
         };
         if (kResident) mbar_wait(q_full, 0, 6);
         if (kGrad) {
@@ -368,6 +428,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         } else {
             for (int jj = 0; jj < nt; ++jj) gemm_d(jj);
         }
+#undef MMA4_SS
 #undef RING_TAKE
 #ifdef DSRL_POS_TIMING
         if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
