@@ -90,3 +90,35 @@ def test_torch_timing_port_matches_reference(name):
     np.testing.assert_allclose(float(loss), float(G[f"{name}/loss64"]), rtol=1e-12)
     assert relerr(d1.numpy(), expand_pooled(G[f"{name}/g1_64"], k, H, W)) < 1e-10
     assert relerr(d2.numpy(), expand_pooled(G[f"{name}/g2_64"], k, H, W)) < 1e-10
+
+
+def test_position_torch_port_matches_oracle():
+    """oracle/fa_position_torch_port.py (the CPU timing baseline of the position stress): summing its row blocks gives
+    the float64 oracle's loss and gradients."""
+    import torch
+    from oracle import fa_position_torch_port as tp
+    x1, x2 = pos_inputs((1, 16, 16, 24), (1, 9, 16, 24), 3)
+    k = 2
+    N = (16 // k) * (24 // k)
+    ol, o1, o2 = fa_oracle.fa_position(x1, x2, k, "sum")
+    a, b = torch.from_numpy(x1).double(), torch.from_numpy(x2).double()
+    tot, g1, g2 = 0.0, 0.0, 0.0
+    for r0 in range(0, N, 40):
+        l, d1, d2 = tp.fwd_bwd_rows(a, b, k, r0, min(N, r0 + 40))
+        tot, g1, g2 = tot + float(l), g1 + d1.numpy(), g2 + d2.numpy()
+    np.testing.assert_allclose(tot, ol, rtol=1e-12)
+    assert relerr(g1, o1) < 1e-10 and relerr(g2, o2) < 1e-10
+
+
+def test_tf32_operand_rounding_variant():
+    """round_tf32 = cvt.rna.tf32.f32 (10 explicit mantissa bits, ties away from zero); the rounded-operand oracle stays
+    within TF32 distance of the exact one on the loss while its gradient shows the sign-flip sensitivity."""
+    x = np.array([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -10, -(1.0 + 2.0 ** -11), 3.1415927, 0.0], dtype=np.float32)
+    r = fa_oracle.round_tf32(x)
+    assert r[0] == 1.0 and r[1] == 1.0 + 2.0 ** -10 and r[2] == 1.0 + 2.0 ** -10 and r[3] == -(1.0 + 2.0 ** -10) and r[5] == 0.0
+    assert abs(r[4] - 3.1415927) <= 2.0 ** -10 and (np.float32(r[4]).view(np.uint32) & 0x1FFF) == 0
+    x1, x2 = pos_inputs((1, 32, 16, 16), (1, 32, 16, 16), 11)
+    le, g1, _ = fa_oracle.fa_position(x1, x2, 1, "mean")
+    lt, t1, _ = fa_oracle.fa_position(x1, x2, 1, "mean", operand_rounding="tf32")
+    assert abs(lt - le) <= 1e-4 * abs(le)
+    assert 1e-5 < relerr(t1, g1) < 5e-2
