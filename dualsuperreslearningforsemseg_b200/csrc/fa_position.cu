@@ -35,7 +35,9 @@ using namespace tc;
 constexpr int kTile = 128;          // positions per tile (MMA M and N)
 constexpr int kChunk = 32;          // fp32 elements per 128-byte swizzle row = K extent of one operand box
 constexpr int kBoxBytes = kTile * kChunk * 4;    // 16 KB: one TMA box (128 rows x 32 fp32, 128-byte swizzle)
-constexpr int kStageBytes = 2 * kBoxBytes;       // a pipeline stage holds up to two boxes behind one full/empty barrier pair
+// a pipeline stage holds up to kSB boxes behind one full/empty barrier pair: 2 when the CTA's own operand rows are
+// resident in shared memory (little room left), 4 when everything is streamed (so one barrier round trip feeds >= 8 MMAs)
+__host__ __device__ constexpr int stage_boxes(bool resident) { return resident ? 2 : 4; }
 constexpr int kThreads = 192;
 constexpr int kMaxGroupCh = 256;    // gradient accumulator columns per CTA
 constexpr uint32_t kTmemCols = 512;
@@ -79,9 +81,10 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     g.split = split ? 1 : 0;
     const int qboxes = g.nkc * (1 + g.split);
     g.q_resident = qboxes <= 8;
-    g.stages = (avail - (g.q_resident ? qboxes : 0)) / 2;
+    const int sb = stage_boxes(g.q_resident);
+    g.stages = (avail - (g.q_resident ? qboxes : 0)) / sb;
     if (g.stages > 6) g.stages = 6;
-    g.smem_bytes = 1024 + (size_t)(g.q_resident ? qboxes : 0) * kBoxBytes + (size_t)g.stages * kStageBytes + kSmemAux;
+    g.smem_bytes = 1024 + (size_t)(g.q_resident ? qboxes : 0) * kBoxBytes + (size_t)g.stages * sb * kBoxBytes + kSmemAux;
     return true;
 }
 
@@ -183,6 +186,10 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     extern __shared__ unsigned char smraw[];
     const uint32_t raw = smem_u32(smraw);
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);     // 1024-byte aligned: swizzle-128B tiles
+    constexpr int kSB = stage_boxes(kResident);                 // boxes per stage
+    constexpr int kStageBytes = kSB * kBoxBytes;
+    constexpr int kU = (kResident ? 0 : (kSplit ? 2 : 1)) + (kSplit ? 2 : 1);   // operand boxes per 32-channel chunk: [Q hi, Q lo,] K hi [, K lo]
+    constexpr int kUPS = kSB / kU;                              // chunks per stage
     const int S = g.stages, nkc = g.nkc, nq = kResident ? nkc * (kSplit ? 2 : 1) : 0;
     unsigned char *qreg = sm;
     unsigned char *ring = sm + (size_t)nq * kBoxBytes;
@@ -238,43 +245,49 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             }
             __syncwarp();
         }
-        // fills the current stage with box A and (if two) box B
-#define RING_FILL(tmA, a0, a1, two, tmB, b0, b1)                                                         \
+        // fills the current stage: waits for the slot, arms the barrier with the byte count, runs BODY (TMA issues into `dst`)
+#define STAGE_FILL(nboxes, ...)                                                                          \
         do {                                                                                             \
             TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 1));                                          \
             if (elect_one()) {                                                                           \
                 unsigned char *dst = ring + (size_t)slot * kStageBytes;                                  \
-                mbar_arrive_expect_tx(&full[slot], (two) ? kStageBytes : kBoxBytes);                     \
-                tma_load_2d(dst, tmA, &full[slot], a0, a1);                                              \
-                if (two) tma_load_2d(dst + kBoxBytes, tmB, &full[slot], b0, b1);                         \
+                uint64_t *bar = &full[slot];                                                             \
+                mbar_arrive_expect_tx(bar, (uint32_t)(nboxes) * kBoxBytes);                              \
+                __VA_ARGS__                                                                              \
             }                                                                                            \
             __syncwarp();                                                                                \
             RING_ADVANCE();                                                                              \
         } while (0)
-        // operand boxes of D(i, j)
+        // operand boxes of D(i, j): per 32-channel chunk [Q_i hi, Q_i lo,] K_j hi [, K_j lo]; kUPS chunks per stage
         auto load_k = [&](int j) {
             const int row_k = b * g.Npad + j * kTile;
-            if (kResident && !kSplit) {            // two channel chunks of K_j per stage
-                for (int kc = 0; kc < nkc; kc += 2)
-                    RING_FILL(&tm_pm, kc * kChunk, row_k, kc + 1 < nkc, &tm_pm, (kc + 1) * kChunk, row_k);
-            } else if (kResident) {                // K_j hi + lo of one chunk
-                for (int kc = 0; kc < nkc; ++kc) RING_FILL(&tm_pm, kc * kChunk, row_k, true, &tm_pm, kc * kChunk, row_k + lo_rows);
-            } else if (!kSplit) {                  // Q_i + K_j of one chunk
-                for (int kc = 0; kc < nkc; ++kc) RING_FILL(&tm_pm, kc * kChunk, row_q, true, &tm_pm, kc * kChunk, row_k);
-            } else {                               // (Q_i hi, lo) then (K_j hi, lo)
-                for (int kc = 0; kc < nkc; ++kc) {
-                    RING_FILL(&tm_pm, kc * kChunk, row_q, true, &tm_pm, kc * kChunk, row_q + lo_rows);
-                    RING_FILL(&tm_pm, kc * kChunk, row_k, true, &tm_pm, kc * kChunk, row_k + lo_rows);
-                }
+            for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
+                const int nu = min(kUPS, nkc - kc0);
+                STAGE_FILL(nu * kU, {
+                    for (int u = 0; u < nu; ++u) {
+                        const int c0 = (kc0 + u) * kChunk;
+                        unsigned char *d = dst + (size_t)u * kU * kBoxBytes;
+                        if (!kResident) {
+                            tma_load_2d(d, &tm_pm, bar, c0, row_q); d += kBoxBytes;
+                            if (kSplit) { tma_load_2d(d, &tm_pm, bar, c0, row_q + lo_rows); d += kBoxBytes; }
+                        }
+                        tma_load_2d(d, &tm_pm, bar, c0, row_k); d += kBoxBytes;
+                        if (kSplit) tma_load_2d(d, &tm_pm, bar, c0, row_k + lo_rows);
+                    }
+                });
             }
         };
-        // B boxes of the gradient contraction, flattened over (32-position chunk jc, 128-channel box bx), two per stage
+        // B boxes of the gradient contraction, flattened over (32-position chunk jc, 128-channel box bx), kSB per stage
         auto load_v = [&](int j) {
-            const int nb = (kTile / kChunk) * nbox;
-            for (int i = 0; i < nb; i += 2) {
-                const int jc0 = i / nbox, bx0 = i - jc0 * nbox, jc1 = (i + 1) / nbox, bx1 = (i + 1) - jc1 * nbox;
-                RING_FILL(&tm_cm, j * kTile + jc0 * kChunk, b * g.Kc + gbeg + bx0 * kTile, true,
-                          &tm_cm, j * kTile + jc1 * kChunk, b * g.Kc + gbeg + bx1 * kTile);
+            const int nb = (kTile / kChunk) * nbox;          // 4 or 8
+            for (int i0 = 0; i0 < nb; i0 += kSB) {
+                const int n = min(kSB, nb - i0);
+                STAGE_FILL(n, {
+                    for (int h = 0; h < n; ++h) {
+                        const int jc = (i0 + h) / nbox, bx = (i0 + h) - jc * nbox;
+                        tma_load_2d(dst + (size_t)h * kBoxBytes, &tm_cm, bar, j * kTile + jc * kChunk, b * g.Kc + gbeg + bx * kTile);
+                    }
+                });
             }
         };
         if (kGrad) {
@@ -286,7 +299,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         } else {
             for (int jj = 0; jj < nt; ++jj) load_k(j0 + jj);
         }
-#undef RING_FILL
+#undef STAGE_FILL
 #ifdef DSRL_POS_TIMING
         if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
             long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
@@ -304,6 +317,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         const uint32_t id_pos = idesc_tf32(kTile, kTile, false), id_neg = idesc_tf32(kTile, kTile, true);
         const int last_rows = gN - (nbox - 1) * kTile;                                   // last channel box may be narrower
         const uint32_t id_last = idesc_tf32(kTile, last_rows, false), id_wide = idesc_tf32(kTile, 2 * kTile, false);
+        const bool wide = nbox == 2 && last_rows == kTile;                               // 256 channels: N = 256 instructions
         const int kc_neg = g.C1p / kChunk;                                               // first chunk of branch 2 (subtracted)
 #define RING_TAKE(desc_out, slot_out)                                                      \
         do {                                                                               \
@@ -324,65 +338,32 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             const int buf = jj & 1;
             const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
             if (!kGrad) TWAIT(w_drain, mbar_wait(&p_full[buf], ((jj >> 1) & 1) ^ 1, 4));    // epilogue drained this buffer
-            if (kResident && !kSplit) {
-                for (int kc = 0; kc < nkc; kc += 2) {
-                    uint64_t bd; int sb;
-                    RING_TAKE(bd, sb);
-                    fence_after_sync();
-                    if (elect_one()) {
-                        const uint64_t ad = q_desc + (uint64_t)kc * kBoxDesc;
-                        MMA4_SS(dcol, ad, bd, (kc >= kc_neg ? id_neg : id_pos), kc != 0);
-                        if (kc + 1 < nkc) MMA4_SS(dcol, ad + kBoxDesc, bd + kBoxDesc, (kc + 1 >= kc_neg ? id_neg : id_pos), 1);
-                        umma_commit(&empty[sb]);
-                        if (kc + 2 >= nkc) umma_commit(&d_full[buf]);
+            for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
+                uint64_t sd; int ss;
+                RING_TAKE(sd, ss);
+                fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (int u = 0; u < kUPS; ++u) {
+                        const int kc = kc0 + u;
+                        if (kc < nkc) {
+                            const uint64_t ub = sd + (uint64_t)(u * kU) * kBoxDesc;
+                            const uint64_t a_hi = kResident ? q_desc + (uint64_t)kc * kBoxDesc : ub;
+                            const uint64_t a_lo = kResident ? q_desc + (uint64_t)(nkc + kc) * kBoxDesc : ub + kBoxDesc;
+                            const uint64_t b_hi = kResident ? ub : ub + (kSplit ? 2 : 1) * kBoxDesc;
+                            const uint64_t b_lo = b_hi + kBoxDesc;
+                            const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
+                            MMA4_SS(dcol, a_hi, b_hi, id, kc != 0);
+                            if (kSplit) {
+                                MMA4_SS(dcol, a_hi, b_lo, id, 1);
+                                MMA4_SS(dcol, a_lo, b_hi, id, 1);
+                            }
+                        }
                     }
-                    __syncwarp();
+                    umma_commit(&empty[ss]);
+                    if (kc0 + kUPS >= nkc) umma_commit(&d_full[buf]);
                 }
-            } else if (kResident) {
-                for (int kc = 0; kc < nkc; ++kc) {
-                    uint64_t bd; int sb;
-                    RING_TAKE(bd, sb);
-                    fence_after_sync();
-                    if (elect_one()) {
-                        const uint64_t a_hi = q_desc + (uint64_t)kc * kBoxDesc, a_lo = q_desc + (uint64_t)(nkc + kc) * kBoxDesc;
-                        const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
-                        MMA4_SS(dcol, a_hi, bd, id, kc != 0);
-                        MMA4_SS(dcol, a_hi, bd + kBoxDesc, id, 1);
-                        MMA4_SS(dcol, a_lo, bd, id, 1);
-                        umma_commit(&empty[sb]);
-                        if (kc == nkc - 1) umma_commit(&d_full[buf]);
-                    }
-                    __syncwarp();
-                }
-            } else if (!kSplit) {
-                for (int kc = 0; kc < nkc; ++kc) {
-                    uint64_t sd; int ss;
-                    RING_TAKE(sd, ss);
-                    fence_after_sync();
-                    if (elect_one()) {
-                        MMA4_SS(dcol, sd, sd + kBoxDesc, (kc >= kc_neg ? id_neg : id_pos), kc != 0);
-                        umma_commit(&empty[ss]);
-                        if (kc == nkc - 1) umma_commit(&d_full[buf]);
-                    }
-                    __syncwarp();
-                }
-            } else {
-                for (int kc = 0; kc < nkc; ++kc) {
-                    uint64_t qd, kd; int sq, sk;
-                    RING_TAKE(qd, sq);
-                    RING_TAKE(kd, sk);
-                    fence_after_sync();
-                    if (elect_one()) {
-                        const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
-                        MMA4_SS(dcol, qd, kd, id, kc != 0);
-                        MMA4_SS(dcol, qd, kd + kBoxDesc, id, 1);
-                        MMA4_SS(dcol, qd + kBoxDesc, kd, id, 1);
-                        umma_commit(&empty[sq]);
-                        umma_commit(&empty[sk]);
-                        if (kc == nkc - 1) umma_commit(&d_full[buf]);
-                    }
-                    __syncwarp();
-                }
+                __syncwarp();
             }
         };
         // O(i, :) += sign(D(i, j)) * Fcat_j     (A = the sign tile the epilogue left in the D columns)
@@ -391,29 +372,36 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
             TWAIT(w_p, mbar_wait(&p_full[buf], (jj >> 1) & 1, 5));
             const int nb = (kTile / kChunk) * nbox;
-            for (int i = 0; i < nb; i += 2) {
+            for (int i0 = 0; i0 < nb; i0 += kSB) {
                 uint64_t bd; int sb;
                 RING_TAKE(bd, sb);
                 fence_after_sync();
                 if (elect_one()) {
-                    if (nbox == 2 && last_rows == kTile) {
-                        // both boxes belong to the same 32 positions: one N = 256 instruction per K step
-                        const uint32_t acol = pcol + (uint32_t)((i >> 1) * kChunk);
+                    if (wide) {
+                        // boxes (jc, 0) and (jc, 1) are adjacent: one N = 256 instruction per K step
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(tmem, acol + ks * 8, bd + 2 * ks, id_wide, (jj | i | ks) != 0);
+                        for (int pr = 0; pr < kSB / 2; ++pr) {
+                            const int jc = (i0 >> 1) + pr;
+                            const uint32_t acol = pcol + (uint32_t)(jc * kChunk);
+                            const uint64_t bp = bd + (uint64_t)(2 * pr) * kBoxDesc;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(tmem, acol + ks * 8, bp + 2 * ks, id_wide, (jj | jc | ks) != 0);
+                        }
                     } else {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int jc = (i + h) / nbox, bx = (i + h) - jc * nbox;
-                            const uint32_t id = bx == nbox - 1 ? id_last : id_pos;
+                        for (int h = 0; h < kSB; ++h) {
+                            if (i0 + h < nb) {
+                                const int jc = (i0 + h) / nbox, bx = (i0 + h) - jc * nbox;
+                                const uint32_t id = bx == nbox - 1 ? id_last : id_pos;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8),
-                                            bd + (uint64_t)h * kBoxDesc + 2 * ks, id, (jj | jc | ks) != 0);
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8),
+                                                bd + (uint64_t)h * kBoxDesc + 2 * ks, id, (jj | jc | ks) != 0);
+                            }
                         }
                     }
                     umma_commit(&empty[sb]);
-                    if (last && i + 2 >= nb) umma_commit(o_full);
+                    if (last && i0 + kSB >= nb) umma_commit(o_full);
                 }
                 __syncwarp();
             }
