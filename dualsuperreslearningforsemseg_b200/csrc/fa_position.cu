@@ -21,6 +21,7 @@
 //                   [0,256) gradient accumulator, [256,512) two D / sign tiles (double buffered).
 //   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -51,10 +52,11 @@ struct PosGeom {
     int tiles, nkc;         // Npad / 128, Kc / 32
     int split;              // 1: 3xTF32 -- operands carried as hi + lo TF32 parts, D = hi*hi + hi*lo + lo*hi
     int q_resident, stages;
+    int jsplit;             // gradient variant: the column tiles of one row tile are spread over jsplit CTAs (small grids)
     size_t smem_bytes;
 };
 
-struct PosWs { size_t Fpm, Fcm, nrm, partials, total; };
+struct PosWs { size_t Fpm, Fcm, nrm, partials, opart, total; };
 struct PosSaved { size_t dP, total; };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -85,6 +87,21 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     g.stages = (avail - (g.q_resident ? qboxes : 0)) / sb;
     if (g.stages > 6) g.stages = 6;
     g.smem_bytes = 1024 + (size_t)(g.q_resident ? qboxes : 0) * kBoxBytes + (size_t)g.stages * sb * kBoxBytes + kSmemAux;
+    // Wave quantisation: every CTA of the gradient variant does the same work (all column tiles of one row tile), and
+    // only one CTA fits per SM, so a grid of e.g. 512 CTAs takes ceil(512/148) = 4 rounds instead of 3.46.  Splitting
+    // the column range over `jsplit` CTAs (partial accumulators summed by fa_pos_jacobian) makes the rounds shorter.
+    g.jsplit = 1;
+    const long long ctas = (long long)g.tiles * g.G * B, sms = device_sm_count();
+    double best = (double)((ctas + sms - 1) / sms);
+    for (int s = 2; s <= 4; s *= 2) {
+        if (g.tiles % s) break;
+        const double cost = (double)((ctas * s + sms - 1) / sms) / s;
+        if (cost < 0.96 * best) { best = cost; g.jsplit = s; }
+    }
+    if (const char *force = getenv("DSRL_POS_JSPLIT")) {          // test hook: force 1, 2 or 4 (when it divides the tile count)
+        const int s = atoi(force);
+        if ((s == 1 || s == 2 || s == 4) && g.tiles % s == 0) g.jsplit = s;
+    }
     return true;
 }
 
@@ -94,7 +111,8 @@ inline PosWs make_ws(const PosGeom &g) {
     w.Fpm = off;      off = align_up(off + (size_t)(1 + g.split) * g.B * g.Npad * g.Kc * 4, 1024);   // hi rows, then lo rows
     w.Fcm = off;      off = align_up(off + ((size_t)g.B * g.Kc + kTile) * g.Npad * 4, 1024);   // + one box of slack rows
     w.nrm = off;      off = align_up(off + (size_t)g.B * 2 * g.Npad * 4, 256);
-    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * 8 + 16384, 256);   // + debug timing area
+    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * g.jsplit * 8 + 16384, 256);   // + debug timing area
+    w.opart = off;    off = align_up(off + (g.jsplit > 1 ? (size_t)g.jsplit * g.B * g.Npad * g.Kc * 4 : 0), 256);
     w.total = off;
     return w;
 }
@@ -163,6 +181,7 @@ struct PosArgs {
     const float *Fpm;
     const float *nrm;
     float *dP;
+    float *opart;       // jsplit > 1: raw partial accumulators (jsplit, B, Npad, Kc)
     double *partials;
     unsigned *ticket;
     double *sum_out;
@@ -204,10 +223,12 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     int *flag = reinterpret_cast<int *>(red + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int itile = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
-    const int T = g.tiles;
-    const int j0 = kGrad ? 0 : itile;              // forward-only uses the symmetry D_ij = D_ji: tiles j >= i, weight 2
-    const int nt = T - j0;
+    const int T = g.tiles, js = kGrad ? blockIdx.x / T : 0;
+    const int itile = blockIdx.x - js * T, grp = blockIdx.y, b = blockIdx.z;
+    // column tiles of this CTA: gradient variant -> an equal share of all tiles; forward-only -> the symmetry
+    // D_ij = D_ji: tiles j >= i with weight 2
+    const int nt = kGrad ? T / g.jsplit : T - itile;
+    const int j0 = kGrad ? js * nt : itile;
     const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], nbox = (gN + kTile - 1) / kTile;
     const int row_q = b * g.Npad + itile * kTile, lo_rows = g.B * g.Npad;     // lo parts live lo_rows below the hi parts
 
@@ -291,10 +312,10 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             }
         };
         if (kGrad) {
-            load_k(0);
-            for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) load_k(j + 1);
-                load_v(j);
+            load_k(j0);
+            for (int jj = 0; jj < nt; ++jj) {
+                if (jj + 1 < nt) load_k(j0 + jj + 1);
+                load_v(j0 + jj);
             }
         } else {
             for (int jj = 0; jj < nt; ++jj) load_k(j0 + jj);
@@ -409,9 +430,9 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         if (kResident) mbar_wait(q_full, 0, 6);
         if (kGrad) {
             gemm_d(0);
-            for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) gemm_d(j + 1);      // keeps the tensor pipe busy while the epilogue turns D(j) into signs
-                gemm_g(j, j == T - 1);
+            for (int jj = 0; jj < nt; ++jj) {
+                if (jj + 1 < nt) gemm_d(jj + 1);   // keeps the tensor pipe busy while the epilogue turns D(j) into signs
+                gemm_g(jj, jj == nt - 1);
             }
         } else {
             for (int jj = 0; jj < nt; ++jj) gemm_d(jj);
@@ -471,7 +492,21 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         (void)t_begin; (void)w_d;
 #endif
 
-        if (kGrad) {
+        if (kGrad && g.jsplit > 1) {
+            // partial accumulator of this column share: raw rows to global memory, finished by fa_pos_jacobian
+            mbar_wait(o_full, 0, 7);
+            fence_after_sync();
+            const int row = itile * kTile + r;
+            float *orow = a.opart + (((size_t)js * g.B + b) * g.Npad + row) * g.Kc + gbeg;
+            for (int c0 = 0; c0 < gN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4)
+                    reinterpret_cast<uint4 *>(orow + c0)[e4] = make_uint4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+            }
+        } else if (kGrad) {
             // normalisation Jacobian of the gradient accumulator, stored channel-major (coalesced along positions)
             mbar_wait(o_full, 0, 7);
             fence_after_sync();
@@ -523,7 +558,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             if (lane == 0) red[et >> 5] = tot;
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) {
-                a.partials[(size_t)b * T + itile] = red[0] + red[1] + red[2] + red[3];
+                a.partials[((size_t)js * gridDim.z + b) * T + itile] = red[0] + red[1] + red[2] + red[3];
                 __threadfence();
                 const unsigned nparts = gridDim.x * gridDim.z;
                 *flag = atomicInc(a.ticket, nparts - 1) == nparts - 1;      // self-resetting
@@ -551,6 +586,40 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// jsplit > 1: sum the partial accumulators, apply the normalisation Jacobian, store dP channel-major
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
+                                                      const float *__restrict__ nrm, float grad_scale, float *__restrict__ dP) {
+    extern __shared__ float T[];                     // [Kc][33] summed accumulator of a 32-position strip
+    __shared__ float s_proj[2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, p0 = blockIdx.x * 32;
+    for (int q = warp; q < 32; q += 8) {              // position-major rows in, fixed summation order over the shares
+        for (int c = lane; c < g.Kc; c += 32) {
+            float s = 0.f;
+            for (int js = 0; js < g.jsplit; ++js) s += opart[(((size_t)js * g.B + b) * g.Npad + p0 + q) * g.Kc + c];
+            T[c * 33 + q] = s;
+        }
+    }
+    __syncthreads();
+    if (warp < 2) {                                   // proj = <Fh_i, O_i> over the channels of branch `warp`
+        const int c0 = warp ? g.C1p : 0, c1 = warp ? g.Kc : g.C1p;
+        float s = 0.f;
+        for (int c = c0; c < c1; ++c) s = fmaf(Fcm[((size_t)b * g.Kc + c) * g.Npad + p0 + lane], T[c * 33 + lane], s);
+        const float n = nrm[((size_t)b * 2 + warp) * g.Npad + p0 + lane];
+        s_proj[warp][lane] = n > 1e-12f ? s : 0.f;    // F/eps branch of the clamp: no projection
+    }
+    __syncthreads();
+    for (int c = warp; c < g.Kc; c += 8) {
+        const int br = c >= g.C1p;
+        const float n = nrm[((size_t)b * 2 + br) * g.Npad + p0 + lane];
+        const float scale = (br ? -grad_scale : grad_scale) / fmaxf(n, 1e-12f);
+        const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
+        dP[o] = (T[c * 33 + lane] - Fcm[o] * s_proj[br][lane]) * scale;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -674,6 +743,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     PosArgs a;
     a.Fpm = Fpm; a.nrm = nrm;
     a.dP = reinterpret_cast<float *>(saved + so.dP);
+    a.opart = reinterpret_cast<float *>(ws + wo.opart);
     a.partials = reinterpret_cast<double *>(ws + wo.partials);
     a.ticket = ticket;
     a.sum_out = reinterpret_cast<double *>(saved);
@@ -681,7 +751,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)B * (double)g.N * (double)g.N : 1.0;
     a.loss_div = Z;
     a.grad_scale = (float)(2.0 / Z);
-    const dim3 grid(g.tiles, need_grad ? g.G : 1, B);
+    const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
 #define LAUNCH_TILES(GR, SP, RS)                                                                          \
     do {                                                                                                  \
         if ((rc = opt_in_smem(fa_pos_tiles<GR, SP, RS>, g.smem_bytes))) return rc;                        \
@@ -699,6 +769,11 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
         default: LAUNCH_TILES(true, true, true); break;
     }
 #undef LAUNCH_TILES
+    DSRL_LAUNCH_CHECK();
+    if (need_grad && g.jsplit > 1) {
+        if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
+        fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, Fcm, nrm, a.grad_scale, a.dP);
+    }
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
 }

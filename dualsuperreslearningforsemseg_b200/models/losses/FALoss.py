@@ -19,6 +19,7 @@ Keyword-only extensions (defaults preserve the reference behaviour):
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -32,11 +33,12 @@ _size_cache = {}
 
 
 def _sizes(mode, B, C1, C2, H, W, k):
-    key = (mode, B, C1, C2, H, W, k)
+    geom = (mode, B, C1, C2, H, W, k)
+    key = geom + (os.environ.get("DSRL_POS_JSPLIT"),)        # test hook that changes the workspace layout
     v = _size_cache.get(key)
     if v is None:
         L = _lib.lib()
-        v = (int(L.dsrl_fa_saved_bytes(*key)), int(L.dsrl_fa_workspace_bytes(*key)))
+        v = (int(L.dsrl_fa_saved_bytes(*geom)), int(L.dsrl_fa_workspace_bytes(*geom)))
         _size_cache[key] = v
     return v
 

@@ -129,6 +129,22 @@ def test_full_size_sample_of_config4():
     assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
 
 
+@pytest.mark.parametrize("jsplit", ["1", "2", "4"])
+def test_column_split_variants_agree(jsplit, monkeypatch):
+    """The gradient kernel may spread the column tiles of a row tile over 1, 2 or 4 CTAs (DSRL_POS_JSPLIT forces the
+    choice the library otherwise makes from the grid size): same loss and gradients within FP32 summation order."""
+    x1, x2 = pos_margin_inputs(1, 64, 64, 32, 32, 5)
+    ol, o1, o2 = fa_oracle.fa_position(x1, x2, 1, "mean")
+    monkeypatch.setenv("DSRL_POS_JSPLIT", jsplit)
+    for shape2 in (None, (1, 200, 32, 32)):           # one channel group / two channel groups
+        if shape2 is not None:
+            x1, x2 = pos_margin_inputs(1, 200, 200, 32, 32, 5)
+            ol, o1, o2 = fa_oracle.fa_position(x1, x2, 1, "mean")
+        loss, d1, d2 = run(x1, x2, 1, "mean", precision="fp32")
+        assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
+        assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
+
+
 def test_repeatable_and_one_sided_grad():
     from dualsuperreslearningforsemseg_b200.models.losses import FALoss
     x1, x2 = pos_inputs((1, 64, 32, 32), (1, 64, 32, 32), 7)
