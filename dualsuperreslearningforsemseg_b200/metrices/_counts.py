@@ -139,6 +139,23 @@ class PendingRows:
         return table.cpu().numpy()
 
 
+def gather_rows(table, group=None):
+    """All-gather of per-update rows, rank-major; ranks may hold different numbers of updates (e.g. 500 updates over
+    8 ranks): the row counts are exchanged first and the tables padded to the longest."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([table.shape[0]], dtype=torch.int64, device=table.device)
+    counts = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    width = table.shape[1]
+    padded = torch.zeros((max(counts), width), dtype=table.dtype, device=table.device)
+    padded[: table.shape[0]] = table
+    outs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(outs, padded, group=group)
+    return torch.cat([o[:c] for o, c in zip(outs, counts)], dim=0)
+
+
 def sync_rows(pending: PendingRows, group=None, mode: str = "sum"):
     """Multi-GPU exchange for the per-update rows.  ``sum``: every rank processed a shard of each
     update's pixels (same number of updates everywhere) -> element-wise int64 all-reduce, bit-exact at any world
@@ -153,10 +170,7 @@ def sync_rows(pending: PendingRows, group=None, mode: str = "sum"):
         table = table.clone()
         dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
     elif mode == "gather":
-        world = dist.get_world_size(group)
-        outs = [torch.empty_like(table) for _ in range(world)]
-        dist.all_gather(outs, table.contiguous(), group=group)
-        table = torch.cat(outs, dim=0)
+        table = gather_rows(table, group)
     else:
         raise ValueError("mode must be 'sum' or 'gather'")
     pending.replace(table)

@@ -25,6 +25,8 @@ class mIoU:
         self.miou = 0.0
         self._ious = []
         self._pending = _counts.PendingRows()
+        self._tot_inter = np.zeros(self.num_classes, dtype=np.int64)     # dataset-level sums (dataset_level())
+        self._tot_union = np.zeros(self.num_classes, dtype=np.int64)
 
     # -- updates ------------------------------------------------------------------------------------------
     def update(self, pred, target, valid_labels_mask):
@@ -60,11 +62,24 @@ class mIoU:
             with np.errstate(divide='ignore', invalid='ignore'), warnings.catch_warnings():
                 warnings.simplefilter("ignore", RuntimeWarning)
                 self._ious.append(np.nanmean(area_inter / area_union))
+            self._tot_inter += area_inter
+            self._tot_union += area_union
 
     @property
     def ious(self):
         self._finish()
         return self._ious
+
+    def dataset_level(self):
+        """The two dataset-level definitions the reference's README quotes next to its results (README.md:10-16) but
+        does not implement in ``metrices``: intersections and unions summed over ALL updates first.  Returns percent
+        ``(sum_c I_c / sum_c U_c, nanmean_c(I_c / U_c))``.  ``__call__`` keeps the reference's per-update mean."""
+        self._finish()
+        with np.errstate(divide='ignore', invalid='ignore'), warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            pooled = np.float64(self._tot_inter.sum()) / np.float64(self._tot_union.sum()) * 100.
+            per_class = np.nanmean(self._tot_inter / self._tot_union) * 100.
+        return pooled, per_class
 
     def __call__(self):
         if self.dirty:

@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
         row = _row(pred[sl], target[sl], mask[sl], nc)
         m._pending.add(row); m.dirty = True
         a._pending.add(row[:, 3 * nc:]); a.dirty = True
-    for seed in (21, 22, 23, 24):     # 'gather' mode: whole updates live on different ranks (same count each)
+    for seed in (21, 22, 23, 24, 25):     # 'gather' mode: whole updates live on different ranks (3 on one, 2 on the other)
         if seed % world == rank:
             mg._pending.add(_row(*seg_case("plain", seed, (4, 33, 47), nc), nc)); mg.dirty = True
     m.sync(mode="sum"); a.sync(mode="sum"); mg.sync(mode="gather")
@@ -71,7 +71,7 @@ def test_two_rank_metric_sync_is_bit_exact():
         m.update(*seg_case("plain", seed, (4, 33, 47), nc))
         a.update(*seg_case("plain", seed, (4, 33, 47), nc))
     mg = seg_oracle.MIoUOracle(nc)
-    for seed in (21, 22, 23, 24):
+    for seed in (21, 22, 23, 24, 25):
         mg.update(*seg_case("plain", seed, (4, 33, 47), nc))
     for rank, miou, acc, ious, gious, loss in res:
         assert miou == m() and acc == a() and ious == m.ious

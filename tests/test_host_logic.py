@@ -82,3 +82,22 @@ def test_metric_shape_bug_checks():
         m.update(np.zeros((1, 4, 4), np.int64), np.zeros((1, 4, 5), np.uint8), np.ones((1, 4, 4), bool))
     with pytest.raises(AssertionError, match="channel-order"):
         m.update(np.zeros((4, 4), np.int64), np.zeros((4, 4), np.uint8), np.ones((4, 4), bool))
+
+
+def test_dataset_level_miou_accessor():
+    """README.md:10-16 quotes dataset-level IoU definitions; the accessor derives them from the same exact rows."""
+    import torch
+    from dualsuperreslearningforsemseg_b200.metrices import mIoU
+    nc = 6
+    m = mIoU(nc)
+    tot_i, tot_u = np.zeros(nc, dtype=np.int64), np.zeros(nc, dtype=np.int64)
+    for seed in (1, 2, 3):
+        pred, target, mask = seg_case("plain", seed, (2, 21, 35), nc)
+        ap, ai, at, c, v = seg_oracle.seg_counts(pred, target, mask, nc)
+        m._pending.add(torch.from_numpy(np.concatenate([ap, ai, at, [c, v]]).astype(np.int64))[None]); m.dirty = True
+        tot_i += ai
+        tot_u += ap + at - ai
+    pooled, per_class = m.dataset_level()
+    assert pooled == tot_i.sum() / tot_u.sum() * 100.0
+    assert per_class == np.nanmean(tot_i / tot_u) * 100.0
+    assert len(m.ious) == 3                                   # the per-update list (the reference's definition) is untouched
