@@ -404,6 +404,89 @@ def bench_seg_counts(args, rank, world, dev, peaks, num_maps=500, steps=None, wa
     }
 
 
+def bench_seg_logits(args, rank, world, dev, peaks, images=32, steps=5, warmup=3):
+    """fused argmax + counts from the (B, 19, H, W) fp32 logits (what benchmark.py:61-77 does through a D2H copy
+    and np.argmax).  One update per image; images sharded across ranks."""
+    from dualsuperreslearningforsemseg_b200.metrices import mIoU, _counts
+    from dualsuperreslearningforsemseg_b200 import _lib
+    per_rank = images // world + (1 if rank < images % world else 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + rank)
+    H, W = SEG_HW
+    logits = torch.randn((per_rank, SEG_NC, H, W), device=dev, generator=g)
+    target = torch.randint(0, SEG_NC, (per_rank, H, W), device=dev, generator=g, dtype=torch.uint8)
+    target.masked_fill_(torch.rand((per_rank, H, W), device=dev, generator=g) < 0.1, 255)
+
+    lg5, tg4 = logits[:, None], target[:, None]                  # (U, B=1, NC, H, W): one update per image, one launch
+
+    def step():
+        return _counts.counts_from_logits(lg5, tg4, None, SEG_NC, updates_leading=True)[0]
+
+    n0 = _lib.launch_count()
+    rows = step()
+    launches_per_step = _lib.launch_count() - n0
+    # untimed check of image 0 against the oracle
+    from oracle import seg_oracle
+    p0 = seg_oracle.argmax_first(logits[0:1].cpu().numpy())
+    t0 = target[0:1].cpu().numpy()
+    ap, ai, at, c, v = seg_oracle.seg_counts(p0, t0, t0 != 255, SEG_NC)
+    assert np.array_equal(rows[0].cpu().numpy(), np.concatenate([ap, ai, at, [c, v]])), "seg_logits bench output differs from the oracle"
+    with ClockSampler(dev.index) as clk:
+        ms = timed_steps(step, steps, max(3, warmup), world, flush=None)      # 5 GB of logits per step >> L2
+    step_ms = max_over_ranks(ms, world, dev) / steps
+    bytes_per_px = SEG_NC * 4 + 1
+    npx = per_rank * H * W
+    achieved = npx * bytes_per_px / (step_ms * 1e-3) / 1e9
+    # end to end: logits already on the device (they are the model's output), target from pinned host memory, percentages read back
+    ht = target.cpu().pin_memory()
+
+    def e2e_step():
+        m = mIoU(SEG_NC)
+        for i in range(per_rank):
+            m.update_from_logits(logits[i:i + 1], ht[i:i + 1].to(dev, non_blocking=True))
+        return m()
+
+    e2e_step()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_step()
+    e1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    return {
+        "metric": "seg_counts_from_logits_gpx_per_s", "unit": "Gpx/s", "value": images * H * W / (step_ms * 1e-3) / 1e9,
+        "ms_per_step": step_ms, "steps": steps, "dtype": "f32->int64", "scaling": "strong",
+        "config": {"workload": f"seg_logits: fused argmax + counts, {images} images of ({SEG_NC},{H},{W}) fp32 logits + uint8 target = {bytes_per_px} B/px, "
+                               "one update per image, one launch for all images", "images_per_gpu": per_rank,
+                   "l2": "inputs (5 GB) larger than L2, no flush"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_step": npx * bytes_per_px},
+        "e2e": {"value": world * npx / (e2e_ms * 1e-3) / 1e9, "unit": "Gpx/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(npx), "d2h_bytes_per_step": int(per_rank * 59 * 8),
+                "note": "mIoU.update_from_logits per image; logits are device-resident model outputs, targets come from pinned host memory"},
+        "gpu_launches": int(sum_over_ranks(launches_per_step * steps, world, dev)),
+        "clocks": clk.summary(),
+    }
+
+
+def cpu_seg_logits(threads=None):
+    """benchmark.py:68-77 on the host for one image: np.argmax over the class axis + the metric updates."""
+    from oracle import seg_oracle
+    rng = np.random.default_rng(SEED)
+    H, W = SEG_HW
+    logits = rng.standard_normal((1, SEG_NC, H, W), dtype=np.float32)
+    target = rng.integers(0, SEG_NC, (1, H, W), dtype=np.uint8)
+    t0 = time.perf_counter()
+    pred = seg_oracle.argmax_first(logits)
+    mo, ao = seg_oracle.MIoUOracle(SEG_NC), seg_oracle.AccuracyOracle()
+    mo.update(pred, target, target != 255)
+    ao.update(pred, target, target != 255)
+    dt = time.perf_counter() - t0
+    return {"value": H * W / dt / 1e9, "unit": "Gpx/s", "cores": 1, "kind": "port",
+            "sample": "1 image: np.argmax(logits, axis=1) + oracle/seg_oracle.py updates (single thread like benchmark.py:68-77)"}
+
+
 def cpu_seg_counts(maps=2, threads=None):
     from _inputs import cfg3_maps
     from oracle import seg_oracle
@@ -695,6 +778,7 @@ def main():
             attempt("fa_train", lambda: bench_fa_train(argparse.Namespace(steps=200, warmup=10), rank, world, dev, peaks))
         if args.workload != "seg_counts":
             attempt("seg_counts", lambda: bench_seg_counts(args, rank, world, dev, peaks, steps=5, warmup=3))
+        attempt("seg_logits", lambda: bench_seg_logits(args, rank, world, dev, peaks))
         if args.workload != "fa_stress":
             attempt("fa_stress", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, light=True))
         else:
@@ -703,7 +787,8 @@ def main():
         if rank == 0 and world == 1:
             cpu_fn = {"fa_train": cpu_fa_train, "seg_counts": cpu_seg_counts, "fa_stress": cpu_fa_stress}
             res["cpu_baseline"] = cpu_fn[args.workload]()
-            for name in ("fa_train", "seg_counts"):
+            cpu_fn["seg_logits"] = cpu_seg_logits
+            for name in ("fa_train", "seg_counts", "seg_logits"):
                 if name in extra and "error" not in extra[name]:
                     extra[name]["cpu_baseline"] = cpu_fn[name]()
     if rank == 0:

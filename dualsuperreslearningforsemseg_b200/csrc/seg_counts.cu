@@ -31,6 +31,9 @@ namespace {
 #define DSRL_SEG_UNROLL 1
 #endif
 constexpr int kPxPerThread = 128;  // vector-body pixels per thread per tile (+ <= 2 head/tail) -- must stay < 254
+// The logits kernel moves 19x more bytes per pixel, so a much smaller tile already amortises the flush and gives one
+// image (2 Mpx) 256 CTAs instead of 64 (measured: 64 CTAs per launch left the kernel at 17 % of the HBM peak).
+constexpr int kLogitsPxPerThread = 32;
 
 template <typename T, int N>
 struct alignas(sizeof(T) * N > 16 ? 16 : sizeof(T) * N) Pack {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(BLOCK) seg_counts_logits_kernel(const float *_
                                                                   int nc, int ignore_label, int tiles_per_image,
                                                                   unsigned long long *__restrict__ counts,
                                                                   long long *__restrict__ pred_out) {
-    constexpr long long TILE = (long long)BLOCK * kPxPerThread;
+    constexpr long long TILE = (long long)BLOCK * kLogitsPxPerThread;
     extern __shared__ __align__(16) uint8_t sm[];
     const long long img = blockIdx.x / tiles_per_image;  // global image index = u*batch + i
     const int tt = blockIdx.x % tiles_per_image;
@@ -330,7 +333,7 @@ int dispatch_pred(const void *pred, int pred_dtype, const void *target, int targ
 template <typename TT, int VEC, int BLOCK>
 int launch_logits(const float *logits, const void *target, const uint8_t *mask, int64_t num_updates, int64_t batch,
                   int64_t hw, int nc, int ignore_label, int64_t *counts, int64_t *pred_out, cudaStream_t st) {
-    constexpr long long TILE = (long long)BLOCK * kPxPerThread;
+    constexpr long long TILE = (long long)BLOCK * kLogitsPxPerThread;
     const int rows = 3 * nc + 3;
     const size_t smem = (size_t)((rows + 3) / 4) * BLOCK * 4 + (size_t)(rows + 4) * sizeof(int);
     const long long tiles_per_image = (hw + TILE - 1) / TILE;

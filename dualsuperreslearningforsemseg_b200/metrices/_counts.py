@@ -88,24 +88,28 @@ def counts_for_update(pred, target, mask, nc: int, updates_leading: bool = False
     return rows
 
 
-def counts_from_logits(logits, target, mask, nc: int, ignore_label: int = IGNORE_DEFAULT, want_pred: bool = False):
-    """Fused argmax + counts for ONE update: logits (B, NC, H, W) fp32 CUDA, target (B, H, W)."""
-    if not (torch.is_tensor(logits) and logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 4):
-        raise TypeError("logits must be a 4-D float32 CUDA tensor (B, NC, H, W)")
-    B, C, H, W = logits.shape
+def counts_from_logits(logits, target, mask, nc: int, ignore_label: int = IGNORE_DEFAULT, want_pred: bool = False,
+                       updates_leading: bool = False):
+    """Fused argmax + counts: logits (B, NC, H, W) fp32 CUDA, target (B, H, W) -> ONE update; with ``updates_leading``
+    logits (U, B, NC, H, W), target (U, B, H, W) -> U updates in one launch."""
+    want = 5 if updates_leading else 4
+    if not (torch.is_tensor(logits) and logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == want):
+        raise TypeError(f"logits must be a {want}-D float32 CUDA tensor ({'U, ' if updates_leading else ''}B, NC, H, W)")
+    U = logits.shape[0] if updates_leading else 1
+    B, C, H, W = logits.shape[-4:]
     assert C == nc, "BUG CHECK: logits channel count must equal num_classes."
-    assert tuple(target.shape) == (B, H, W), "BUG CHECK: 'pred' and 'target' must be of the same shape of (B, H, W)."
+    assert tuple(target.shape) == tuple(logits.shape[:-3]) + (H, W), "BUG CHECK: 'pred' and 'target' must be of the same shape of (B, H, W)."
     dev = logits.device
     lg = logits.contiguous()
     t = _as_cuda(target, dev, True)
     m = _as_cuda(mask, dev, False) if mask is not None else None
-    rows = torch.empty((1, row_len(nc)), dtype=torch.int64, device=dev)
-    pred = torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_pred else None
+    rows = torch.empty((U, row_len(nc)), dtype=torch.int64, device=dev)
+    pred = torch.empty(tuple(target.shape), dtype=torch.int64, device=dev) if want_pred else None
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().dsrl_seg_counts_from_logits(
             ctypes.c_void_p(lg.data_ptr()), ctypes.c_void_p(t.data_ptr()), _DT[t.dtype],
-            ctypes.c_void_p(m.data_ptr()) if m is not None else None, 1, B, H * W, nc, ignore_label,
+            ctypes.c_void_p(m.data_ptr()) if m is not None else None, U, B, H * W, nc, ignore_label,
             ctypes.c_void_p(rows.data_ptr()), ctypes.c_void_p(pred.data_ptr()) if pred is not None else None, stream))
     rows._dsrl_keepalive = (lg, t, m)
     return rows, pred

@@ -145,3 +145,19 @@ def test_fused_argmax_counts(shape):
     m2.update_from_logits(torch.from_numpy(logits).cuda(), torch.from_numpy(target).cuda())      # mask derived in-kernel
     mo2 = seg_oracle.MIoUOracle(C); mo2.update(pred, target, target != 255)
     assert np.array_equal(bits(m2.ious), bits(mo2.ious))
+
+
+def test_logits_many_updates_one_launch():
+    """(U, B, NC, H, W) logits -> U rows in one launch, equal to U separate update_from_logits calls."""
+    from dualsuperreslearningforsemseg_b200.metrices import _counts
+    rng = np.random.default_rng(5)
+    U, B, nc, H, W = 3, 2, 19, 40, 52
+    logits = rng.standard_normal((U, B, nc, H, W)).astype(np.float32)
+    target = rng.integers(0, nc, (U, B, H, W)).astype(np.uint8)
+    target[rng.random(target.shape) < 0.1] = 255
+    rows, _ = _counts.counts_from_logits(torch.from_numpy(logits).cuda(), torch.from_numpy(target).cuda(), None, nc, updates_leading=True)
+    rows = rows.cpu().numpy()
+    for u in range(U):
+        pred = seg_oracle.argmax_first(logits[u])
+        ap, ai, at, c, v = seg_oracle.seg_counts(pred, target[u], target[u] != 255, nc)
+        assert np.array_equal(rows[u], np.concatenate([ap, ai, at, [c, v]]))
