@@ -10,6 +10,8 @@ One JSON line on stdout (rank 0).  Workloads (BASELINE.json configs):
                          shards over 1/2/4/8 GPUs]
   fa_train   configs[1]  FA loss fwd+bwd, reference semantics, batch 6 x (1, 64, 128) fp32 per GPU
   seg_counts configs[2]  mIoU + accuracy counts, 19 classes, 500 label maps of 1024 x 2048 (int64/uint8/bool)
+  (extra only) seg_logits  fused argmax + counts from fp32 logits
+  (extra only) train_step  configs[4]  full stage-3 DSRL training step around the hot path (harness/, torch DDP when N > 1)
 
 A "step" is one pass of the hot path over one batch of synthetic input.  `value` is measured with the inputs
 resident in HBM (CUDA events on the launching stream); `e2e` is the same metric through the public drop-in
@@ -668,6 +670,66 @@ def cpu_fa_stress(budget_s=15.0, threads=None, C=None, rows=256):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# workload: train_step (BASELINE configs[4]) -- the caller of the hot path, harness/ (plain PyTorch + torch DDP)
+# ----------------------------------------------------------------------------------------------------------------
+class _TorchFALoss(torch.nn.Module):
+    """What a user runs without this library: the reference FALoss restated in eager PyTorch, on the GPU."""
+
+    def forward(self, a, b):
+        from oracle import fa_torch_port
+        return fa_torch_port.fa_loss(a, b, FA_K, "mean")
+
+
+def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6):
+    from harness.train_step import Stage3Step, synthetic_batch
+    from dualsuperreslearningforsemseg_b200.models.losses import FALoss
+    from dualsuperreslearningforsemseg_b200 import _lib
+    img, org, target = synthetic_batch(batch, dev, SEED + rank)
+    out = {}
+    for name, fa in (("dsrl_b200", FALoss()), ("pytorch_eager_fa", _TorchFALoss())):
+        step = Stage3Step(fa, dev, ddp=world > 1)
+        n0 = _lib.launch_count()
+        for _ in range(max(3, warmup)):
+            losses = step(img, org, target)
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            losses = step(img, org, target)
+        e1.record()
+        barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+        # the FA term alone (forward + backward on the step's own feature-transformer outputs)
+        with torch.no_grad():
+            o = step.model(img)
+        a, b = o[2].detach().requires_grad_(True), o[3].detach().requires_grad_(True)
+        for _ in range(3):
+            fa(a, b).backward()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(20):
+            fa(a, b).backward()
+        f1.record()
+        torch.cuda.synchronize()
+        out[name] = {"ms_per_step": ms, "images_per_s": world * batch / (ms * 1e-3), "fa_fwd_bwd_ms": f0.elapsed_time(f1) / 20,
+                     "losses_ce_mse_fa_total": [float(x) for x in losses],
+                     "lib_launches": int(_lib.launch_count() - n0)}
+        del step
+        torch.cuda.empty_cache()
+    ours, ref = out["dsrl_b200"], out["pytorch_eager_fa"]
+    return {"metric": "stage3_train_images_per_s", "unit": "images/s", "value": ours["images_per_s"], "ms_per_step": ours["ms_per_step"],
+            "steps": steps, "dtype": "f32", "scaling": "weak",
+            "config": {"workload": f"train_step: BASELINE configs[4] -- full stage-3 DSRL step (SSSR+SISR+FA, CE + 0.1 MSE + 1.0 FA, SGD), "
+                                   f"random-init weights, synthetic 256x512 -> 512x1024, batch {batch} per GPU, "
+                                   f"{'torch DDP over NCCL' if world > 1 else 'single GPU'}; model = harness/dsrl_model.py (cuDNN fp32)",
+                       "fa_inputs": [batch, 1, 64, 128]},
+            "with_dsrl_b200_fa": ours, "with_pytorch_eager_fa": ref,
+            "fa_speedup_in_step": ref["fa_fwd_bwd_ms"] / ours["fa_fwd_bwd_ms"],
+            "step_speedup": ref["ms_per_step"] / ours["ms_per_step"]}
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # main
 # ----------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
@@ -779,6 +841,7 @@ def main():
         if args.workload != "seg_counts":
             attempt("seg_counts", lambda: bench_seg_counts(args, rank, world, dev, peaks, steps=5, warmup=3))
         attempt("seg_logits", lambda: bench_seg_logits(args, rank, world, dev, peaks))
+        attempt("train_step", lambda: bench_train_step(args, rank, world, dev, peaks))
         if args.workload != "fa_stress":
             attempt("fa_stress", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, light=True))
         else:
