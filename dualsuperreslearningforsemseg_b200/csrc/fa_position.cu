@@ -53,7 +53,8 @@ struct PosGeom {
     int split;              // 1: 3xTF32 -- operands carried as hi + lo TF32 parts, D = hi*hi + hi*lo + lo*hi
     int q_resident, stages;
     int jsplit;             // gradient variant: the column tiles of one row tile are spread over jsplit CTAs (small grids)
-    size_t smem_bytes;
+    int pair, pair_stages;  // CTA-pair form of the gradient variant usable for this geometry; its ring depth
+    size_t smem_bytes, pair_smem_bytes;
 };
 
 struct PosWs { size_t Fpm, Fcm, nrm, partials, opart, total; };
@@ -97,6 +98,16 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         if (g.tiles % s) break;
         const double cost = (double)((ctas * s + sms - 1) / sms) / s;
         if (cost < 0.96 * best) { best = cost; g.jsplit = s; }
+    }
+    // CTA-pair form: single TF32 pass, an even number of row tiles
+    g.pair = !g.split && (g.tiles % 2 == 0);
+    if (const char *e = getenv("DSRL_POS_PAIR")) { if (atoi(e) == 0) g.pair = 0; }
+    {
+        const int stage = g.q_resident ? 4 * (kBoxBytes / 2) : 2 * (kBoxBytes + kBoxBytes / 2);
+        const size_t qbytes = g.q_resident ? (size_t)g.nkc * kBoxBytes : 0;
+        g.pair_stages = (int)((kSmemBudget - 1024 - kSmemAux - qbytes) / stage);
+        if (g.pair_stages > 6) g.pair_stages = 6;
+        g.pair_smem_bytes = 1024 + qbytes + (size_t)g.pair_stages * stage + kSmemAux;
     }
     if (const char *force = getenv("DSRL_POS_JSPLIT")) {          // test hook: force 1, 2 or 4 (when it divides the tile count)
         const int s = atoi(force);
@@ -195,6 +206,164 @@ struct PosArgs {
 #else
 #define TWAIT(acc, stmt) do { stmt; } while (0)
 #endif
+
+// Epilogue role, shared by the single-CTA and the CTA-pair tile kernels (warps 2..5 of a CTA): per column tile turn D into
+// |D| (loss partial) and sign(D) (in place, operand of the gradient MMAs); after the last tile finish the gradient
+// accumulator (normalisation Jacobian, or the raw partial rows when the column range is split); finally the loss.
+// kPair: the barrier the MMA issuer waits on lives in the leader CTA of the pair.
+struct EpiCtx {
+    uint64_t *d_full, *p_full, *o_full;
+    double *red;
+    int *flag;
+    uint32_t tmem;
+    int itile, js, grp, b, j0, nt, gN, gbeg, T;
+    int weight_below;     // forward-only CTA pairs: weight of a tile below the diagonal (0)
+};
+
+template <bool kGrad, bool kPair>
+__device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a, const EpiCtx &c) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *d_full = c.d_full, *p_full = c.p_full, *o_full = c.o_full;
+    double *red = c.red;
+    int *flag = c.flag;
+    const uint32_t tmem = c.tmem;
+    const int itile = c.itile, js = c.js, grp = c.grp, b = c.b, j0 = c.j0, nt = c.nt, gN = c.gN, gbeg = c.gbeg, T = c.T;
+    {
+    // ===================================== epilogue warps =====================================
+    const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    double acc = 0.0;
+    long long w_d = 0;
+    const long long t_begin = clock64();
+    for (int jj = 0; jj < nt; ++jj) {
+        const int buf = jj & 1, j = j0 + jj;
+        TWAIT(w_d, mbar_wait(&d_full[buf], (jj >> 1) & 1, 3));
+        fence_after_sync();
+        const bool diag = j == itile;
+        float tsum = 0.f;
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32);
+            tmem_ld32(taddr, v);
+            tmem_ld_wait();
+            if (diag && cg == q) {                               // S_ii = 1 in both branches: a structural tie
+#pragma unroll
+                for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float x = __uint_as_float(v[e]);
+                tsum += fabsf(x);
+                if (kGrad) v[e] = (v[e] & 0x80000000u) | (x != 0.f ? 0x3f800000u : 0u);     // sign(x) as a TF32 value
+            }
+            if (kGrad) tmem_st32(taddr, v);
+        }
+        if (kGrad) tmem_st_wait();
+        fence_before_sync();
+        if (kPair) mbar_arrive_leader(&p_full[buf]); else mbar_arrive(&p_full[buf]);
+        acc += (double)tsum * ((kGrad || diag) ? 1.0 : 2.0);
+    }
+#ifdef DSRL_POS_TIMING
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+        long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+        tm[6] = clock64() - t_begin; tm[7] = w_d;
+    }
+#else
+    (void)t_begin; (void)w_d;
+#endif
+
+    if (kGrad && g.jsplit > 1) {
+        // partial accumulator of this column share: raw rows to global memory, finished by fa_pos_jacobian
+        mbar_wait(o_full, 0, 7);
+        fence_after_sync();
+        const int row = itile * kTile + r;
+        float *orow = a.opart + (((size_t)js * g.B + b) * g.Npad + row) * g.Kc + gbeg;
+        for (int c0 = 0; c0 < gN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4)
+                reinterpret_cast<uint4 *>(orow + c0)[e4] = make_uint4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+        }
+    } else if (kGrad) {
+        // normalisation Jacobian of the gradient accumulator, stored channel-major (coalesced along positions)
+        mbar_wait(o_full, 0, 7);
+        fence_after_sync();
+        const int row = itile * kTile + r;
+        const float *frow = a.Fpm + ((size_t)b * g.Npad + row) * g.Kc;
+        for (int br = 0; br < 2; ++br) {
+            const int cb = br ? g.C1p : 0, ce = br ? g.Kc : g.C1p;         // channel range of the branch
+            if (cb < gbeg || ce > gbeg + gN) continue;                     // not in this CTA's group
+            const float n = a.nrm[((size_t)b * 2 + br) * g.Npad + row];
+            const float sgn = br ? -a.grad_scale : a.grad_scale;           // dL/dFh2 = -2 Fh2 Sigma
+            float proj = 0.f;
+            for (int c0 = cb; c0 < ce; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
+                    proj = fmaf(f.x, __uint_as_float(v[e4 * 4 + 0]), proj);
+                    proj = fmaf(f.y, __uint_as_float(v[e4 * 4 + 1]), proj);
+                    proj = fmaf(f.z, __uint_as_float(v[e4 * 4 + 2]), proj);
+                    proj = fmaf(f.w, __uint_as_float(v[e4 * 4 + 3]), proj);
+                }
+            }
+            const bool dead = !(n > 1e-12f);                                // F/eps branch of the clamp: no projection
+            const float scale = sgn / fmaxf(n, 1e-12f);
+            if (dead) proj = 0.f;
+            for (int c0 = cb; c0 < ce; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
+                tmem_ld_wait();
+                float *dst = a.dP + ((size_t)b * g.Kc + c0) * g.Npad + row;
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
+                    dst[(size_t)(e4 * 4 + 0) * g.Npad] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale;
+                    dst[(size_t)(e4 * 4 + 1) * g.Npad] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale;
+                    dst[(size_t)(e4 * 4 + 2) * g.Npad] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale;
+                    dst[(size_t)(e4 * 4 + 3) * g.Npad] = (__uint_as_float(v[e4 * 4 + 3]) - f.w * proj) * scale;
+                }
+            }
+        }
+    }
+
+    // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
+    if (grp == 0) {
+        const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
+        double tot = warp_sum(acc);
+        if (lane == 0) red[et >> 5] = tot;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+            a.partials[((size_t)js * gridDim.z + b) * T + itile] = red[0] + red[1] + red[2] + red[3];
+            __threadfence();
+            const unsigned nparts = gridDim.x * gridDim.z;
+            *flag = atomicInc(a.ticket, nparts - 1) == nparts - 1;      // self-resetting
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*flag) {
+            __threadfence();
+            const int nparts = (int)(gridDim.x * gridDim.z);
+            double s = 0.0;
+            for (int i = et; i < nparts; i += 128) s += __ldcg(a.partials + i);
+            s = warp_sum(s);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (lane == 0) red[4 + (et >> 5)] = s;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+                const double all = red[4] + red[5] + red[6] + red[7];
+                *a.sum_out = all;
+                *a.loss_out = (float)(all / a.loss_div);
+            }
+        }
+    }
+    }
+}
+
 
 // kGrad:     also accumulate the gradient contraction (otherwise loss only, tiles j >= i by symmetry)
 // kSplit:    3xTF32 -- D = hi*hi + hi*lo + lo*hi with the lo parts as extra operand boxes
@@ -449,143 +618,219 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 #endif
     } else {
         // ===================================== epilogue warps =====================================
-        const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        double acc = 0.0;
-        long long w_d = 0;
-        const long long t_begin = clock64();
-        for (int jj = 0; jj < nt; ++jj) {
-            const int buf = jj & 1, j = j0 + jj;
-            TWAIT(w_d, mbar_wait(&d_full[buf], (jj >> 1) & 1, 3));
-            fence_after_sync();
-            const bool diag = j == itile;
-            float tsum = 0.f;
-#pragma unroll 1
-            for (int cg = 0; cg < 4; ++cg) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32);
-                tmem_ld32(taddr, v);
-                tmem_ld_wait();
-                if (diag && cg == q) {                               // S_ii = 1 in both branches: a structural tie
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float x = __uint_as_float(v[e]);
-                    tsum += fabsf(x);
-                    if (kGrad) v[e] = (v[e] & 0x80000000u) | (x != 0.f ? 0x3f800000u : 0u);     // sign(x) as a TF32 value
-                }
-                if (kGrad) tmem_st32(taddr, v);
-            }
-            if (kGrad) tmem_st_wait();
-            fence_before_sync();
-            mbar_arrive(&p_full[buf]);
-            acc += (double)tsum * ((kGrad || diag) ? 1.0 : 2.0);
-        }
-#ifdef DSRL_POS_TIMING
-        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
-            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
-            tm[6] = clock64() - t_begin; tm[7] = w_d;
-        }
-#else
-        (void)t_begin; (void)w_d;
-#endif
-
-        if (kGrad && g.jsplit > 1) {
-            // partial accumulator of this column share: raw rows to global memory, finished by fa_pos_jacobian
-            mbar_wait(o_full, 0, 7);
-            fence_after_sync();
-            const int row = itile * kTile + r;
-            float *orow = a.opart + (((size_t)js * g.B + b) * g.Npad + row) * g.Kc + gbeg;
-            for (int c0 = 0; c0 < gN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4)
-                    reinterpret_cast<uint4 *>(orow + c0)[e4] = make_uint4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-            }
-        } else if (kGrad) {
-            // normalisation Jacobian of the gradient accumulator, stored channel-major (coalesced along positions)
-            mbar_wait(o_full, 0, 7);
-            fence_after_sync();
-            const int row = itile * kTile + r;
-            const float *frow = a.Fpm + ((size_t)b * g.Npad + row) * g.Kc;
-            for (int br = 0; br < 2; ++br) {
-                const int cb = br ? g.C1p : 0, ce = br ? g.Kc : g.C1p;         // channel range of the branch
-                if (cb < gbeg || ce > gbeg + gN) continue;                     // not in this CTA's group
-                const float n = a.nrm[((size_t)b * 2 + br) * g.Npad + row];
-                const float sgn = br ? -a.grad_scale : a.grad_scale;           // dL/dFh2 = -2 Fh2 Sigma
-                float proj = 0.f;
-                for (int c0 = cb; c0 < ce; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
-                        proj = fmaf(f.x, __uint_as_float(v[e4 * 4 + 0]), proj);
-                        proj = fmaf(f.y, __uint_as_float(v[e4 * 4 + 1]), proj);
-                        proj = fmaf(f.z, __uint_as_float(v[e4 * 4 + 2]), proj);
-                        proj = fmaf(f.w, __uint_as_float(v[e4 * 4 + 3]), proj);
-                    }
-                }
-                const bool dead = !(n > 1e-12f);                                // F/eps branch of the clamp: no projection
-                const float scale = sgn / fmaxf(n, 1e-12f);
-                if (dead) proj = 0.f;
-                for (int c0 = cb; c0 < ce; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
-                    tmem_ld_wait();
-                    float *dst = a.dP + ((size_t)b * g.Kc + c0) * g.Npad + row;
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
-                        dst[(size_t)(e4 * 4 + 0) * g.Npad] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale;
-                        dst[(size_t)(e4 * 4 + 1) * g.Npad] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale;
-                        dst[(size_t)(e4 * 4 + 2) * g.Npad] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale;
-                        dst[(size_t)(e4 * 4 + 3) * g.Npad] = (__uint_as_float(v[e4 * 4 + 3]) - f.w * proj) * scale;
-                    }
-                }
-            }
-        }
-
-        // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
-        if (grp == 0) {
-            const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
-            double tot = warp_sum(acc);
-            if (lane == 0) red[et >> 5] = tot;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) {
-                a.partials[((size_t)js * gridDim.z + b) * T + itile] = red[0] + red[1] + red[2] + red[3];
-                __threadfence();
-                const unsigned nparts = gridDim.x * gridDim.z;
-                *flag = atomicInc(a.ticket, nparts - 1) == nparts - 1;      // self-resetting
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*flag) {
-                __threadfence();
-                const int nparts = (int)(gridDim.x * gridDim.z);
-                double s = 0.0;
-                for (int i = et; i < nparts; i += 128) s += __ldcg(a.partials + i);
-                s = warp_sum(s);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (lane == 0) red[4 + (et >> 5)] = s;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    const double all = red[4] + red[5] + red[6] + red[7];
-                    *a.sum_out = all;
-                    *a.loss_out = (float)(all / a.loss_div);
-                }
-            }
-        }
+        EpiCtx c;
+        c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.tmem = tmem;
+        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T; c.weight_below = 0;
+        epilogue_role<kGrad, false>(g, a, c);
     }
 #undef RING_ADVANCE
 
     fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair form of the gradient variant (cluster of 2, tcgen05 cta_group::2, M = 256)
+// ---------------------------------------------------------------------------------------------------------------
+// Two CTAs own two consecutive 128-row tiles.  The leader (even CTA) issues every MMA for both: A rows / D rows come from
+// each CTA's own shared / tensor memory, and each CTA supplies only HALF of every B tile (64 of the 128 K_j rows, half of
+// the V_j channels).  Per column tile a CTA therefore receives half the K_j / V_j boxes and the tensor cores read 6 KB
+// instead of 8 KB of shared memory per D step and 4 KB instead of 8 KB per gradient step -- the single-CTA form is
+// shared-memory-bandwidth bound.  The full barriers live in the leader (both CTAs' TMA loads count bytes
+// there); empty / d_full / o_full are signalled in both CTAs by multicast commits; both epilogues arrive on the leader's
+// p_full.
+constexpr int kPairKBox = kBoxBytes / 2;           // 64 rows of K_j per CTA
+
+template <bool kResident>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                  const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t raw = smem_u32(smraw);
+    unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
+    // per-CTA stage: resident -> 4 K boxes (32 KB) or 2 V boxes; streamed -> 2 x (Q box 16 KB + K box 8 KB) = 48 KB or 2 V boxes
+    constexpr int kStageBytes = kResident ? 4 * kPairKBox : 2 * (kBoxBytes + kPairKBox);
+    constexpr int kUPS = kResident ? 4 : 2;                         // 32-channel chunks per stage
+    constexpr int kUnitBytes = kResident ? kPairKBox : kBoxBytes + kPairKBox;
+    const int S = g.pair_stages, nkc = g.nkc, nq = kResident ? nkc : 0;
+    unsigned char *qreg = sm;
+    unsigned char *ring = sm + (size_t)nq * kBoxBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
+    uint64_t *empty = full + S;
+    uint64_t *q_full = empty + S;
+    uint64_t *d_full = q_full + 1;
+    uint64_t *p_full = d_full + 2;
+    uint64_t *o_full = p_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
+    double *red = reinterpret_cast<double *>(o_full + 2);
+    int *flag = reinterpret_cast<int *>(red + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int T = g.tiles, js = blockIdx.x / T;
+    const int itile = blockIdx.x - js * T, grp = blockIdx.y, b = blockIdx.z;          // T is even: the pair shares js
+    const int nt = T / g.jsplit, j0 = js * nt;
+    const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], vrows = gN / 2;                   // this CTA's share of the V_j channels
+    const uint32_t vbytes = (uint32_t)vrows * kChunk * 4;
+    const int row_q = b * g.Npad + itile * kTile;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_q);
+        prefetch_tmap(&tm_k);
+        prefetch_tmap(&tm_v);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 256); }     // both CTAs' epilogue threads
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
+    fence_before_sync();
+    cluster_sync();                         // peer barriers are initialised before anything signals them
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    int slot = 0;
+    uint32_t ph = 0;
+#define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs, each for its own shared memory) =====================================
+        if (kResident) {
+            if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nq * kBoxBytes);
+                for (int kc = 0; kc < nq; ++kc) tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, kc * kChunk, row_q);
+            }
+            __syncwarp();
+        }
+#define STAGE_FILL(bytes_per_cta, ...)                                                                   \
+        do {                                                                                             \
+            mbar_wait(&empty[slot], ph ^ 1, 11);                                                         \
+            if (elect_one()) {                                                                           \
+                unsigned char *dst = ring + (size_t)slot * kStageBytes;                                  \
+                uint64_t *bar = &full[slot];                                                             \
+                if (leader) mbar_arrive_expect_tx(bar, 2u * (uint32_t)(bytes_per_cta));                  \
+                __VA_ARGS__                                                                              \
+            }                                                                                            \
+            __syncwarp();                                                                                \
+            RING_ADVANCE();                                                                              \
+        } while (0)
+        auto load_k = [&](int j) {
+            const int row_k = b * g.Npad + j * kTile + (int)rank * (kTile / 2);           // this CTA's 64 rows of K_j
+            for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
+                const int nu = min(kUPS, nkc - kc0);
+                STAGE_FILL(nu * kUnitBytes, {
+                    for (int u = 0; u < nu; ++u) {
+                        const int c0 = (kc0 + u) * kChunk;
+                        unsigned char *d = dst + (size_t)u * kUnitBytes;
+                        if (!kResident) { tma_load_2d_pair(d, &tm_q, bar, c0, row_q); d += kBoxBytes; }
+                        tma_load_2d_pair(d, &tm_k, bar, c0, row_k);
+                    }
+                });
+            }
+        };
+        auto load_v = [&](int j) {
+            const int row_v = b * g.Kc + gbeg + (int)rank * vrows;                        // this CTA's half of the channels
+            for (int jc0 = 0; jc0 < kTile / kChunk; jc0 += 2) {
+                STAGE_FILL(2 * vbytes, {
+                    tma_load_2d_pair(dst, &tm_v, bar, j * kTile + jc0 * kChunk, row_v);
+                    tma_load_2d_pair(dst + kBoxBytes, &tm_v, bar, j * kTile + (jc0 + 1) * kChunk, row_v);
+                });
+            }
+        };
+        load_k(j0);
+        for (int jj = 0; jj < nt; ++jj) {
+            if (jj + 1 < nt) load_k(j0 + jj + 1);
+            load_v(j0 + jj);
+        }
+#undef STAGE_FILL
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================================
+        if (leader) {
+            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
+            const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
+            const uint32_t id_pos = idesc_tf32(2 * kTile, kTile, false), id_neg = idesc_tf32(2 * kTile, kTile, true);
+            const uint32_t id_g = idesc_tf32(2 * kTile, gN, false);
+            const int kc_neg = g.C1p / kChunk;
+#define MMA4_SS(dcol, ad, bd, id, acc0)                                                    \
+            do {                                                                           \
+                mma_tf32_ss_pair(dcol, (ad), (bd), id, acc0);                              \
+                mma_tf32_ss_pair(dcol, (ad) + 2, (bd) + 2, id, 1);                         \
+                mma_tf32_ss_pair(dcol, (ad) + 4, (bd) + 4, id, 1);                         \
+                mma_tf32_ss_pair(dcol, (ad) + 6, (bd) + 6, id, 1);                         \
+            } while (0)
+            auto gemm_d = [&](int jj) {
+                const int buf = jj & 1;
+                const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
+                for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
+                    mbar_wait(&full[slot], ph, 12);
+                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
+                    const int ss = slot;
+                    RING_ADVANCE();
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int u = 0; u < kUPS; ++u) {
+                            const int kc = kc0 + u;
+                            if (kc < nkc) {
+                                const uint64_t ub = sd + (uint64_t)u * kUnitDesc;
+                                const uint64_t ad = kResident ? q_desc + (uint64_t)kc * kBoxDesc : ub;
+                                const uint64_t bd = kResident ? ub : ub + kBoxDesc;
+                                MMA4_SS(dcol, ad, bd, (kc >= kc_neg ? id_neg : id_pos), kc != 0);
+                            }
+                        }
+                        umma_commit_pair(&empty[ss]);
+                        if (kc0 + kUPS >= nkc) umma_commit_pair(&d_full[buf]);
+                    }
+                    __syncwarp();
+                }
+                (void)kKDesc;
+            };
+            auto gemm_g = [&](int jj, bool last) {
+                const int buf = jj & 1;
+                const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
+                mbar_wait(&p_full[buf], (jj >> 1) & 1, 15);
+                for (int jc0 = 0; jc0 < kTile / kChunk; jc0 += 2) {
+                    mbar_wait(&full[slot], ph, 13);
+                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
+                    const int ss = slot;
+                    RING_ADVANCE();
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t acol = pcol + (uint32_t)((jc0 + h) * kChunk);
+                            const uint64_t bd = sd + (uint64_t)h * kBoxDesc;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts_pair(tmem, acol + ks * 8, bd + 2 * ks, id_g, (jj | (jc0 + h) | ks) != 0);
+                        }
+                        umma_commit_pair(&empty[ss]);
+                        if (last && jc0 + 2 >= kTile / kChunk) umma_commit_pair(o_full);
+                    }
+                    __syncwarp();
+                }
+            };
+            if (kResident) mbar_wait(q_full, 0, 16);
+            gemm_d(0);
+            for (int jj = 0; jj < nt; ++jj) {
+                if (jj + 1 < nt) gemm_d(jj + 1);
+                gemm_g(jj, jj == nt - 1);
+            }
+#undef MMA4_SS
+        }
+    } else {
+        EpiCtx c;
+        c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.tmem = tmem;
+        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T; c.weight_below = 0;
+        epilogue_role<true, true>(g, a, c);
+    }
+#undef RING_ADVANCE
+
+    fence_before_sync();
+    cluster_sync();                         // the leader's MMAs read the peer's shared / tensor memory until the very end
+    if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -677,12 +922,12 @@ EncodeTiledFn encode_fn() {
 }
 
 // rows x cols fp32 matrix, row-major; box = 128 rows x 32 columns, 128-byte swizzle
-int make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t cols) {
+int make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t cols, int box_rows = kTile) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) DSRL_FAIL(DSRL_ERR_CUDA, "FA(position): cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)kTile};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -752,6 +997,29 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     a.loss_div = Z;
     a.grad_scale = (float)(2.0 / Z);
     const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
+    if (need_grad && g.pair) {
+        // both channel groups have the same width when there are two (C1p == C2p) or the V box height would differ per group
+        const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];
+        if (same) {
+            CUtensorMap tm_k, tm_v;
+            if ((rc = make_map(&tm_k, Fpm, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2))) return rc;
+            if ((rc = make_map(&tm_v, Fcm, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2))) return rc;
+            if (g.q_resident) {
+                if ((rc = opt_in_smem(fa_pos_tiles_pair<true>, g.pair_smem_bytes))) return rc;
+                fa_pos_tiles_pair<true><<<grid, kThreads, g.pair_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
+            } else {
+                if ((rc = opt_in_smem(fa_pos_tiles_pair<false>, g.pair_smem_bytes))) return rc;
+                fa_pos_tiles_pair<false><<<grid, kThreads, g.pair_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
+            }
+            DSRL_LAUNCH_CHECK();
+            if (g.jsplit > 1) {
+                if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
+                fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, Fcm, nrm, a.grad_scale, a.dP);
+                DSRL_LAUNCH_CHECK();
+            }
+            return DSRL_OK;
+        }
+    }
 #define LAUNCH_TILES(GR, SP, RS)                                                                          \
     do {                                                                                                  \
         if ((rc = opt_in_smem(fa_pos_tiles<GR, SP, RS>, g.smem_bytes))) return rc;                        \

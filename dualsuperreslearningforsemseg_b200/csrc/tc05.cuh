@@ -43,8 +43,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // Waits for the phase with the given parity.  A pipeline bug must not hang the GPU: after ~4e9 cycles the kernel
 // reports which barrier starved and traps (the launch then fails with an error instead of never finishing).
 __device__ __noinline__ void mbar_timeout(uint64_t *bar, uint32_t parity, int tag) {
-    printf("[dsrl] mbarrier timeout: block (%d,%d,%d) thread %d tag %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
-           threadIdx.x, tag, smem_u32(bar), parity);
+    printf("[dsrl] mbarrier timeout: block (%d,%d,%d) thread %d tag %d bar 0x%x parity %u state 0x%llx\n", blockIdx.x, blockIdx.y, blockIdx.z,
+           threadIdx.x, tag, smem_u32(bar), parity, *reinterpret_cast<volatile unsigned long long *>(bar));
     __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = 0) {
@@ -147,6 +147,57 @@ __device__ __forceinline__ float round_tf32(float x) {   // round-to-nearest TF3
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+
+// ---- CTA pair (cluster of 2, tcgen05 cta_group::2) ------------------------------------------------------------------
+// The even CTA of the pair (the "leader") issues every MMA; an M = 256 instruction takes rows 0-127 of A / D from the
+// leader's shared / tensor memory and rows 128-255 from the peer's at the SAME offsets, and one half of the B rows from
+// each CTA.  Barriers the leader waits on live in the leader; peers reach them through shared::cluster addresses.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster window address -> leader's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {   // one warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// box lands in THIS CTA's shared memory; the bytes are counted on the LEADER's copy of `bar`
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+// arrives on `bar` at the same offset in every CTA of `mask` once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar, uint16_t mask = 3) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {      // arrive on the leader's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 }  // namespace tc
