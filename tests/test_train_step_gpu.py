@@ -1,7 +1,7 @@
 """BASELINE configs[4] in miniature: a stage-3 DSRL training step (harness/) with the drop-in FALoss against the same step
-with a plain-PyTorch restatement of the reference FALoss (oracle/fa_torch_port.py) -- identical weights and inputs.
-The FA term and the gradients it sends into the two feature transformers must agree; CE / MSE are bit-identical by
-construction.  Also runs the metrics on the step's logits."""
+with a plain-PyTorch restatement of the reference FALoss (oracle/fa_torch_port.py) applied to the same forward graph.  The FA term and the
+gradients it sends into the feature transformers / SISR decoder must agree.  Also runs a full optimiser step and the
+metrics on the step's logits."""
 import numpy as np
 import pytest
 import torch
@@ -22,28 +22,28 @@ def test_stage3_step_matches_pytorch_fa():
     from oracle import seg_oracle
     dev = torch.device("cuda", 0)
     img, org, target = synthetic_batch(2, dev, 1)
-    ours, ref = Stage3Step(FALoss(), dev), Stage3Step(TorchFALoss(), dev)
-    ref.core.load_state_dict(ours.core.state_dict())
-    # dropout makes two training-mode forwards differ: draw the same masks
-    outs = []
-    for step in (ours, ref):
-        torch.manual_seed(7)
-        ce, mse, fa, o = step.losses(img, org, target)
-        (ce + mse + fa).backward()
-        outs.append((ce, mse, fa, o))
-    (ce1, mse1, fa1, o1), (ce2, mse2, fa2, _) = outs
-    assert float(ce1) == float(ce2) and float(mse1) == float(mse2)
-    assert o1[2].shape == (2, 1, 64, 128)                                     # the FA inputs of the real model
-    assert abs(float(fa1) - float(fa2)) <= 1e-4 * abs(float(fa2)), (float(fa1), float(fa2))
-    for name in ("SSSR_feature_transformer.0.weight", "SISR_feature_transformer.0.weight"):
-        g1 = dict(ours.core.named_parameters())[name].grad
-        g2 = dict(ref.core.named_parameters())[name].grad
+    step = Stage3Step(FALoss(), dev)
+    # ONE forward graph (cuDNN may pick different algorithms for two forwards, so two model copies are not bit-comparable);
+    # both FA implementations are applied to the same feature-transformer outputs and back-propagated through it
+    ce, mse, fa_ours, o = step.losses(img, org, target)
+    assert o[2].shape == (2, 1, 64, 128) and o[3].shape == (2, 1, 64, 128)    # the FA inputs of the real model
+    fa_ref = TorchFALoss()(o[2], o[3])
+    assert abs(float(fa_ours) - float(fa_ref)) <= 1e-4 * abs(float(fa_ref)), (float(fa_ours), float(fa_ref))
+    params = dict(step.core.named_parameters())
+    names = ("SSSR_feature_transformer.0.weight", "SISR_feature_transformer.0.weight", "SISR_decoder.0.weight")
+    g_ours = torch.autograd.grad(fa_ours, [params[n] for n in names], retain_graph=True)
+    g_ref = torch.autograd.grad(fa_ref, [params[n] for n in names], retain_graph=True)
+    for n, g1, g2 in zip(names, g_ours, g_ref):
         rel = float((g1 - g2).norm() / g2.norm())
-        assert rel <= 1e-3, (name, rel)
-    # a full optimiser step runs, and the metrics take the step's logits without leaving the device
-    ours(img, org, target)
+        assert rel <= 1e-3, (n, rel)
+    # the whole objective back-propagates and a full optimiser step runs (train_or_resume.py:438-445)
+    (ce + mse + fa_ours).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in step.core.parameters())
+    losses = step(img, org, target)
+    assert all(np.isfinite(float(x)) for x in losses)
+    # the metrics take the step's logits without leaving the device (train_or_resume.py:476-481)
     m, a = mIoU(19), Accuracy()
-    pred = torch.argmax(o1[0].detach(), dim=1)
+    pred = torch.argmax(o[0].detach(), dim=1)
     m.update(pred, target, target != 255)
     a.update(pred, target, target != 255)
     mo, ao = seg_oracle.MIoUOracle(19), seg_oracle.AccuracyOracle()
