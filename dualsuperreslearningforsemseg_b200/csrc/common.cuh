@@ -95,6 +95,11 @@ __device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
+__device__ __forceinline__ float ldg_stream_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint16_t ldg_stream_u16(const void *p) {
     uint16_t r;
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));

@@ -19,6 +19,9 @@
 //   fa_pos_tiles    one CTA per (128-row tile i, channel group, sample): warp 0 = TMA producer, warp 1 = MMA issuer,
 //                   warps 2..5 = epilogue (|D| sum, sign tile, final normalisation Jacobian).  TMEM: columns
 //                   [0,256) gradient accumulator, [256,512) two D / sign tiles (double buffered).
+//   fa_pos_tiles_pair  the same for a cluster of two CTAs (two row tiles) with tcgen05 cta_group::2, M = 256: each CTA
+//                   supplies half of every B tile, which halves the B-operand shared-memory traffic (the hot variant)
+//   fa_pos_jacobian sums the partial accumulators when the column range of a row tile is split over several CTAs
 //   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)
 #include <cuda.h>
 #include <stdlib.h>
@@ -148,17 +151,36 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
     const int py = valid ? p / g.w : 0, px = valid ? p - py * g.w : 0;
     const float inv_kk = 1.f / (float)(g.k * g.k);
 
-    for (int c = warp; c < g.Kc; c += 8) {
-        const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
-        float v = 0.f;
-        if (valid && cc < Cr) {
-            const float *x = (br ? x2 : x1) + (((size_t)b * Cr + cc) * g.H + (size_t)py * g.k) * g.W + (size_t)px * g.k;
-            float s = 0.f;
-            for (int dy = 0; dy < g.k; ++dy)
-                for (int dx = 0; dx < g.k; ++dx) s += __ldg(x + (size_t)dy * g.W + dx);
-            v = s * inv_kk;
+    if (g.k == 1) {
+        // no pooling: one coalesced 128-byte row per (channel, strip); eight independent loads in flight per warp
+        const size_t hw = (size_t)g.H * g.W;
+        for (int c8 = warp * 8; c8 < g.Kc; c8 += 64) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c8 + u;
+                const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
+                const bool ok = valid && c < g.Kc && cc < Cr;
+                const float *x = (br ? x2 : x1) + ((size_t)b * Cr + (ok ? cc : 0)) * hw + (ok ? p : 0);
+                v[u] = ok ? ldg_stream_f32(x) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c8 + u < g.Kc) T[(c8 + u) * 33 + lane] = v[u];
         }
-        T[c * 33 + lane] = v;
+    } else {
+        for (int c = warp; c < g.Kc; c += 8) {
+            const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
+            float v = 0.f;
+            if (valid && cc < Cr) {
+                const float *x = (br ? x2 : x1) + (((size_t)b * Cr + cc) * g.H + (size_t)py * g.k) * g.W + (size_t)px * g.k;
+                float s = 0.f;
+                for (int dy = 0; dy < g.k; ++dy)
+                    for (int dx = 0; dx < g.k; ++dx) s += __ldg(x + (size_t)dy * g.W + dx);
+                v = s * inv_kk;
+            }
+            T[c * 33 + lane] = v;
+        }
     }
     __syncthreads();
     if (warp < 2) {                                   // per-position L2 norm over the channels of branch `warp`
@@ -217,7 +239,6 @@ struct EpiCtx {
     int *flag;
     uint32_t tmem;
     int itile, js, grp, b, j0, nt, gN, gbeg, T;
-    int weight_below;     // forward-only CTA pairs: weight of a tile below the diagonal (0)
 };
 
 template <bool kGrad, bool kPair>
@@ -620,7 +641,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         // ===================================== epilogue warps =====================================
         EpiCtx c;
         c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.tmem = tmem;
-        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T; c.weight_below = 0;
+        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
         epilogue_role<kGrad, false>(g, a, c);
     }
 #undef RING_ADVANCE
@@ -749,7 +770,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================================
         if (leader) {
-            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
+            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
             const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
             const uint32_t id_pos = idesc_tf32(2 * kTile, kTile, false), id_neg = idesc_tf32(2 * kTile, kTile, true);
             const uint32_t id_g = idesc_tf32(2 * kTile, gN, false);
@@ -786,7 +807,6 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     }
                     __syncwarp();
                 }
-                (void)kKDesc;
             };
             auto gemm_g = [&](int jj, bool last) {
                 const int buf = jj & 1;
@@ -823,7 +843,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     } else {
         EpiCtx c;
         c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.tmem = tmem;
-        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T; c.weight_below = 0;
+        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
         epilogue_role<true, true>(g, a, c);
     }
 #undef RING_ADVANCE
