@@ -251,6 +251,19 @@ def bench_fa_train(args, rank, world, dev, peaks):
     barrier(world)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
 
+    # what a user runs today on the same GPU: the reference algorithm in eager PyTorch (BASELINE.md plan item 3)
+    from oracle import fa_torch_port
+    for _ in range(3):
+        fa_torch_port.fwd_bwd(a_c, b_c, FA_K)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(20):
+        fa_torch_port.fwd_bwd(a_c, b_c, FA_K)
+    g1.record()
+    torch.cuda.synchronize()
+    eager_ms = g0.elapsed_time(g1) / 20
+
     step_ms = ms / args.steps
     alg_bytes = 2 * 2 * int(np.prod(FA_TRAIN_SHAPE)) * 4          # read x1,x2 + write dx1,dx2
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
@@ -265,7 +278,8 @@ def bench_fa_train(args, rank, world, dev, peaks):
                    "shape": list(FA_TRAIN_SHAPE), "subsample_factor": FA_K, "pairs_per_gpu": pairs,
                    "l2": "flushed before every step (256 MiB fill, outside the per-step event pair)",
                    "launch": f"CUDA graph replay of the step's {launches_per_step} kernels (FAPlan: fused forward + backward)", "parallelism": f"dp{world} (batch shard, no data-path collective)",
-                   "ms_per_step_l2_warm": ms_hot / args.steps, "loss": loss_val},
+                   "ms_per_step_l2_warm": ms_hot / args.steps, "loss": loss_val,
+                   "pytorch_eager_same_gpu_ms": eager_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic().get("fa_train"),
                      "peak_source": peaks["source"],

@@ -179,3 +179,23 @@ def test_rejects_unsupported():
     b = torch.zeros((1, 8, 16, 16), device="cuda")
     with pytest.raises(_lib.DsrlError):
         FALoss(subsample_factor=1, affinity="position", reduction="none")(b, b)
+
+
+def test_dead_positions_follow_the_clamp():
+    """Positions whose pooled feature vector is all zero (post-ReLU features with few channels): the normalisation clamps
+    the norm at 1e-12, so Fh = 0 there, the position's affinities are 0 and its gradient is G / eps like the oracle's."""
+    x1, x2 = pos_inputs((1, 3, 16, 16), (1, 3, 16, 16), 9)
+    x1[0, :, 2, 3] = 0.0
+    x1[0, :, 7, :4] = 0.0
+    x2[0, :, 5, 5] = 0.0
+    dead1 = (np.abs(x1).sum(axis=1) == 0).sum()
+    assert dead1 >= 5
+    ol, o1, o2 = fa_oracle.fa_position(x1, x2, 1, "mean")
+    loss, d1, d2 = run(x1, x2, 1, "mean", precision="fp32")
+    assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
+    # gradients at dead positions are O(1/eps): compare the live and the dead part separately
+    live1 = np.abs(x1).sum(axis=1, keepdims=True) > 0
+    live2 = np.abs(x2).sum(axis=1, keepdims=True) > 0
+    for d, o, live in ((d1, o1, live1), (d2, o2, live2)):
+        assert relnorm(d * live, o * live) <= RANDOM_GRAD_FP32, relnorm(d * live, o * live)
+        assert relnorm(d * ~live, o * ~live) <= RANDOM_GRAD_FP32, relnorm(d * ~live, o * ~live)
