@@ -32,6 +32,7 @@ __all__ = [
     "fa_reference",
     "fa_position",
     "round_tf32",
+    "fa_position_rows",
     "allpairs_l1_sorted",
 ]
 
@@ -255,3 +256,31 @@ def fa_position(x1, x2, k: int = 8, reduction: str = "mean", grad_out=None, need
         return unpool_grad(dF.reshape(B, C, h, w), k, H, W)
 
     return loss, back(P1, Fh1, n1, Gh1), back(P2, Fh2, n2, Gh2)
+
+
+def fa_position_rows(x1, x2, rows, k: int = 8, reduction: str = "mean", operand_rounding: str | None = None):
+    """Sampled check for maps too large for :func:`fa_position` in seconds (N = 32768, C = 256): for sample 0 and the given
+    position indices ``rows`` return ``(sum_j |D_ij| over those rows, dX1[0, :, rows], dX2[0, :, rows])`` -- the gradient of
+    a position only needs that position's affinity row, so these columns are exact.  k must be 1 (no pooling)."""
+    if k != 1:
+        raise ValueError("fa_position_rows: only k = 1")
+    x1 = np.asarray(x1, dtype=np.float64)
+    x2 = np.asarray(x2, dtype=np.float64)
+    B, _, H, W = x1.shape
+    N = H * W
+    rows = np.asarray(rows, dtype=np.int64)
+    F1, Fh1, n1 = _position_normalise(x1[:1])
+    F2, Fh2, n2 = _position_normalise(x2[:1])
+    if operand_rounding == "tf32":
+        Fh1, Fh2 = round_tf32(Fh1), round_tf32(Fh2)
+    Z = float(B * N * N) if reduction == "mean" else 1.0
+    D = Fh1[0][:, rows].T @ Fh1[0] - Fh2[0][:, rows].T @ Fh2[0]          # (len(rows), N)
+    D[np.arange(rows.size), rows] = 0.0
+    Sg = np.sign(D) / Z
+    out = [np.abs(D).sum()]
+    for Fh, nrm, sgn in ((Fh1, n1, 2.0), (Fh2, n2, -2.0)):
+        Gh = sgn * (Fh[0] @ Sg.T)                                       # (C, len(rows)): dL/dFh at the sampled positions
+        Fr = Fh[0][:, rows]
+        proj = (Fr * Gh).sum(axis=0, keepdims=True)
+        out.append((Gh - Fr * proj) / nrm[0][:, rows])
+    return tuple(out)

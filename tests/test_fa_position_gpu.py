@@ -199,3 +199,19 @@ def test_dead_positions_follow_the_clamp():
     for d, o, live in ((d1, o1, live1), (d2, o2, live2)):
         assert relnorm(d * live, o * live) <= RANDOM_GRAD_FP32, relnorm(d * live, o * live)
         assert relnorm(d * ~live, o * ~live) <= RANDOM_GRAD_FP32, relnorm(d * ~live, o * ~live)
+
+
+def test_full_size_c256_sampled_rows():
+    """BASELINE configs[3] at its bench size for one sample (N = 32768, C = 256 per branch: two channel groups, streamed
+    operands, CTA pairs, column split).  The float64 oracle is evaluated on 384 sampled positions (their gradient columns
+    are exact); the loss is cross-checked between the gradient kernel, the forward-only kernel and the 3xTF32 path."""
+    x1, x2 = pos_margin_inputs(1, 256, 256, 128, 256, 54321)
+    rows = np.random.default_rng(3).choice(128 * 256, size=384, replace=False)
+    _, o1, o2 = fa_oracle.fa_position_rows(x1, x2, rows, 1, "mean")
+    loss, d1, d2 = run(x1, x2, 1, "mean", precision="tf32")
+    g1 = d1[0].reshape(256, -1)[:, rows]
+    g2 = d2[0].reshape(256, -1)[:, rows]
+    assert relnorm(g1, o1) <= GRAD_RTOL and relnorm(g2, o2) <= GRAD_RTOL, (relnorm(g1, o1), relnorm(g2, o2))
+    loss_ng, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="tf32")
+    loss_32, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="fp32")
+    assert abs(loss - loss_ng) <= 1e-6 * abs(loss) and abs(loss - loss_32) <= LOSS_RTOL * abs(loss), (loss, loss_ng, loss_32)

@@ -122,3 +122,15 @@ def test_tf32_operand_rounding_variant():
     lt, t1, _ = fa_oracle.fa_position(x1, x2, 1, "mean", operand_rounding="tf32")
     assert abs(lt - le) <= 1e-4 * abs(le)
     assert 1e-5 < relerr(t1, g1) < 5e-2
+
+
+def test_position_sampled_rows_match_full_oracle():
+    x1, x2 = pos_inputs((2, 12, 8, 16), (2, 7, 8, 16), 21)
+    ol, o1, o2 = fa_oracle.fa_position(x1, x2, 1, "mean")
+    rows = np.array([0, 5, 17, 100, 127])
+    part, g1, g2 = fa_oracle.fa_position_rows(x1, x2, rows, 1, "mean")
+    assert relerr(g1, o1[0].reshape(12, -1)[:, rows]) < 1e-12
+    assert relerr(g2, o2[0].reshape(7, -1)[:, rows]) < 1e-12
+    allrows, _, _ = fa_oracle.fa_position_rows(x1[:1], x2[:1], np.arange(128), 1, "sum")
+    l0, _, _ = fa_oracle.fa_position(x1[:1], x2[:1], 1, "sum", need_grad=False)
+    np.testing.assert_allclose(allrows, l0, rtol=1e-12)
