@@ -102,12 +102,12 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         const double cost = (double)((ctas * s + sms - 1) / sms) / s;
         if (cost < 0.96 * best) { best = cost; g.jsplit = s; }
     }
-    // CTA-pair form: single TF32 pass, an even number of row tiles
-    g.pair = !g.split && (g.tiles % 2 == 0);
+    // CTA-pair form: needs an even number of row tiles
+    g.pair = g.tiles % 2 == 0;
     if (const char *e = getenv("DSRL_POS_PAIR")) { if (atoi(e) == 0) g.pair = 0; }
     {
         const int stage = g.q_resident ? 4 * (kBoxBytes / 2) : 2 * (kBoxBytes + kBoxBytes / 2);
-        const size_t qbytes = g.q_resident ? (size_t)g.nkc * kBoxBytes : 0;
+        const size_t qbytes = g.q_resident ? (size_t)qboxes * kBoxBytes : 0;
         g.pair_stages = (int)((kSmemBudget - 1024 - kSmemAux - qbytes) / stage);
         if (g.pair_stages > 6) g.pair_stages = 6;
         g.pair_smem_bytes = 1024 + qbytes + (size_t)g.pair_stages * stage + kSmemAux;
@@ -663,18 +663,20 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 // p_full.
 constexpr int kPairKBox = kBoxBytes / 2;           // 64 rows of K_j per CTA
 
-template <bool kResident>
+template <bool kSplit, bool kResident>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
     extern __shared__ unsigned char smraw[];
     const uint32_t raw = smem_u32(smraw);
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
-    // per-CTA stage: resident -> 4 K boxes (32 KB) or 2 V boxes; streamed -> 2 x (Q box 16 KB + K box 8 KB) = 48 KB or 2 V boxes
+    // per-CTA operand boxes of one 32-channel chunk: [Q hi 16 KB, Q lo 16 KB,] K hi 8 KB [, K lo 8 KB]; a stage holds
+    // 32 KB (operand rows resident) or 48 KB (streamed) of them, or two V boxes
+    constexpr int kParts = kSplit ? 2 : 1;
+    constexpr int kUnitBytes = (kResident ? 0 : kParts * kBoxBytes) + kParts * kPairKBox;
     constexpr int kStageBytes = kResident ? 4 * kPairKBox : 2 * (kBoxBytes + kPairKBox);
-    constexpr int kUPS = kResident ? 4 : 2;                         // 32-channel chunks per stage
-    constexpr int kUnitBytes = kResident ? kPairKBox : kBoxBytes + kPairKBox;
-    const int S = g.pair_stages, nkc = g.nkc, nq = kResident ? nkc : 0;
+    constexpr int kUPS = kStageBytes / kUnitBytes;                  // chunks per stage: 4, 2 (split) | 2, 1 (split)
+    const int S = g.pair_stages, nkc = g.nkc, nq = kResident ? nkc * kParts : 0;
     unsigned char *qreg = sm;
     unsigned char *ring = sm + (size_t)nq * kBoxBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
@@ -695,7 +697,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int nt = T / g.jsplit, j0 = js * nt;
     const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], vrows = gN / 2;                   // this CTA's share of the V_j channels
     const uint32_t vbytes = (uint32_t)vrows * kChunk * 4;
-    const int row_q = b * g.Npad + itile * kTile;
+    const int row_q = b * g.Npad + itile * kTile, lo_rows = g.B * g.Npad;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_q);
@@ -722,7 +724,8 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (kResident) {
             if (elect_one()) {
                 if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nq * kBoxBytes);
-                for (int kc = 0; kc < nq; ++kc) tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, kc * kChunk, row_q);
+                for (int kc = 0; kc < nq; ++kc)
+                    tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
             }
             __syncwarp();
         }
@@ -746,8 +749,12 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     for (int u = 0; u < nu; ++u) {
                         const int c0 = (kc0 + u) * kChunk;
                         unsigned char *d = dst + (size_t)u * kUnitBytes;
-                        if (!kResident) { tma_load_2d_pair(d, &tm_q, bar, c0, row_q); d += kBoxBytes; }
-                        tma_load_2d_pair(d, &tm_k, bar, c0, row_k);
+                        if (!kResident) {
+                            tma_load_2d_pair(d, &tm_q, bar, c0, row_q); d += kBoxBytes;
+                            if (kSplit) { tma_load_2d_pair(d, &tm_q, bar, c0, row_q + lo_rows); d += kBoxBytes; }
+                        }
+                        tma_load_2d_pair(d, &tm_k, bar, c0, row_k); d += kPairKBox;
+                        if (kSplit) tma_load_2d_pair(d, &tm_k, bar, c0, row_k + lo_rows);
                     }
                 });
             }
@@ -770,7 +777,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================================
         if (leader) {
-            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
+            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
             const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
             const uint32_t id_pos = idesc_tf32(2 * kTile, kTile, false), id_neg = idesc_tf32(2 * kTile, kTile, true);
             const uint32_t id_g = idesc_tf32(2 * kTile, gN, false);
@@ -797,9 +804,16 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                             const int kc = kc0 + u;
                             if (kc < nkc) {
                                 const uint64_t ub = sd + (uint64_t)u * kUnitDesc;
-                                const uint64_t ad = kResident ? q_desc + (uint64_t)kc * kBoxDesc : ub;
-                                const uint64_t bd = kResident ? ub : ub + kBoxDesc;
-                                MMA4_SS(dcol, ad, bd, (kc >= kc_neg ? id_neg : id_pos), kc != 0);
+                                const uint64_t a_hi = kResident ? q_desc + (uint64_t)kc * kBoxDesc : ub;
+                                const uint64_t a_lo = kResident ? q_desc + (uint64_t)(nkc + kc) * kBoxDesc : ub + kBoxDesc;
+                                const uint64_t b_hi = kResident ? ub : ub + kParts * kBoxDesc;
+                                const uint64_t b_lo = b_hi + kKDesc;
+                                const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
+                                MMA4_SS(dcol, a_hi, b_hi, id, kc != 0);
+                                if (kSplit) {
+                                    MMA4_SS(dcol, a_hi, b_lo, id, 1);
+                                    MMA4_SS(dcol, a_lo, b_hi, id, 1);
+                                }
                             }
                         }
                         umma_commit_pair(&empty[ss]);
@@ -1022,15 +1036,16 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
         const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];
         if (same) {
             CUtensorMap tm_k, tm_v;
-            if ((rc = make_map(&tm_k, Fpm, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2))) return rc;
+            if ((rc = make_map(&tm_k, Fpm, (uint64_t)(1 + g.split) * B * g.Npad, (uint64_t)g.Kc, kTile / 2))) return rc;
             if ((rc = make_map(&tm_v, Fcm, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2))) return rc;
-            if (g.q_resident) {
-                if ((rc = opt_in_smem(fa_pos_tiles_pair<true>, g.pair_smem_bytes))) return rc;
-                fa_pos_tiles_pair<true><<<grid, kThreads, g.pair_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
-            } else {
-                if ((rc = opt_in_smem(fa_pos_tiles_pair<false>, g.pair_smem_bytes))) return rc;
-                fa_pos_tiles_pair<false><<<grid, kThreads, g.pair_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
-            }
+#define LAUNCH_PAIR(SP, RS)                                                                               \
+            do {                                                                                          \
+                if ((rc = opt_in_smem(fa_pos_tiles_pair<SP, RS>, g.pair_smem_bytes))) return rc;          \
+                fa_pos_tiles_pair<SP, RS><<<grid, kThreads, g.pair_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a); \
+            } while (0)
+            if (g.split) { if (g.q_resident) LAUNCH_PAIR(true, true); else LAUNCH_PAIR(true, false); }
+            else         { if (g.q_resident) LAUNCH_PAIR(false, true); else LAUNCH_PAIR(false, false); }
+#undef LAUNCH_PAIR
             DSRL_LAUNCH_CHECK();
             if (g.jsplit > 1) {
                 if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
