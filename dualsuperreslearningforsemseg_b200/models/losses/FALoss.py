@@ -13,8 +13,11 @@ All arithmetic runs in hand-written sm_100a kernels behind the C-ABI of ``libdsr
 PyTorch/CPU fallback: CPU tensors raise.
 
 Keyword-only extensions (defaults preserve the reference behaviour):
-  affinity='reference' | 'position'   'position' = the paper's N x N position affinity (not in the reference)
-  precision=None | 'fp32' | 'tf32' | 'bf16'   tensor-core operand precision for 'position'
+  affinity='reference' | 'position'   'position' = the paper's N x N position affinity (not in the reference; the two
+                                      inputs may then differ in C; reduction 'mean' or 'sum')
+  precision=None | 'tf32' | 'fp32'    tensor-core arithmetic of 'position': 'tf32' (default) = one tcgen05 kind::tf32 pass
+                                      with FP32 accumulation; 'fp32' = 3xTF32 split (hi*hi + hi*lo + lo*hi), about FP32
+                                      accuracy at ~2x the time.  The reference semantics always runs in FP32 FMA.
 """
 from __future__ import annotations
 
@@ -26,7 +29,7 @@ import torch
 from ... import _lib
 
 _RED = {"none": _lib.REDUCE_NONE, "mean": _lib.REDUCE_MEAN, "sum": _lib.REDUCE_SUM}
-_PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "bf16": _lib.PREC_BF16}
+_PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32}
 _MODE = {"reference": _lib.FA_REFERENCE, "position": _lib.FA_POSITION}
 
 _size_cache = {}

@@ -48,9 +48,9 @@ enum dsrl_fa_mode {
 enum dsrl_reduction { DSRL_REDUCE_NONE = 0, DSRL_REDUCE_MEAN = 1, DSRL_REDUCE_SUM = 2 }; /* FALoss.py:32-34 */
 
 enum dsrl_precision {
-    DSRL_PREC_FP32 = 0,   /* CUDA-core FP32 FMA (reference mode always uses this) */
-    DSRL_PREC_TF32 = 1,   /* tcgen05 kind::tf32, FP32 accumulate in TMEM (position mode default) */
-    DSRL_PREC_BF16 = 2    /* tcgen05 kind::f16 with BF16 operands */
+    DSRL_PREC_FP32 = 0,   /* reference mode: CUDA-core FP32 FMA (always); position mode: 3xTF32 split on tcgen05 */
+    DSRL_PREC_TF32 = 1,   /* position mode default: one tcgen05 kind::tf32 pass, FP32 accumulate in TMEM */
+    DSRL_PREC_BF16 = 2    /* reserved: rejected with DSRL_ERR_UNSUPPORTED (a single BF16 pass misses the loss tolerance) */
 };
 
 enum dsrl_dtype { DSRL_U8 = 0, DSRL_I32 = 1, DSRL_I64 = 2 };
@@ -70,7 +70,8 @@ uint64_t dsrl_launch_count(void);
 size_t dsrl_fa_saved_bytes(int mode, int B, int C1, int C2, int H, int W, int k);
 size_t dsrl_fa_workspace_bytes(int mode, int B, int C1, int C2, int H, int W, int k);
 
-/* Forward.  x1, x2: (B, C, H, W) fp32.  k = subsample_factor (FALoss.py:14,23-24).
+/* Forward.  x1: (B, C1, H, W), x2: (B, C2, H, W) fp32.  k = subsample_factor (FALoss.py:14,23-24).
+ * `workspace` and `saved` must be 16-byte aligned; position mode may launch a cluster kernel (CTA pairs).
  * loss_out: 1 float for mean/sum; (B, C, n*n) floats, n = (W/k)^2, for DSRL_REDUCE_NONE (FALoss.py:27-34).
  * need_grad != 0 also prepares the gradient in `saved` (fused forward+backward work, one pass over the
  * pairs).  For mean/sum the local (this rank's) sum of |.| terms is left as a double at saved[0..8) so that
