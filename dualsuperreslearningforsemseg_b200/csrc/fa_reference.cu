@@ -766,6 +766,8 @@ struct FusedBranch {
     float S[kFusedMaxW * kFusedMaxW];
     int cnt[kFusedMaxW * kFusedMaxW];
     float Gs[kFusedMaxW * kFusedLda];
+    float sorted[kFusedMaxW * kFusedMaxW];     // this branch's S values, ascending
+    double pre[kFusedMaxW * kFusedMaxW + 1];   // their exclusive prefix sums
     float xs[32], xl[32];
     double scratch[34];
 };
@@ -859,37 +861,63 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
     __syncthreads();
 
     TSTAMP(4);
-    // 4. all pairs (FALoss.py:27-34): group `br` owns the values of branch `br` and streams the other branch
+    // 4. all pairs (FALoss.py:27-34), exact in O(n log n) instead of n^2: each group sorts its own branch's values
+    //    (bitonic: shuffles inside a warp, 6 shared-memory exchanges across warps) and prefix-sums them in fp64; then
+    //    every value x of the OTHER branch is ranked with two binary searches:
+    //        lt = #{y < x}, le = #{y <= x}:   sum_j sign(x - y_j) = lt - (n - le)        (exact integer)
+    //                                         sum_j |x - y_j|     = x (lt - gt) - pre[lt] + (pre[n] - pre[le])
+    //    A NaN anywhere (dead channel, sigma = 0) makes the loss NaN and every sign 0, as torch's sign() does.
     double local = 0.0;
-    if (ht < n && (br == 0 || need_grad)) {
-        const float *Y = sb[1 - br].S;
-        const float xv = fb.S[ht];
-        int c = 0;
-        float acc = 0.f;
-        if (br == 0) {
-#pragma unroll 2
-            for (int j = 0; j < n; j += 4) {            // n = w*w; the tail is handled below when w is odd
-                if (j + 4 > n) break;
-                const float4 y = *reinterpret_cast<const float4 *>(Y + j);
-                sign_acc(c, xv, y.x); sign_acc(c, xv, y.y); sign_acc(c, xv, y.z); sign_acc(c, xv, y.w);
-                acc += fabsf(xv - y.x); acc += fabsf(xv - y.y); acc += fabsf(xv - y.z); acc += fabsf(xv - y.w);
-            }
-        } else {
-#pragma unroll 2
-            for (int j = 0; j < n; j += 4) {
-                if (j + 4 > n) break;
-                const float4 y = *reinterpret_cast<const float4 *>(Y + j);
-                sign_acc(c, xv, y.x); sign_acc(c, xv, y.y); sign_acc(c, xv, y.z); sign_acc(c, xv, y.w);
-            }
-        }
+    {
+        const int lane = ht & 31;
+        float v = ht < n ? fb.S[ht] : INFINITY;
+        const bool has_nan = __syncthreads_or(ht < n && v != v) != 0;
 #pragma unroll 1
-        for (int j = n & ~3; j < n; ++j) {
-            const float y = Y[j];
-            sign_acc(c, xv, y);
-            if (br == 0) acc += fabsf(xv - y);
+        for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll 1
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                float o;
+                if (j >= 32) {                                   // partner in another warp: through shared memory
+                    fb.sorted[ht] = v;
+                    grp.sync();
+                    o = fb.sorted[ht ^ j];
+                    grp.sync();
+                } else {
+                    o = __shfl_xor_sync(0xffffffffu, v, j);
+                }
+                const bool keep_min = ((ht & k) == 0) == ((ht & j) == 0);
+                v = keep_min ? fminf(v, o) : fmaxf(v, o);
+            }
         }
-        fb.cnt[ht] = c;
-        local = (double)acc;
+        fb.sorted[ht] = v;
+        // exclusive prefix sums of the sorted values (the +inf padding sits at the end and is never read)
+        double p = ht < n ? (double)v : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, p, o);
+            if (lane >= o) p += t;
+        }
+        if (lane == 31) fb.scratch[ht >> 5] = p;
+        grp.sync();
+        double base = 0.0;
+        for (int wq = 0; wq < (ht >> 5); ++wq) base += fb.scratch[wq];
+        fb.pre[ht + 1] = base + p;
+        if (ht == 0) fb.pre[0] = 0.0;
+        __syncthreads();                                         // both branches sorted and summed
+
+        if (ht < n && (br == 0 || need_grad)) {
+            const FusedBranch &ob = sb[1 - br];
+            const float x = fb.S[ht];
+            int lo = 0, hi = n;                                  // lt: first index with y >= x
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ob.sorted[mid] < x) lo = mid + 1; else hi = mid; }
+            const int lt = lo;
+            hi = n;                                              // le: first index with y > x
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ob.sorted[mid] <= x) lo = mid + 1; else hi = mid; }
+            const int le = lo, gt = n - le;
+            fb.cnt[ht] = has_nan ? 0 : lt - gt;
+            if (br == 0)
+                local = has_nan ? (double)NAN : (double)x * (double)(lt - gt) - ob.pre[lt] + (ob.pre[n] - ob.pre[le]);
+        }
     }
     TSTAMP(5);
     if (br == 0) {

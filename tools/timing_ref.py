@@ -1,0 +1,12 @@
+"""Phase clocks of fa_ref_fused_small (needs a -DDSRL_FUSED_TIMING build: DSRL_B200_LIB=tools/libdsrl_timing.so)."""
+import sys, torch, numpy as np
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+from _inputs import fa_inputs
+from dualsuperreslearningforsemseg_b200.functional import FAPlan
+x1, x2 = fa_inputs((6, 1, 64, 128), "relu", 54321)
+a, b = torch.from_numpy(x1).cuda(), torch.from_numpy(x2).cuda()
+plan = FAPlan((6, 1, 64, 128), subsample_factor=8)
+for _ in range(5):
+    plan.forward(a, b, True); torch.cuda.synchronize()
+    tm = plan.ws.view(torch.int64)[64:73].cpu().numpy()
+    print("phase cycles (pool, M, sigma, S, pairs, partial, grad, finish):", np.diff(tm), "total", tm[8] - tm[0])
