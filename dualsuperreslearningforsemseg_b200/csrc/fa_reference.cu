@@ -306,14 +306,14 @@ __device__ __noinline__ double group_sum_d(double v, double *scratch, int gtid, 
 }
 
 __device__ __noinline__ float top_singular_warp(const float *sA, int rs, int cs, int m, int L, float *M0, float *M1,
-                                                float *xs, float *xl) {
+                                                float *xs, float *xl, int squarings) {
     // fp32 throughout: sigma only needs ~1e-6 relative (the loss tolerance is 1e-4, the reference itself is fp32) and
     // this single-warp dependent chain is the critical path of the whole forward -- fp64 shuffles/rsqrt tripled it.
     const int lane = threadIdx.x & 31;
     const int qi = 32 / m, qj = 32 - qi * m, i0 = lane / m, j0 = lane - i0 * m;   // (i, j) of entry o advance by (qi, qj) per 32
     float *cur = M0, *nxt = M1;
 #pragma unroll 1
-    for (int sq = 0; sq < 6; ++sq) {
+    for (int sq = 0; sq < squarings; ++sq) {
         float tr = lane < m ? cur[lane * m + lane] : 0.f;
         tr = warp_sum(tr);
         if (!(tr > 0.f)) break;
@@ -835,8 +835,33 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
     }
     grp.sync();
     TSTAMP(2);
+    // six trace-normalised squarings of M by the whole group (one entry per thread, m*m <= 256): M^(64) is numerically
+    // rank one unless the spectral gap is tiny; one warp then polishes the vectors with power steps on V itself
+    float *mcur = fb.M, *mnxt = fb.M + m * m;
+    {
+        const int mi = ht / m, mj = ht - mi * m;
+#pragma unroll 1
+        for (int sq = 0; sq < 6; ++sq) {
+            float tr = 0.f;
+            for (int d = 0; d < m; ++d) tr += mcur[d * m + d];
+            if (!(tr > 0.f)) break;                              // zero / NaN matrix: same decision in every thread
+            const float inv = __frcp_rn(tr);
+            if (ht < m * m) {
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+                for (int k = 0; k + 1 < m; k += 2) {
+                    s0 = fmaf(mcur[mi * m + k], mcur[k * m + mj], s0);
+                    s1 = fmaf(mcur[mi * m + k + 1], mcur[(k + 1) * m + mj], s1);
+                }
+                if (m & 1) s0 = fmaf(mcur[mi * m + m - 1], mcur[(m - 1) * m + mj], s0);
+                mnxt[ht] = (s0 + s1) * inv * inv;
+            }
+            grp.sync();
+            float *t = mcur; mcur = mnxt; mnxt = t;
+        }
+    }
     if (ht < 32) {
-        const double sg = top_singular_warp(fb.P, rs, cs, m, L, fb.M, fb.M + m * m, fb.xs, fb.xl);
+        const double sg = top_singular_warp(fb.P, rs, cs, m, L, mcur, mnxt, fb.xs, fb.xl, 0);
         if (ht == 0) fb.scratch[33] = sg;
     }
     grp.sync();
