@@ -775,7 +775,19 @@ inline bool fused_ok(const RefGeom &g) { return g.w <= kFusedMaxW && g.h <= kFus
 
 __device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, int W, int k, bool vec4) {
     float s = 0.f;
-    if (vec4) {
+    if (vec4 && k == 8) {
+        // the model's subsample factor: all 16 vector loads of the 8 x 8 window in flight at once (the inputs are cold in
+        // HBM; issued one row at a time the pooling phase was eight dependent memory latencies long)
+        float4 v[16];
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) {
+            const float4 *r = reinterpret_cast<const float4 *>(base + (size_t)dy * W);
+            v[2 * dy] = __ldg(r);
+            v[2 * dy + 1] = __ldg(r + 1);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { s += v[q].x; s += v[q].y; s += v[q].z; s += v[q].w; }
+    } else if (vec4) {
 #pragma unroll 1
         for (int dy = 0; dy < k; ++dy) {
             const float4 *r = reinterpret_cast<const float4 *>(base + (size_t)dy * W);
