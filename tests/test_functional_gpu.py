@@ -1,0 +1,50 @@
+"""functional.FAPlan (allocation-free C-ABI access) against the autograd drop-in, eagerly and under CUDA-graph replay,
+for both FA semantics (the position path launches TMA / cluster kernels: they must be capturable)."""
+import pytest
+import torch
+
+from _inputs import fa_inputs, pos_margin_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _autograd(x1, x2, k, go, **kw):
+    from dualsuperreslearningforsemseg_b200.models.losses import FALoss
+    a = x1.clone().requires_grad_(True)
+    b = x2.clone().requires_grad_(True)
+    loss = FALoss(subsample_factor=k, **kw)(a, b)
+    (loss * go).backward()
+    return loss.detach(), a.grad, b.grad
+
+
+@pytest.mark.parametrize("mode", ["reference", "position_tf32", "position_fp32"])
+def test_plan_matches_autograd_and_replays_in_a_graph(mode):
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    dev = torch.device("cuda", 0)
+    if mode == "reference":
+        x1, x2 = fa_inputs((6, 1, 64, 128), "relu", 54321)
+        k, kw = 8, {}
+    else:
+        x1, x2 = pos_margin_inputs(2, 64, 64, 32, 32, 54321)
+        k, kw = 1, {"affinity": "position", "precision": mode.split("_")[1]}
+    x1, x2 = torch.from_numpy(x1).to(dev), torch.from_numpy(x2).to(dev)
+    go = torch.full((), 0.5, device=dev)
+    ref_loss, ref_d1, ref_d2 = _autograd(x1, x2, k, go, **kw)
+    plan = FAPlan(tuple(x1.shape), tuple(x2.shape), subsample_factor=k, device=dev, **kw)
+    loss, d1, d2 = plan.forward_backward(x1, x2, go)
+    torch.cuda.synchronize()
+    assert float(loss) == float(ref_loss) and torch.equal(d1, ref_d1) and torch.equal(d2, ref_d2)
+    # capture the step once, then replay it on new inputs written into the captured buffers
+    sx1, sx2 = x1.clone(), x2.clone()
+    plan.forward_backward(sx1, sx2, go)                      # eager warm-up on the static buffers
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        plan.forward_backward(sx1, sx2, go)
+    y1, y2 = x2.clone(), x1.clone()                          # swapped branches: loss identical, gradients swap and flip roles
+    sx1.copy_(y1)
+    sx2.copy_(y2)
+    graph.replay()
+    torch.cuda.synchronize()
+    l2, e1, e2 = _autograd(y1, y2, k, go, **kw)
+    assert float(plan.loss) == float(l2) and torch.equal(plan.dx1, e1) and torch.equal(plan.dx2, e2)
