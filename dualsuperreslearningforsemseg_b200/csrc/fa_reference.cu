@@ -13,7 +13,9 @@
 //
 // Kernels (general path, any n that fits):
 //   fa_ref_prepare   grid (B*C, 2 branches): pool -> one-sided Jacobi for sigma,u1,v1 -> S; zeroes the counters
-//   fa_ref_pairs     grid (tiles, 2 passes, B*C): brute-force all-pairs, atomics only on int32 counters
+//   fa_ref_pairs_sorted  n >= 8192: exact O(n log n) all-pairs (sort + fp64 prefix sums + rank searches), one CTA per
+//                    (b, c, side, chunk of 16384 sorted values)
+//   fa_ref_pairs     smaller n: grid (tiles, 2 passes, B*C): brute-force all-pairs, atomics only on int32 counters
 //   fa_ref_grad      grid (B*C, 2 branches): G^ = A^(G+G^T), spectral-norm Jacobian, pooled gradient; loss finish
 //   fa_ref_unpool    backward proper: dX = grad_out * dP / k^2 spread over the k x k windows (float4 stores)
 //   fa_ref_none_fwd / fa_ref_none_pairs: reduction='none' (the (B,C,n^2) tensor is the API's output there)
@@ -599,6 +601,104 @@ __global__ void __launch_bounds__(kPairsBlock) fa_ref_pairs(RefGeom g, RefSaved 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// all pairs, exact in O(n log n): sort one side, prefix-sum it in fp64, rank the other side.  The sorted side is cut into
+// chunks of <= 16384 values (one CTA's shared memory); ranks and sums add over chunks.  For every x, per chunk:
+//     lt = #{y < x}, le = #{y <= x}, gt = n_chunk - le
+//     sum_j sign(x - y_j) = lt - gt (exact integer)        sum_j |x - y_j| = x (lt - gt) - pre[lt] + (pre[n] - pre[le])
+// A NaN anywhere in either operand (dead channel) makes the loss NaN and every sign 0, as torch's sign() does.
+// (sigma = 0 turns the WHOLE map of a (b, c, branch) into NaN, so a chunk-local check sees it.)
+// grid (direction, B*C, chunk): direction 0 ranks branch 1 against sorted branch 2 (and owns the loss), 1 the reverse.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 1024, kSortChunk = 16384, kSortMinN = 8192;
+inline int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+inline int sort_chunks(int n) { return (n + kSortChunk - 1) / kSortChunk; }
+inline int sort_chunk_len(int n) { const int c = sort_chunks(n); return (n + c - 1) / c; }
+inline size_t sorted_smem_bytes(int m) { return align_up((size_t)next_pow2(m) * 4, 16) + ((size_t)m + 1) * 8 + 40 * 8; }
+
+__global__ void __launch_bounds__(kSortThreads) fa_ref_pairs_sorted(RefGeom g, RefSaved so, unsigned char *__restrict__ saved,
+                                                                   double *__restrict__ partials, int chunk_len, int P) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float *sy = reinterpret_cast<float *>(smraw);
+    double *pre = reinterpret_cast<double *>(smraw + align_up((size_t)P * 4, 16));
+    double *scratch = pre + chunk_len + 1;                        // [34] + totals
+    const int dir = blockIdx.x, bc = blockIdx.y, ch = blockIdx.z, nx = g.n, tid = threadIdx.x;
+    const int y0 = ch * chunk_len, n = min(chunk_len, nx - y0);  // this CTA's chunk of the sorted side
+    const float *X = reinterpret_cast<const float *>(saved + so.S) + ((size_t)dir * g.BC + bc) * nx;
+    const float *Y = reinterpret_cast<const float *>(saved + so.S) + ((size_t)(1 - dir) * g.BC + bc) * nx + y0;
+    int *cnt = reinterpret_cast<int *>(saved + so.cnt) + ((size_t)dir * g.BC + bc) * nx;
+    const bool single = gridDim.z == 1;
+
+    int nan = 0;
+    for (int i = tid; i < P; i += kSortThreads) {
+        const float y = i < n ? Y[i] : INFINITY;
+        sy[i] = y;
+        nan |= (y != y);
+    }
+    for (int i = tid; i < nx; i += kSortThreads) { const float x = X[i]; nan |= (x != x); }
+    const bool has_nan = __syncthreads_or(nan) != 0;              // also orders the stores above
+
+    // bitonic sort of P values: pair t of stride j is (i, i | j), i = t with a zero inserted at bit log2(j)
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += kSortThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), q = i | j;
+                const float a = sy[i], b = sy[q];
+                if ((a > b) == ((i & k) == 0)) { sy[i] = b; sy[q] = a; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // exclusive fp64 prefix sums: each thread owns a contiguous run, runs are chained by a block scan of their totals
+    const int run = (n + kSortThreads - 1) / kSortThreads, r0 = min(n, tid * run), r1 = min(n, r0 + run);
+    double mine = 0.0;
+    for (int i = r0; i < r1; ++i) mine += (double)sy[i];
+    double incl = mine;                                           // inclusive scan over threads: warp, then across warps
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) scratch[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        double w = scratch[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        scratch[lane] = w;                                        // inclusive totals of warps 0..lane
+    }
+    __syncthreads();
+    double acc = (wid ? scratch[wid - 1] : 0.0) + incl - mine;    // sum of everything before this thread's run
+    for (int i = r0; i < r1; ++i) { pre[i] = acc; acc += (double)sy[i]; }
+    if (r1 == n && r0 < n) pre[n] = acc;
+    if (n == 0 && tid == 0) pre[0] = 0.0;
+    __syncthreads();
+
+    double local = 0.0;
+    for (int i = tid; i < nx; i += kSortThreads) {
+        const float x = X[i];
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sy[mid] < x) lo = mid + 1; else hi = mid; }
+        const int lt = lo;
+        hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sy[mid] <= x) lo = mid + 1; else hi = mid; }
+        const int le = lo, gt = n - le;
+        const int c = has_nan ? 0 : lt - gt;
+        if (single) cnt[i] = c; else if (c) atomicAdd(&cnt[i], c);          // counters were zeroed by fa_ref_prepare
+        if (dir == 0) local += (double)x * (double)(lt - gt) - pre[lt] + (pre[n] - pre[le]);
+    }
+    if (dir == 0) {
+        __syncthreads();
+        const double tot = block_sum(local, scratch);
+        if (tid == 0) partials[(size_t)bc * gridDim.z + ch] = has_nan ? (double)NAN : tot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // grad: pooled-resolution gradient for unit upstream gradient, and the loss finish
 // ---------------------------------------------------------------------------------------------------------------
 struct GradSmem { size_t A, Gs, uv, scratch, total; int gs_in_smem; };
@@ -1057,7 +1157,8 @@ size_t fa_ref_workspace_bytes(int B, int C, int H, int W, int k) {
     RefGeom g;
     if (!make_geom(B, C, H, W, k, g)) return 0;
     PairsPlan p = make_pairs_plan(g);
-    const size_t partials = (size_t)g.BC * p.owner_tiles * p.ysplits * sizeof(double);
+    const size_t brute = (size_t)g.BC * p.owner_tiles * p.ysplits, sorted = (size_t)g.BC * sort_chunks(g.n);
+    const size_t partials = (brute > sorted ? brute : sorted) * sizeof(double);
     const size_t gfl = 2 * (size_t)g.BC * g.n * sizeof(float);  // reduction='none' backward
     return align_up(partials > gfl ? partials : gfl, 256) + 256;
 }
@@ -1097,8 +1198,17 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
         return DSRL_OK;  // the gradient needs the upstream tensor: all of it happens in backward
     }
 
-    PairsPlan plan = make_pairs_plan(g);
     double *partials = static_cast<double *>(ws);
+    const double Zs = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
+    if (g.n >= kSortMinN) {      // exact O(n log n) all-pairs (smaller maps: the n^2 stream over many CTAs has less latency)
+        const int nch = sort_chunks(g.n), len = sort_chunk_len(g.n);
+        const size_t smem = sorted_smem_bytes(len);
+        if ((rc = opt_in_smem(fa_ref_pairs_sorted, smem))) return rc;
+        fa_ref_pairs_sorted<<<dim3(need_grad ? 2 : 1, g.BC, nch), kSortThreads, smem, st>>>(g, so, saved, partials, len, next_pow2(len));
+        DSRL_LAUNCH_CHECK();
+        return launch_grad(g, so, saved, nullptr, (float)(1.0 / Zs), partials, g.BC * nch, Zs, loss_out, need_grad, st);
+    }
+    PairsPlan plan = make_pairs_plan(g);
     dim3 grid(plan.owner_tiles * plan.ysplits, need_grad ? 2 : 1, g.BC);
     if (plan.R == 4) fa_ref_pairs<4><<<grid, kPairsBlock, 0, st>>>(g, so, saved, partials, plan);
     else fa_ref_pairs<1><<<grid, kPairsBlock, 0, st>>>(g, so, saved, partials, plan);

@@ -78,6 +78,22 @@ def test_large_maps_against_sorted_oracle(shape, k):
     assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize("shape", [(2, 1, 256, 512), (2, 1, 1024, 1024), (2, 1, 512, 1152)])
+def test_dead_channel_on_every_all_pairs_path(shape):
+    """sigma = 0 (an all-zero pooled map) must give a NaN loss, NaN gradient for the dead (b, c) of the dead branch and an
+    exactly-zero gradient for the same (b, c) of the other branch (torch's sign(NaN) = 0) -- on the n^2 stream (n = 4096),
+    the single-chunk sorted path (n = 16384) and the chunked sorted path (n = 20736)."""
+    x1, x2 = fa_inputs(shape, "relu", 5)
+    x1[1, 0] = 0.0
+    loss, d1, d2 = run(x1, x2, 8, "mean")
+    assert np.isnan(float(loss))
+    assert np.isnan(d1[1, 0]).all() and np.isfinite(d1[0, 0]).all()
+    assert np.all(d2[1, 0] == 0.0) and np.isfinite(d2[0, 0]).all() and np.abs(d2[0, 0]).max() > 0
+    # the live sample's gradients are those of the same inputs without the dead one, rescaled by the batch size
+    _, e1, e2 = run(x1[:1], x2[:1], 8, "mean")
+    assert relnorm(2.0 * d1[0], e1[0]) <= 1e-5 and relnorm(2.0 * d2[0], e2[0]) <= 1e-5
+
+
 def test_size_independent_properties_at_training_shape():
     """BASELINE config 2 shape.  (i) the all-pairs L1 is symmetric in its arguments; (ii) spectral normalisation
     makes the loss invariant to a positive rescaling of either input, hence <dX, X> = 0; (iii) backward is
