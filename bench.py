@@ -264,6 +264,23 @@ def bench_fa_train(args, rank, world, dev, peaks):
     torch.cuda.synchronize()
     eager_ms = g0.elapsed_time(g1) / 20
 
+    # BASELINE configs[0] (the reference's CPU-runnable case) on the GPU: 1a = literal flow, 1b = 32 x 64 pooled positions
+    from _inputs import fa_inputs
+    cfg0 = {}
+    for name, shape in (("cfg1a_1x1x64x128", (1, 1, 64, 128)), ("cfg1b_1x1x256x512", (1, 1, 256, 512))):
+        u, v = (torch.from_numpy(t).to(dev) for t in fa_inputs(shape, "relu", SEED))
+        pl = FAPlan(shape, subsample_factor=FA_K, device=dev)
+        for _ in range(3):
+            pl.forward_backward(u, v, go)
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(20):
+            pl.forward_backward(u, v, go)
+        h1.record()
+        torch.cuda.synchronize()
+        cfg0[name] = {"pairs": fa_pairs(shape, FA_K), "gpu_ms_fwd_bwd": h0.elapsed_time(h1) / 20, "loss": float(pl.loss.item())}
+
     step_ms = ms / args.steps
     alg_bytes = 2 * 2 * int(np.prod(FA_TRAIN_SHAPE)) * 4          # read x1,x2 + write dx1,dx2
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
@@ -279,7 +296,7 @@ def bench_fa_train(args, rank, world, dev, peaks):
                    "l2": "flushed before every step (256 MiB fill, outside the per-step event pair)",
                    "launch": f"CUDA graph replay of the step's {launches_per_step} kernels (FAPlan: fused forward + backward)", "parallelism": f"dp{world} (batch shard, no data-path collective)",
                    "ms_per_step_l2_warm": ms_hot / args.steps, "loss": loss_val,
-                   "pytorch_eager_same_gpu_ms": eager_ms},
+                   "pytorch_eager_same_gpu_ms": eager_ms, "configs0_on_gpu": cfg0},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic().get("fa_train"),
                      "peak_source": peaks["source"],
@@ -294,9 +311,12 @@ def bench_fa_train(args, rank, world, dev, peaks):
     return res
 
 
-def cpu_fa_train(budget_s=12.0, threads=None):
-    """The reference's CPU path, via the torch port in oracle/, on the host cores."""
+def cpu_fa_train(budget_s=10.0, threads=None):
+    """The reference's CPU path, via the torch port in oracle/, on the host cores (BASELINE.md plan items 2-3):
+    headline = configs[1] with all threads; `by_config` adds configs[0] (1a literal flow, 1b = 32x64 positions) and the
+    single-thread times (best of a few calls each)."""
     from oracle import fa_torch_port
+    from _inputs import fa_inputs
     x1h, x2h = fa_train_inputs()
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -310,9 +330,30 @@ def cpu_fa_train(budget_s=12.0, threads=None):
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= 2000:
             break
-    return {"value": fa_pairs(FA_TRAIN_SHAPE, FA_K) * n / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
-            "ms_per_step": dt / n * 1e3,
-            "sample": f"{n} fwd+bwd calls of oracle/fa_torch_port.py (PyTorch-CPU port of FALoss.py:8-34) on the full configs[1] batch"}
+    out = {"value": fa_pairs(FA_TRAIN_SHAPE, FA_K) * n / dt / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+           "ms_per_step": dt / n * 1e3,
+           "sample": f"{n} fwd+bwd calls of oracle/fa_torch_port.py (PyTorch-CPU port of FALoss.py:8-34) on the full configs[1] batch"}
+
+    def best_ms(shape, nthreads, reps):
+        torch.set_num_threads(nthreads)
+        u, v = (torch.from_numpy(t) for t in fa_inputs(shape, "relu", SEED))
+        fa_torch_port.fwd_bwd(u, v, FA_K)
+        best = 1e9
+        for _ in range(reps):
+            t1 = time.perf_counter()
+            fa_torch_port.fwd_bwd(u, v, FA_K)
+            best = min(best, time.perf_counter() - t1)
+        return best * 1e3
+
+    by = {}
+    for name, shape, reps in (("cfg1a_1x1x64x128", (1, 1, 64, 128), 20), ("cfg1b_1x1x256x512", (1, 1, 256, 512), 3),
+                              ("cfg2_6x1x64x128", FA_TRAIN_SHAPE, 20)):
+        by[name] = {"pairs": fa_pairs(shape, FA_K), "best_ms_1_thread": best_ms(shape, 1, reps),
+                    f"best_ms_{threads}_threads": best_ms(shape, threads, reps)}
+    torch.set_num_threads(threads)
+    out["by_config"] = by
+    out["host"] = {"cpu_count": os.cpu_count(), "torch": torch.__version__, "numpy": np.__version__}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
