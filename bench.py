@@ -40,6 +40,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 SEED = 54321  # the reference's RANDOM_SEED (settings.py:25)
+EXTRA_BUDGET_S = 420  # wall-clock budget of the secondary workloads + CPU baselines of a default run
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -884,7 +885,33 @@ def main():
     res = fn(args, rank, world, dev, peaks)
     torch.cuda.empty_cache()
     extra = {}
+
+    def emit():
+        if rank == 0:
+            r = dict(res)
+            out = {"metric": r.pop("metric"), "value": r.pop("value"), "unit": r.pop("unit"), "n_gpus": world,
+                   "steps": r.pop("steps", args.steps), "warmup": args.warmup, "ms_per_step": r.pop("ms_per_step"),
+                   "higher_is_better": True, "scaling": r.pop("scaling"), "vs_baseline": None, "dtype": r.pop("dtype"),
+                   "data": "synthetic", **r}
+            if extra:
+                out["extra"] = extra
+            print(json.dumps(out), flush=True)
+
+    # The primary measurement is complete here.  The secondary workloads must never cost it: if one of them wedges (a rank
+    # that failed inside a collective leaves the others waiting), a watchdog prints the line without them and exits 0.
+    def bail():
+        extra["watchdog"] = {"error": f"secondary workloads exceeded {EXTRA_BUDGET_S} s; primary result printed without them"}
+        emit()
+        os._exit(0)
+
+    cpu_fn = {"fa_train": cpu_fa_train, "seg_counts": cpu_seg_counts, "fa_stress": cpu_fa_stress, "seg_logits": cpu_seg_logits}
+    if not args.no_extra and rank == 0 and world == 1:
+        res["cpu_baseline"] = cpu_fn[args.workload]()          # part of the primary line: before anything that could wedge
+    watchdog = threading.Timer(EXTRA_BUDGET_S, bail)
+    watchdog.daemon = True
     if not args.no_extra:
+        watchdog.start()
+
         def attempt(name, thunk):
             try:
                 extra[name] = thunk()
@@ -903,20 +930,11 @@ def main():
             attempt("fa_stress_c128", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=5, warmup=3, C=128, light=True))
             attempt("fa_stress_c256_3xtf32", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, precision="fp32", light=True))
         if rank == 0 and world == 1:
-            cpu_fn = {"fa_train": cpu_fa_train, "seg_counts": cpu_seg_counts, "fa_stress": cpu_fa_stress}
-            res["cpu_baseline"] = cpu_fn[args.workload]()
-            cpu_fn["seg_logits"] = cpu_seg_logits
             for name in ("fa_train", "seg_counts", "seg_logits"):
                 if name in extra and "error" not in extra[name]:
                     extra[name]["cpu_baseline"] = cpu_fn[name]()
-    if rank == 0:
-        out = {"metric": res.pop("metric"), "value": res.pop("value"), "unit": res.pop("unit"), "n_gpus": world,
-               "steps": res.pop("steps", args.steps), "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"),
-               "higher_is_better": True, "scaling": res.pop("scaling"), "vs_baseline": None, "dtype": res.pop("dtype"),
-               "data": "synthetic", **res}
-        if extra:
-            out["extra"] = extra
-        print(json.dumps(out), flush=True)
+        watchdog.cancel()
+    emit()
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
