@@ -169,14 +169,35 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
                 if (c8 + u < g.Kc) T[(c8 + u) * 33 + lane] = v[u];
         }
     } else {
+        // k x k mean (FALoss.py:23-24).  With k % 4 == 0 every window row is k/4 aligned 16-byte vectors and a warp's 32
+        // neighbouring windows form one contiguous run per input row; all vectors of up to 8 rows are issued before summing.
+        const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0;
         for (int c = warp; c < g.Kc; c += 8) {
             const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
             float v = 0.f;
             if (valid && cc < Cr) {
                 const float *x = (br ? x2 : x1) + (((size_t)b * Cr + cc) * g.H + (size_t)py * g.k) * g.W + (size_t)px * g.k;
                 float s = 0.f;
-                for (int dy = 0; dy < g.k; ++dy)
-                    for (int dx = 0; dx < g.k; ++dx) s += __ldg(x + (size_t)dy * g.W + dx);
+                if (vec4 && g.k == 8) {
+                    float4 r[16];
+#pragma unroll
+                    for (int dy = 0; dy < 8; ++dy) {
+                        const uint4 a = ldg_stream_u4(x + (size_t)dy * g.W), bq = ldg_stream_u4(x + (size_t)dy * g.W + 4);
+                        r[2 * dy] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+                        r[2 * dy + 1] = make_float4(__uint_as_float(bq.x), __uint_as_float(bq.y), __uint_as_float(bq.z), __uint_as_float(bq.w));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { s += r[q].x; s += r[q].y; s += r[q].z; s += r[q].w; }
+                } else if (vec4) {
+                    for (int dy = 0; dy < g.k; ++dy)
+                        for (int q = 0; q < g.k / 4; ++q) {
+                            const uint4 a = ldg_stream_u4(x + (size_t)dy * g.W + 4 * q);
+                            s += __uint_as_float(a.x); s += __uint_as_float(a.y); s += __uint_as_float(a.z); s += __uint_as_float(a.w);
+                        }
+                } else {
+                    for (int dy = 0; dy < g.k; ++dy)
+                        for (int dx = 0; dx < g.k; ++dx) s += __ldg(x + (size_t)dy * g.W + dx);
+                }
                 v = s * inv_kk;
             }
             T[c * 33 + lane] = v;
@@ -904,33 +925,55 @@ __global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *_
 // ---------------------------------------------------------------------------------------------------------------
 // backward proper
 // ---------------------------------------------------------------------------------------------------------------
+// One thread row (64 threads) per output row: the (b, c, y) decomposition and the source row are computed once per row,
+// the inner loop is a broadcast load + one 16-byte store (a per-element 64-bit div/mod version ran at 27 % of the HBM peak).
 template <int VEC>
-__global__ void fa_pos_unpool(PosGeom g, const float *__restrict__ dP, const float *__restrict__ grad_out,
-                              float *__restrict__ dx1, float *__restrict__ dx2) {
+__global__ void __launch_bounds__(256) fa_pos_unpool(PosGeom g, const float *__restrict__ dP, const float *__restrict__ grad_out,
+                                                      float *__restrict__ dx1, float *__restrict__ dx2) {
     const float scale = __ldg(grad_out) / (float)(g.k * g.k);
+    const long long rows1 = (long long)g.B * g.C1 * g.H, rows2 = (long long)g.B * g.C2 * g.H;
+    const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    if (row >= rows1 + rows2) return;
+    const int br = row >= rows1;
+    float *dx = br ? dx2 : dx1;
+    if (!dx) return;
+    const long long rr = br ? row - rows1 : row;
+    const int Cr = br ? g.C2 : g.C1;
+    const int y = (int)(rr % g.H);
+    const long long bcq = rr / g.H;
+    const int c = (int)(bcq % Cr), b = (int)(bcq / Cr);
+    const int py = y / g.k;
+    float *dst = dx + rr * g.W;
     const int wv = g.W / VEC;
-    const long long n1 = (long long)g.B * g.C1 * g.H * wv, n2 = (long long)g.B * g.C2 * g.H * wv;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2; idx += (long long)gridDim.x * blockDim.x) {
-        const int br = idx >= n1;
-        float *dx = br ? dx2 : dx1;
-        if (!dx) continue;
-        long long rr = br ? idx - n1 : idx;
-        const int Cr = br ? g.C2 : g.C1;
-        const int xv = (int)(rr % wv); rr /= wv;
-        const int y = (int)(rr % g.H); rr /= g.H;
-        const int c = (int)(rr % Cr);
-        const int b = (int)(rr / Cr);
-        const int py = y / g.k;
-        const float *src = dP + ((size_t)b * g.Kc + (br ? g.C1p : 0) + c) * g.Npad + (size_t)py * g.w;
-        float out[VEC];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-            const int px = (xv * VEC + q) / g.k;
-            out[q] = (py < g.h && px < g.w) ? src[px] * scale : 0.f;
+    if (py >= g.h) {                                           // rows dropped by the floor of the pooling
+        for (int xv = threadIdx.x; xv < wv; xv += blockDim.x) {
+            if (VEC == 4) reinterpret_cast<float4 *>(dst)[xv] = make_float4(0.f, 0.f, 0.f, 0.f); else dst[xv] = 0.f;
         }
-        float *dst = dx + (((size_t)b * Cr + c) * g.H + y) * g.W + (size_t)xv * VEC;
-        if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
-        else dst[0] = out[0];
+        return;
+    }
+    const float *src = dP + ((size_t)b * g.Kc + (br ? g.C1p : 0) + c) * g.Npad + (size_t)py * g.w;
+    const int k = g.k, w = g.w;
+    for (int xv = threadIdx.x; xv < wv; xv += blockDim.x) {
+        if (VEC == 4) {
+            const int x0 = xv * 4;
+            float4 o;
+            if (k == 1 && (w & 3) == 0) {                      // no pooling: a scaled copy, 16 bytes in, 16 bytes out
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src + x0));
+                o = x0 < w ? make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if (k % 4 == 0) {                           // the four outputs share one pooled cell
+                const int px = x0 / k;
+                const float v = px < w ? __ldg(src + px) * scale : 0.f;
+                o = make_float4(v, v, v, v);
+            } else {
+                const int p0 = x0 / k, p1 = (x0 + 1) / k, p2 = (x0 + 2) / k, p3 = (x0 + 3) / k;
+                o = make_float4(p0 < w ? __ldg(src + p0) * scale : 0.f, p1 < w ? __ldg(src + p1) * scale : 0.f,
+                                p2 < w ? __ldg(src + p2) * scale : 0.f, p3 < w ? __ldg(src + p3) * scale : 0.f);
+            }
+            reinterpret_cast<float4 *>(dst)[xv] = o;
+        } else {
+            const int px = xv / k;
+            dst[xv] = px < w ? __ldg(src + px) * scale : 0.f;
+        }
     }
 }
 
@@ -1091,11 +1134,12 @@ int fa_pos_backward(int precision, const float *, const float *, const void *sav
     const float *dP = reinterpret_cast<const float *>(static_cast<const unsigned char *>(saved_v) + so.dP);
     const bool v4 = (W % 4 == 0) && (!dx1 || (reinterpret_cast<uintptr_t>(dx1) & 15) == 0) &&
                     (!dx2 || (reinterpret_cast<uintptr_t>(dx2) & 15) == 0);
-    const long long total = (long long)B * (C1 + C2) * H * (W / (v4 ? 4 : 1));
-    const int threads = 256;
-    const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)device_sm_count() * 16);
-    if (v4) fa_pos_unpool<4><<<blocks, threads, 0, st>>>(g, dP, grad_out, dx1, dx2);
-    else fa_pos_unpool<1><<<blocks, threads, 0, st>>>(g, dP, grad_out, dx1, dx2);
+    const long long rows = (long long)B * (C1 + C2) * H;
+    const dim3 block(64, 4);
+    const long long blocks = (rows + block.y - 1) / block.y;
+    if (blocks > 0x7fffffffLL) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): gradient too large for one launch");
+    if (v4) fa_pos_unpool<4><<<(unsigned)blocks, block, 0, st>>>(g, dP, grad_out, dx1, dx2);
+    else fa_pos_unpool<1><<<(unsigned)blocks, block, 0, st>>>(g, dP, grad_out, dx1, dx2);
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
 }
