@@ -63,3 +63,15 @@ def test_argument_validation_happens_before_device_probe(lib):
     assert lib.dsrl_seg_counts(None, _lib.I64, p, _lib.U8, None, 1, 16, 19, 255, p, None) == _lib.ERR_BAD_ARG
     assert lib.dsrl_fa_forward(0, 0, p, p, 1, 1, 2, 8, 8, 8, 1, 1, p, p, 64, p, 64, None) == _lib.ERR_BAD_SHAPE
     assert lib.dsrl_fa_forward(7, 0, p, p, 1, 1, 1, 8, 8, 8, 1, 1, p, p, 64, p, 64, None) == _lib.ERR_BAD_ARG
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No silent fallback: with the shared library absent the first use raises and says how to build it."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from dualsuperreslearningforsemseg_b200 import _lib\n"
+            "try:\n    _lib.lib()\nexcept RuntimeError as e:\n    print('RAISED', 'no CPU or PyTorch fallback' in str(e))\n" % ROOT)
+    env = dict(os.environ, DSRL_B200_LIB=str(tmp_path / "nope.so"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr
