@@ -110,6 +110,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         const size_t qbytes = g.q_resident ? (size_t)qboxes * kBoxBytes : 0;
         g.pair_stages = (int)((kSmemBudget - 1024 - kSmemAux - qbytes) / stage);
         if (g.pair_stages > 6) g.pair_stages = 6;
+        if (const char *e = getenv("DSRL_POS_STAGES")) { const int v = atoi(e); if (v >= 2 && v < g.pair_stages) g.pair_stages = v; }   // tuning hook
         g.pair_smem_bytes = 1024 + qbytes + (size_t)g.pair_stages * stage + kSmemAux;
     }
     if (const char *force = getenv("DSRL_POS_JSPLIT")) {          // test hook: force 1, 2 or 4 (when it divides the tile count)
