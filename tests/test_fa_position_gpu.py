@@ -13,7 +13,8 @@ reproduces the GPU numbers to 4 digits).  Therefore:
     <= 1e-4 and gradients <= 1e-3 against the unrounded float64 oracle, for both precisions.  This is the parity gate.
     (With fewer than 128 channels per branch the margins of that construction are only ~2 sigma wide -- the cosine of
     two noisy vectors fluctuates like 1/sqrt(C) -- so a few 1e-5 of the entries are still ambiguous for the single
-    TF32 pass and its gradient bound there is 3e-3; the 3xTF32 path keeps 1e-3.)
+    TF32 pass; there it is held to 1e-3 against the oracle on the same rounded operands.  The 3xTF32 path keeps 1e-3
+    against the unrounded oracle everywhere.)
   * RANDOM inputs: loss <= 1e-4 (both precisions); gradients within the flip-limited bounds below, plus -- for
     the single TF32 pass -- agreement with the oracle fed the same TF32-rounded operands."""
 import numpy as np
@@ -82,6 +83,8 @@ CASES = [
     ((1, 256, 16, 32), (1, 256, 16, 32), 1, "mean"),
     ((2, 160, 16, 16), (2, 130, 16, 16), 1, "mean"),
     ((1, 32, 64, 64), (1, 32, 64, 64), 1, "mean"),
+    ((1, 256, 16, 16), (1, 20, 16, 16), 1, "mean"),      # two channel groups of different width: single-CTA kernel
+    ((1, 96, 12, 32), (1, 96, 12, 32), 1, "sum"),        # 3 row tiles: odd tile count, no CTA pairs
 ]
 
 
@@ -91,12 +94,19 @@ def test_margin_inputs_match_float64_oracle(s1, s2, k, red):
     x1, x2 = pos_margin_inputs(s1[0], s1[1], s2[1], s1[2], s1[3], 54321)
     go = 0.37
     ol, o1, o2 = fa_oracle.fa_position(x1, x2, k, red, grad_out=go)
+    tl, t1, t2 = fa_oracle.fa_position(x1, x2, k, red, grad_out=go, operand_rounding="tf32")
     for prec in ("fp32", "tf32"):
         loss, d1, d2 = run(x1, x2, k, red, go=go, precision=prec)
-        gtol = GRAD_RTOL if (prec == "fp32" or min(s1[1], s2[1]) >= 128) else 3e-3
+        # one TF32 pass with fewer than 128 channels: the margins of the construction are only ~2 sigma wide, a few 1e-5 of
+        # the entries stay ambiguous under operand rounding (C = 20: 1.3 % on that branch, reproduced to 4 digits by the
+        # rounded-operand oracle) -- there the kernel is held to 1e-3 against the oracle on the SAME rounded operands
+        tight = prec == "fp32" or min(s1[1], s2[1]) >= 128
         assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (prec, loss, ol)
-        assert relnorm(d1, o1) <= gtol, (prec, relnorm(d1, o1))
-        assert relnorm(d2, o2) <= gtol, (prec, relnorm(d2, o2))
+        if tight:
+            assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (prec, relnorm(d1, o1), relnorm(d2, o2))
+        else:
+            assert relnorm(d1, t1) <= GRAD_RTOL and relnorm(d2, t2) <= GRAD_RTOL, (prec, relnorm(d1, t1), relnorm(d2, t2))
+            assert relnorm(d1, o1) <= RANDOM_GRAD_TF32 and relnorm(d2, o2) <= RANDOM_GRAD_TF32
         loss_ng, _, _ = run(x1, x2, k, red, need_grad=False, precision=prec)
         assert abs(loss_ng - ol) <= LOSS_RTOL * abs(ol), (prec, loss_ng, ol)
 
