@@ -7,11 +7,13 @@
 //
 // This problem is latency / CUDA-core bound (K = h <= 32 at every shape the reference model produces), so it
 // runs in FP32 FMA -- TF32 would already flip enough sign() terms to miss the gradient tolerance -- and the
-// n^2 all-pairs tensor the reference materialises (FALoss.py:27-30) never exists: each CTA streams one side
-// through shared memory against register-resident values of the other side and keeps only
-//   sum |a_i - b_j|   (loss)            and            c_i = sum_j sign(a_i - b_j)   (exact int32, gradient).
+// n^2 all-pairs tensor the reference materialises (FALoss.py:27-30) never exists.  Only
+//   sum |a_i - b_j|   (loss)            and            c_i = sum_j sign(a_i - b_j)   (exact int32, gradient)
+// are kept, computed either exactly in O(n log n) (sort one side, fp64 prefix sums, rank the other side: the fused
+// training-shape kernel and maps with n >= 8192) or as an n^2 stream of one side through shared memory against
+// register-resident values of the other (mid-size maps, where many small CTAs have the lower latency).
 //
-// Kernels (general path, any n that fits):
+// Kernels (fa_ref_fused_small: the reference model's training shapes in ONE launch, see below; general path otherwise):
 //   fa_ref_prepare   grid (B*C, 2 branches): pool -> one-sided Jacobi for sigma,u1,v1 -> S; zeroes the counters
 //   fa_ref_pairs_sorted  n >= 8192: exact O(n log n) all-pairs (sort + fp64 prefix sums + rank searches), one CTA per
 //                    (b, c, side, chunk of 16384 sorted values)
@@ -854,8 +856,8 @@ __global__ void fa_ref_none_pairs(RefGeom g, RefSaved so, const unsigned char *_
 // ---------------------------------------------------------------------------------------------------------------
 // fused small-shape forward: everything for one (b, c) in ONE CTA (the reference model's training shapes:
 // pooled map h <= 32, w <= 16, n = w*w <= 256).  Two 256-thread groups handle the two branches concurrently on
-// their own named barriers (pool -> sigma,u1,v1 -> S), then group g runs all-pairs pass g, then each group
-// produces its branch's pooled gradient.  The loss is finished by the last CTA to arrive (self-resetting
+// their own named barriers (pool -> sigma,u1,v1 -> S), sort their own S, then group g ranks its values against the
+// other group's sorted S (all pairs in O(n log n)), then each group produces its branch's pooled gradient.  The loss is finished by the last CTA to arrive (self-resetting
 // atomicInc ticket), so forward is a single launch with no memset and a deterministic summation order.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kFusedMaxW = 16, kFusedMaxH = 32, kFusedLda = kFusedMaxW + 1;
