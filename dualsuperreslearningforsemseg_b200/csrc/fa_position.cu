@@ -42,12 +42,14 @@ constexpr int kBoxBytes = kTile * kChunk * 4;    // 16 KB: one TMA box (128 rows
 // a pipeline stage holds up to kSB boxes behind one full/empty barrier pair: 2 when the CTA's own operand rows are
 // resident in shared memory (little room left), 4 when everything is streamed (so one barrier round trip feeds >= 8 MMAs)
 __host__ __device__ constexpr int stage_boxes(bool resident) { return resident ? 2 : 4; }
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, each converting half of a tile's columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;   // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 constexpr int kMaxGroupCh = 256;    // gradient accumulator columns per CTA
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 256;     // first column of the two D / sign tiles
 constexpr size_t kSmemBudget = 227 * 1024;
-constexpr size_t kSmemAux = 1024;   // barriers, TMEM pointer, reduction scratch
+constexpr size_t kSmemAux = 1536;   // barriers, TMEM pointer, reduction scratch, projection halves
 
 struct PosGeom {
     int B, C1, C2, H, W, k, h, w, N, Npad, C1p, C2p, Kc, G;
@@ -257,8 +259,9 @@ struct PosArgs {
 // kPair: the barrier the MMA issuer waits on lives in the leader CTA of the pair.
 struct EpiCtx {
     uint64_t *d_full, *p_full, *o_full;
-    double *red;
+    double *red;          // [16]
     int *flag;
+    float *proj;          // [2][128] partial projections of the two column halves
     uint32_t tmem;
     int itile, js, grp, b, j0, nt, gN, gbeg, T;
 };
@@ -269,11 +272,13 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
     uint64_t *d_full = c.d_full, *p_full = c.p_full, *o_full = c.o_full;
     double *red = c.red;
     int *flag = c.flag;
+    float *projbuf = c.proj;
     const uint32_t tmem = c.tmem;
     const int itile = c.itile, js = c.js, grp = c.grp, b = c.b, j0 = c.j0, nt = c.nt, gN = c.gN, gbeg = c.gbeg, T = c.T;
     {
     // ===================================== epilogue warps =====================================
     const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
+    const int half = (warp - 2) >> 2;                          // which half of the columns / channel chunks this warp converts
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     double acc = 0.0;
     long long w_d = 0;
@@ -285,7 +290,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         const bool diag = j == itile;
         float tsum = 0.f;
 #pragma unroll 1
-        for (int cg = 0; cg < 4; ++cg) {
+        for (int cg = 2 * half; cg < 2 * half + 2; ++cg) {
             uint32_t v[32];
             const uint32_t taddr = tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32);
             tmem_ld32(taddr, v);
@@ -322,7 +327,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         fence_after_sync();
         const int row = itile * kTile + r;
         float *orow = a.opart + (((size_t)js * g.B + b) * g.Npad + row) * g.Kc + gbeg;
-        for (int c0 = 0; c0 < gN; c0 += 32) {
+        for (int c0 = 32 * half; c0 < gN; c0 += 64) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
             tmem_ld_wait();
@@ -342,7 +347,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
             const float n = a.nrm[((size_t)b * 2 + br) * g.Npad + row];
             const float sgn = br ? -a.grad_scale : a.grad_scale;           // dL/dFh2 = -2 Fh2 Sigma
             float proj = 0.f;
-            for (int c0 = cb; c0 < ce; c0 += 32) {
+            for (int c0 = cb + 32 * half; c0 < ce; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
                 tmem_ld_wait();
@@ -355,10 +360,15 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
                     proj = fmaf(f.w, __uint_as_float(v[e4 * 4 + 3]), proj);
                 }
             }
+            // the two column halves of a row each hold part of the projection
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            projbuf[half * kTile + r] = proj;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            proj = projbuf[r] + projbuf[kTile + r];
             const bool dead = !(n > 1e-12f);                                // F/eps branch of the clamp: no projection
             const float scale = sgn / fmaxf(n, 1e-12f);
             if (dead) proj = 0.f;
-            for (int c0 = cb; c0 < ce; c0 += 32) {
+            for (int c0 = cb + 32 * half; c0 < ce; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
                 tmem_ld_wait();
@@ -377,28 +387,31 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
 
     // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
     if (grp == 0) {
-        const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;                          // index among the epilogue threads
         double tot = warp_sum(acc);
         if (lane == 0) red[et >> 5] = tot;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (et == 0) {
-            a.partials[((size_t)js * gridDim.z + b) * T + itile] = red[0] + red[1] + red[2] + red[3];
+            double s = 0.0;
+            for (int i = 0; i < kEpiWarps; ++i) s += red[i];
+            a.partials[((size_t)js * gridDim.z + b) * T + itile] = s;
             __threadfence();
             const unsigned nparts = gridDim.x * gridDim.z;
             *flag = atomicInc(a.ticket, nparts - 1) == nparts - 1;      // self-resetting
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (*flag) {
             __threadfence();
             const int nparts = (int)(gridDim.x * gridDim.z);
             double s = 0.0;
-            for (int i = et; i < nparts; i += 128) s += __ldcg(a.partials + i);
+            for (int i = et; i < nparts; i += kEpiThreads) s += __ldcg(a.partials + i);
             s = warp_sum(s);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (lane == 0) red[4 + (et >> 5)] = s;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (lane == 0) red[kEpiWarps + (et >> 5)] = s;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             if (et == 0) {
-                const double all = red[4] + red[5] + red[6] + red[7];
+                double all = 0.0;
+                for (int i = 0; i < kEpiWarps; ++i) all += red[kEpiWarps + i];
                 *a.sum_out = all;
                 *a.loss_out = (float)(all / a.loss_div);
             }
@@ -431,8 +444,9 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     uint64_t *p_full = d_full + 2;      // [2] kGrad: sign tile written (epilogue -> MMA); else: D tile drained
     uint64_t *o_full = p_full + 2;      //     gradient accumulator complete      (MMA -> epilogue)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
-    double *red = reinterpret_cast<double *>(o_full + 2);               // [8]
-    int *flag = reinterpret_cast<int *>(red + 8);
+    double *red = reinterpret_cast<double *>(o_full + 2);               // [16]
+    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
+    float *projbuf = reinterpret_cast<float *>(flag + 2);               // [2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = g.tiles, js = kGrad ? blockIdx.x / T : 0;
@@ -449,7 +463,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         prefetch_tmap(&tm_cm);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], kEpiThreads); }
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -662,7 +676,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
     } else {
         // ===================================== epilogue warps =====================================
         EpiCtx c;
-        c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.tmem = tmem;
+        c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
         c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
         epilogue_role<kGrad, false>(g, a, c);
     }
@@ -709,7 +723,8 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     uint64_t *o_full = p_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
     double *red = reinterpret_cast<double *>(o_full + 2);
-    int *flag = reinterpret_cast<int *>(red + 8);
+    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
+    float *projbuf = reinterpret_cast<float *>(flag + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -727,7 +742,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         prefetch_tmap(&tm_v);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 256); }     // both CTAs' epilogue threads
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 2 * kEpiThreads); }     // both CTAs' epilogue threads
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -878,7 +893,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
     } else {
         EpiCtx c;
-        c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.tmem = tmem;
+        c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
         c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
         epilogue_role<true, true>(g, a, c);
     }
