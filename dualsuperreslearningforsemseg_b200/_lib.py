@@ -21,7 +21,7 @@ U8, I32, I64 = 0, 1, 2
 # every symbol include/dsrl_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
     "dsrl_version", "dsrl_last_error", "dsrl_launch_count",
-    "dsrl_fa_saved_bytes", "dsrl_fa_workspace_bytes", "dsrl_fa_forward", "dsrl_fa_backward",
+    "dsrl_fa_saved_bytes", "dsrl_fa_workspace_bytes", "dsrl_fa_forward", "dsrl_fa_backward", "dsrl_fa_forward_backward",
     "dsrl_seg_counts", "dsrl_seg_counts_from_logits",
 )
 
@@ -53,6 +53,8 @@ def _declare(lib):
     lib.dsrl_fa_forward.argtypes = [i, i, vp, vp, i, i, i, i, i, i, i, i, vp, vp, sz, vp, sz, vp]
     lib.dsrl_fa_backward.restype = i
     lib.dsrl_fa_backward.argtypes = [i, i, vp, vp, vp, sz, vp, vp, vp, i, i, i, i, i, i, i, vp, sz, vp]
+    lib.dsrl_fa_forward_backward.restype = i
+    lib.dsrl_fa_forward_backward.argtypes = [i, i, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, sz, vp, sz, vp]
     lib.dsrl_seg_counts.restype = i
     lib.dsrl_seg_counts.argtypes = [vp, i, vp, i, vp, i64, i64, i, i, vp, vp]
     lib.dsrl_seg_counts_from_logits.restype = i

@@ -9,6 +9,10 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
 int fa_ref_backward(const void *saved, size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C,
                     int H, int W, int k, int reduction, void *ws, size_t ws_bytes, cudaStream_t st);
 
+int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int H, int W, int k, int reduction,
+                            const float *grad_out, float *loss_out, float *dx1, float *dx2, void *saved, size_t saved_bytes,
+                            void *ws, size_t ws_bytes, cudaStream_t st);
+
 size_t fa_pos_saved_bytes(int B, int C1, int C2, int H, int W, int k);
 size_t fa_pos_workspace_bytes(int B, int C1, int C2, int H, int W, int k);
 int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k,
@@ -70,4 +74,25 @@ extern "C" int dsrl_fa_backward(int mode, int precision, const float *x1, const 
     if (mode == DSRL_FA_REFERENCE)
         return fa_ref_backward(saved, saved_bytes, grad_out, dx1, dx2, B, C1, H, W, k, reduction, workspace, workspace_bytes, st);
     return fa_pos_backward(precision, x1, x2, saved, saved_bytes, grad_out, dx1, dx2, B, C1, C2, H, W, k, reduction, workspace, workspace_bytes, st);
+}
+
+extern "C" int dsrl_fa_forward_backward(int mode, int precision, const float *x1, const float *x2, int B, int C1, int C2, int H,
+                                        int W, int k, int reduction, const float *grad_out, float *loss_out, float *dx1,
+                                        float *dx2, void *saved, size_t saved_bytes, void *workspace, size_t workspace_bytes,
+                                        dsrl_stream_t stream) {
+    int rc = check_mode(mode, C1, C2, reduction);
+    if (rc) return rc;
+    if (!x1 || !x2 || !grad_out || !loss_out || !saved || !workspace) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA forward_backward: null pointer");
+    if ((rc = require_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == DSRL_FA_REFERENCE) {
+        rc = fa_ref_forward_backward(x1, x2, B, C1, H, W, k, reduction, grad_out, loss_out, dx1, dx2, saved, saved_bytes, workspace,
+                                     workspace_bytes, st);
+        if (rc != DSRL_ERR_UNSUPPORTED) return rc;       // DSRL_OK or a real error; otherwise fall through to the two-call path
+    }
+    rc = dsrl_fa_forward(mode, precision, x1, x2, B, C1, C2, H, W, k, reduction, 1, loss_out, saved, saved_bytes, workspace,
+                         workspace_bytes, stream);
+    if (rc) return rc;
+    return dsrl_fa_backward(mode, precision, x1, x2, saved, saved_bytes, grad_out, dx1, dx2, B, C1, C2, H, W, k, reduction, workspace,
+                            workspace_bytes, stream);
 }

@@ -909,7 +909,8 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
                                                           RefSaved so, unsigned char *__restrict__ saved,
                                                           double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                           float g_scale, double loss_div, float *__restrict__ loss_out,
-                                                          int need_grad) {
+                                                          int need_grad, const float *__restrict__ grad_out,
+                                                          float *__restrict__ dx1, float *__restrict__ dx2) {
     __shared__ FusedBranch sb[2];
     __shared__ double red[34];
     __shared__ int is_last;
@@ -1088,8 +1089,29 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
         inner = group_sum_d(inner, fb.scratch, ht, 256, 1 + br);
         const float coef = (float)(inner / (sigma * sigma));
         float *gdA = reinterpret_cast<float *>(saved + so.dA) + ((size_t)br * g.BC + bc) * hw;
-        if (c0) gdA[ht] = gh0 / sigf - coef * du[qw] * dv[rw];
-        if (c1) gdA[ht + 256] = gh1 / sigf - coef * du[qw2] * dv[rw2];
+        const float ga0 = gh0 / sigf - coef * du[qw] * dv[rw];
+        const float ga1 = c1 ? gh1 / sigf - coef * du[qw2] * dv[rw2] : 0.f;
+        if (c0) gdA[ht] = ga0;
+        if (c1) gdA[ht + 256] = ga1;
+        // single-launch forward + backward (dsrl_fa_forward_backward): the upstream gradient is already known, so the
+        // pooled gradient is spread over its k x k windows here (host guarantees H % k == 0, W % k == 0, k % 4 == 0 and
+        // 16-byte aligned outputs) instead of by fa_ref_unpool
+        float *dx = br ? dx2 : dx1;
+        if (dx != nullptr) {
+            const float sc = __ldg(grad_out) / (float)(g.k * g.k);
+            float *base = dx + (size_t)bc * g.H * g.W;
+#pragma unroll 1
+            for (int cell = 0; cell < 2; ++cell) {
+                if (cell ? c1 : c0) {
+                    const float v = (cell ? ga1 : ga0) * sc;
+                    const float4 v4 = make_float4(v, v, v, v);
+                    float *p = base + (size_t)(cell ? qw2 : qw) * g.k * g.W + (size_t)(cell ? rw2 : rw) * g.k;
+#pragma unroll 1
+                    for (int dy = 0; dy < g.k; ++dy)
+                        for (int q4 = 0; q4 < (g.k >> 2); ++q4) reinterpret_cast<float4 *>(p + (size_t)dy * g.W)[q4] = v4;
+                }
+            }
+        }
     }
 
     TSTAMP(7);
@@ -1179,7 +1201,7 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
         if (!ticket) return DSRL_ERR_CUDA;
         const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
         fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
-                                                  loss_out, need_grad);
+                                                  loss_out, need_grad, nullptr, nullptr, nullptr);
         DSRL_LAUNCH_CHECK();
         return DSRL_OK;
     }
@@ -1219,6 +1241,27 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
     return launch_grad(g, so, saved, nullptr, (float)(1.0 / Z), partials, g.BC * plan.owner_tiles * plan.ysplits, Z,
                        loss_out, need_grad, st);
+}
+
+// Forward + backward in ONE launch when the geometry allows it (training shapes, windows tile the map exactly);
+// returns DSRL_ERR_UNSUPPORTED otherwise and the caller falls back to forward + backward.
+int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int H, int W, int k, int reduction,
+                            const float *grad_out, float *loss_out, float *dx1, float *dx2, void *saved_v, size_t saved_bytes,
+                            void *ws, size_t ws_bytes, cudaStream_t st) {
+    RefGeom g;
+    if (!make_geom(B, C, H, W, k, g)) DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(reference): bad geometry B=%d C=%d H=%d W=%d k=%d", B, C, H, W, k);
+    const bool aligned = (!dx1 || (reinterpret_cast<uintptr_t>(dx1) & 15) == 0) && (!dx2 || (reinterpret_cast<uintptr_t>(dx2) & 15) == 0);
+    if (reduction == DSRL_REDUCE_NONE || !fused_ok(g) || H % k || W % k || k % 4 || !aligned) return DSRL_ERR_UNSUPPORTED;
+    RefSaved so = make_saved(g);
+    if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(reference): saved blob too small (%zu < %zu)", saved_bytes, so.total);
+    if (ws_bytes < fa_ref_workspace_bytes(B, C, H, W, k)) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(reference): workspace too small");
+    unsigned *ticket = next_ticket_slot();
+    if (!ticket) return DSRL_ERR_CUDA;
+    const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
+    fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket,
+                                              (float)(1.0 / Z), Z, loss_out, 1, grad_out, dx1, dx2);
+    DSRL_LAUNCH_CHECK();
+    return DSRL_OK;
 }
 
 int fa_ref_backward(const void *saved_v, size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C,

@@ -60,7 +60,15 @@ class FAPlan:
 
     def forward_backward(self, x1, x2, grad_out):
         """x1, x2: contiguous fp32 CUDA tensors of the planned shapes; grad_out: fp32 CUDA tensor (1 element for
-        mean/sum).  Returns (loss, dx1, dx2) -- the plan's own buffers, overwritten by the next call."""
-        self.forward(x1, x2, True)
-        self.backward(x1, x2, grad_out)
+        mean/sum).  Returns (loss, dx1, dx2) -- the plan's own buffers, overwritten by the next call.  For mean/sum this
+        is ``dsrl_fa_forward_backward`` (one kernel launch at the reference model's training shapes)."""
+        if self.red == _lib.REDUCE_NONE:
+            self.forward(x1, x2, True)
+            self.backward(x1, x2, grad_out)
+            return self.loss, self.dx1, self.dx2
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(_lib.lib().dsrl_fa_forward_backward(self.mode, self.prec, self._p(x1), self._p(x2), self.B, self.C1, self.C2,
+                                                       self.H, self.W, self.k, self.red, self._p(grad_out), self._p(self.loss),
+                                                       self._p(self.dx1), self._p(self.dx2), self._p(self.saved), self.saved_bytes,
+                                                       self._p(self.ws), self.ws_bytes, st))
         return self.loss, self.dx1, self.dx2
