@@ -51,12 +51,17 @@ def dist_env():
 
 
 def load_peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json, else the fallback B200_PROFILING.md states."""
+    fb = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
-                "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        out = {k: float(d[k]) if d.get(k) else fb[k] for k in fb}
+        missing = [k for k in fb if not d.get(k)]
+        out["source"] = "measured (MEASURED_PEAKS.json)" + (f"; fallback for {missing}" if missing else "")
+        return out
+    except (OSError, ValueError, TypeError):
+        return {**fb, "source": "fallback (B200_PROFILING.md)"}
 
 
 def load_traffic():
