@@ -84,3 +84,26 @@ def check(rc: int):
 
 def launch_count() -> int:
     return int(lib().dsrl_launch_count())
+
+
+# ---- tracing (the reference wraps its commands in torch.autograd.profiler; here NVTX ranges around the C-ABI calls) ----
+NVTX = bool(int(os.environ.get("DSRL_NVTX", "0")))
+
+
+class nvtx_range:
+    """``with nvtx_range("dsrl.fa_forward"):`` -- an NVTX range when DSRL_NVTX=1 (for ``ncu --nvtx`` / timeline tools), free otherwise."""
+
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()

@@ -76,7 +76,7 @@ def counts_for_update(pred, target, mask, nc: int, updates_leading: bool = False
         return torch.zeros((U, row_len(nc)), dtype=torch.int64, device=dev)
     rows = torch.empty((U, row_len(nc)), dtype=torch.int64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.nvtx_range("dsrl.seg_counts"):
         _lib.check(_lib.lib().dsrl_seg_counts(ctypes.c_void_p(p.data_ptr()), _DT[p.dtype], ctypes.c_void_p(t.data_ptr()),
                                               _DT[t.dtype], ctypes.c_void_p(m.data_ptr()) if m is not None else None,
                                               U, npix, nc, ignore_label, ctypes.c_void_p(rows.data_ptr()), stream))
@@ -106,7 +106,7 @@ def counts_from_logits(logits, target, mask, nc: int, ignore_label: int = IGNORE
     rows = torch.empty((U, row_len(nc)), dtype=torch.int64, device=dev)
     pred = torch.empty(tuple(target.shape), dtype=torch.int64, device=dev) if want_pred else None
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _lib.nvtx_range("dsrl.seg_counts_from_logits"):
         _lib.check(_lib.lib().dsrl_seg_counts_from_logits(
             ctypes.c_void_p(lg.data_ptr()), ctypes.c_void_p(t.data_ptr()), _DT[t.dtype],
             ctypes.c_void_p(m.data_ptr()) if m is not None else None, U, B, H * W, nc, ignore_label,

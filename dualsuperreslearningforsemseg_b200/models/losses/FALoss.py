@@ -88,7 +88,7 @@ class _FAFunction(torch.autograd.Function):
             out = torch.empty((), dtype=torch.float32, device=dev)
         need_grad = int(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        with _OnDevice(dev):
+        with _OnDevice(dev), _lib.nvtx_range("dsrl.fa_forward"):
             _lib.check(_lib.lib().dsrl_fa_forward(mode, precision, _ptr(x1c), _ptr(x2c), B, C1, C2, H, W, k, reduction,
                                                   need_grad, _ptr(out), _ptr(saved), saved_bytes, _ptr(ws), ws_bytes,
                                                   stream))
@@ -113,7 +113,7 @@ class _FAFunction(torch.autograd.Function):
         dx2 = torch.empty((B, C2, H, W), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        with _OnDevice(dev):
+        with _OnDevice(dev), _lib.nvtx_range("dsrl.fa_backward"):
             _lib.check(_lib.lib().dsrl_fa_backward(mode, precision, _ptr(x1c), _ptr(x2c), _ptr(saved), saved_bytes,
                                                    _ptr(go), _ptr(dx1), _ptr(dx2), B, C1, C2, H, W, k, reduction,
                                                    _ptr(ws), ws_bytes, stream))
