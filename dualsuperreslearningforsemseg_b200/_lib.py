@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("DSRL_B200_LIB") or os.path.join(PKG_DIR, "libdsrl_b20
 OK, ERR_BAD_SHAPE, ERR_BAD_DTYPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_BAD_ARG = 0, -1, -2, -3, -4, -5
 FA_REFERENCE, FA_POSITION = 0, 1
 REDUCE_NONE, REDUCE_MEAN, REDUCE_SUM = 0, 1, 2
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_F16 = 0, 1, 2, 3
 U8, I32, I64 = 0, 1, 2
 
 # every symbol include/dsrl_b200.h declares (tests/test_abi.py checks the header against this list)

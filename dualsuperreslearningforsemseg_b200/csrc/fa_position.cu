@@ -24,6 +24,7 @@
 //   fa_pos_jacobian sums the partial accumulators when the column range of a row tile is split over several CTAs
 //   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -59,15 +60,16 @@ struct PosGeom {
     int q_resident, stages;
     int jsplit;             // gradient variant: the column tiles of one row tile are spread over jsplit CTAs (small grids)
     int pair, pair_stages;  // CTA-pair form of the gradient variant usable for this geometry; its ring depth
-    size_t smem_bytes, pair_smem_bytes;
+    int half, nkh, half_stages;   // FP16-operand pair form (kind::f16): usable + requested; Kc / 64 chunks; its ring depth
+    size_t smem_bytes, pair_smem_bytes, half_smem_bytes;
 };
 
-struct PosWs { size_t Fpm, Fcm, nrm, partials, opart, total; };
+struct PosWs { size_t Fpm, Fcm, FpmH, FcmH, nrm, partials, opart, total; };
 struct PosSaved { size_t dP, total; };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, PosGeom &g) {
+inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, PosGeom &g, int half = 0) {
     if (B < 1 || C1 < 1 || C2 < 1 || H < 1 || W < 1 || k < 1) return false;
     g.B = B; g.C1 = C1; g.C2 = C2; g.H = H; g.W = W; g.k = k;
     g.h = H / k; g.w = W / k;
@@ -115,6 +117,17 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         if (const char *e = getenv("DSRL_POS_STAGES")) { const int v = atoi(e); if (v >= 2 && v < g.pair_stages) g.pair_stages = v; }   // tuning hook
         g.pair_smem_bytes = 1024 + qbytes + (size_t)g.pair_stages * stage + kSmemAux;
     }
+    // FP16 operands: 64 channels per 128-byte row, so the CTA's own rows (<= 8 boxes) are always resident
+    g.nkh = (g.Kc + 63) / 64;
+    g.half = half && !g.split && g.pair && (g.G == 1 || g.gcnt[0] == g.gcnt[1]);
+    {
+        const size_t qbytes = (size_t)g.nkh * kBoxBytes;
+        g.half_stages = (int)((kSmemBudget - 1024 - kSmemAux - qbytes) / (2 * kBoxBytes));
+        if (g.half_stages > 6) g.half_stages = 6;
+        if (const char *e = getenv("DSRL_POS_STAGES")) { const int v = atoi(e); if (v >= 2 && v < g.half_stages) g.half_stages = v; }
+        g.half_smem_bytes = 1024 + qbytes + (size_t)g.half_stages * 2 * kBoxBytes + kSmemAux;
+        if (g.half_stages < 2) g.half = 0;
+    }
     if (const char *force = getenv("DSRL_POS_JSPLIT")) {          // test hook: force 1, 2 or 4 (when it divides the tile count)
         const int s = atoi(force);
         if ((s == 1 || s == 2 || s == 4) && g.tiles % s == 0) g.jsplit = s;
@@ -127,6 +140,8 @@ inline PosWs make_ws(const PosGeom &g) {
     size_t off = 0;
     w.Fpm = off;      off = align_up(off + (size_t)(1 + g.split) * g.B * g.Npad * g.Kc * 4, 1024);   // hi rows, then lo rows
     w.Fcm = off;      off = align_up(off + ((size_t)g.B * g.Kc + kTile) * g.Npad * 4, 1024);   // + one box of slack rows
+    w.FpmH = off;     off = align_up(off + (g.half ? (size_t)g.B * g.Npad * g.Kc * 2 : 0), 1024);           // FP16 copies of both layouts
+    w.FcmH = off;     off = align_up(off + (g.half ? ((size_t)g.B * g.Kc + kTile) * g.Npad * 2 : 0), 1024);
     w.nrm = off;      off = align_up(off + (size_t)g.B * 2 * g.Npad * 4, 256);
     w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * g.jsplit * 8 + 16384, 256);   // + debug timing area
     w.opart = off;    off = align_up(off + (g.jsplit > 1 ? (size_t)g.jsplit * g.B * g.Npad * g.Kc * 4 : 0), 256);
@@ -145,7 +160,8 @@ inline PosSaved make_saved(const PosGeom &g) {
 // pack: pool, normalise over channels, round to TF32, write both operand layouts
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1, const float *__restrict__ x2, PosGeom g,
-                                                  float *__restrict__ Fpm, float *__restrict__ Fcm, float *__restrict__ nrm) {
+                                                  float *__restrict__ Fpm, float *__restrict__ Fcm, float *__restrict__ nrm,
+                                                  __half *__restrict__ FpmH, __half *__restrict__ FcmH) {
     extern __shared__ float T[];                     // [Kc][33] pooled values of a 32-position strip
     __shared__ float s_inv[2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -218,7 +234,9 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
     __syncthreads();
     for (int c = warp; c < g.Kc; c += 8) {            // channel-major rows: 128 contiguous bytes per warp store
         const int br = c >= g.C1p;
-        Fcm[((size_t)b * g.Kc + c) * g.Npad + p] = round_tf32(T[c * 33 + lane] * s_inv[br][lane]);
+        const float f = T[c * 33 + lane] * s_inv[br][lane];
+        Fcm[((size_t)b * g.Kc + c) * g.Npad + p] = round_tf32(f);
+        if (FcmH) FcmH[((size_t)b * g.Kc + c) * g.Npad + p] = __float2half_rn(f);
     }
     for (int q = warp; q < 32; q += 8) {              // position-major rows: Kc contiguous floats per position
         float *dst = Fpm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
@@ -227,6 +245,11 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
             const float f = T[c * 33 + q] * s_inv[c >= g.C1p][q], hi = round_tf32(f);
             dst[c] = hi;
             if (g.split) dst_lo[c] = round_tf32(f - hi);
+        }
+        if (FpmH) {                                   // FP16 copy: two channels per lane, 128 bytes per warp store
+            __half2 *dh = reinterpret_cast<__half2 *>(FpmH + ((size_t)b * g.Npad + p0 + q) * g.Kc);
+            for (int c = 2 * lane; c < g.Kc; c += 64)
+                dh[c >> 1] = __floats2half2_rn(T[c * 33 + q] * s_inv[c >= g.C1p][q], T[(c + 1) * 33 + q] * s_inv[c + 1 >= g.C1p][q]);
         }
     }
 }
@@ -266,7 +289,7 @@ struct EpiCtx {
     int itile, js, grp, b, j0, nt, gN, gbeg, T;
 };
 
-template <bool kGrad, bool kPair>
+template <bool kGrad, bool kPair, bool kHalf = false>
 __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a, const EpiCtx &c) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t *d_full = c.d_full, *p_full = c.p_full, *o_full = c.o_full;
@@ -305,7 +328,19 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
                 tsum += fabsf(x);
                 if (kGrad) v[e] = (v[e] & 0x80000000u) | (x != 0.f ? 0x3f800000u : 0u);     // sign(x) as a TF32 value
             }
-            if (kGrad) tmem_st32(taddr, v);
+            if (kGrad && !kHalf) tmem_st32(taddr, v);
+            if (kGrad && kHalf) {
+                // FP16 sign tile, two positions per 32-bit column.  The columns a warp writes ([64*half, 64*half + 32) of
+                // the tile) lie inside the column range it has already read, so the two halves never race.
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const uint32_t lo = v[2 * e], hi = v[2 * e + 1];     // already +-1.0f / 0 as FP32 bit patterns
+                    pk[e] = ((lo >> 16) & 0x8000u) | ((lo & 0x7fffffffu) ? 0x3c00u : 0u) |
+                            ((((hi >> 16) & 0x8000u) | ((hi & 0x7fffffffu) ? 0x3c00u : 0u)) << 16);
+                }
+                tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + half * 64 + (cg & 1) * 16), pk);
+            }
         }
         if (kGrad) tmem_st_wait();
         fence_before_sync();
@@ -699,7 +734,9 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 // p_full.
 constexpr int kPairKBox = kBoxBytes / 2;           // 64 rows of K_j per CTA
 
-template <bool kSplit, bool kResident>
+// kHalf: FP16 operands (kind::f16, K = 16): a 128-byte operand row holds 64 channels / positions, so a box covers twice the
+// K extent, every MMA does twice the work per shared-memory byte, and the CTA's own rows are always resident.
+template <bool kSplit, bool kResident, bool kHalf = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
@@ -708,11 +745,14 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
     // per-CTA operand boxes of one 32-channel chunk: [Q hi 16 KB, Q lo 16 KB,] K hi 8 KB [, K lo 8 KB]; a stage holds
     // 32 KB (operand rows resident) or 48 KB (streamed) of them, or two V boxes
+    static_assert(!kHalf || (kResident && !kSplit), "FP16 form: resident rows, single pass");
     constexpr int kParts = kSplit ? 2 : 1;
+    constexpr int kElems = kHalf ? 64 : kChunk;                     // operand elements per 128-byte row
+    constexpr int kVB = kTile / kElems;                             // V boxes per column tile: 4 (TF32) or 2 (FP16)
     constexpr int kUnitBytes = (kResident ? 0 : kParts * kBoxBytes) + kParts * kPairKBox;
     constexpr int kStageBytes = kResident ? 4 * kPairKBox : 2 * (kBoxBytes + kPairKBox);
     constexpr int kUPS = kStageBytes / kUnitBytes;                  // chunks per stage: 4, 2 (split) | 2, 1 (split)
-    const int S = g.pair_stages, nkc = g.nkc, nq = kResident ? nkc * kParts : 0;
+    const int S = kHalf ? g.half_stages : g.pair_stages, nkc = kHalf ? g.nkh : g.nkc, nq = kResident ? nkc * kParts : 0;
     unsigned char *qreg = sm;
     unsigned char *ring = sm + (size_t)nq * kBoxBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
@@ -762,7 +802,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (elect_one()) {
                 if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nq * kBoxBytes);
                 for (int kc = 0; kc < nq; ++kc)
-                    tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
+                    tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, (kc % nkc) * kElems, row_q + (kc / nkc) * lo_rows);
             }
             __syncwarp();
         }
@@ -784,7 +824,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 const int nu = min(kUPS, nkc - kc0);
                 STAGE_FILL(nu * kUnitBytes, {
                     for (int u = 0; u < nu; ++u) {
-                        const int c0 = (kc0 + u) * kChunk;
+                        const int c0 = (kc0 + u) * kElems;
                         unsigned char *d = dst + (size_t)u * kUnitBytes;
                         if (!kResident) {
                             tma_load_2d_pair(d, &tm_q, bar, c0, row_q); d += kBoxBytes;
@@ -798,10 +838,10 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         };
         auto load_v = [&](int j) {
             const int row_v = b * g.Kc + gbeg + (int)rank * vrows;                        // this CTA's half of the channels
-            for (int jc0 = 0; jc0 < kTile / kChunk; jc0 += 2) {
+            for (int jc0 = 0; jc0 < kVB; jc0 += 2) {
                 STAGE_FILL(2 * vbytes, {
-                    tma_load_2d_pair(dst, &tm_v, bar, j * kTile + jc0 * kChunk, row_v);
-                    tma_load_2d_pair(dst + kBoxBytes, &tm_v, bar, j * kTile + (jc0 + 1) * kChunk, row_v);
+                    tma_load_2d_pair(dst, &tm_v, bar, j * kTile + jc0 * kElems, row_v);
+                    tma_load_2d_pair(dst + kBoxBytes, &tm_v, bar, j * kTile + (jc0 + 1) * kElems, row_v);
                 });
             }
         };
@@ -816,15 +856,18 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (leader) {
             constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
             const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
-            const uint32_t id_pos = idesc_tf32(2 * kTile, kTile, false), id_neg = idesc_tf32(2 * kTile, kTile, true);
-            const uint32_t id_g = idesc_tf32(2 * kTile, gN, false);
-            const int kc_neg = g.C1p / kChunk;
-#define MMA4_SS(dcol, ad, bd, id, acc0)                                                    \
-            do {                                                                           \
-                mma_tf32_ss_pair(dcol, (ad), (bd), id, acc0);                              \
-                mma_tf32_ss_pair(dcol, (ad) + 2, (bd) + 2, id, 1);                         \
-                mma_tf32_ss_pair(dcol, (ad) + 4, (bd) + 4, id, 1);                         \
-                mma_tf32_ss_pair(dcol, (ad) + 6, (bd) + 6, id, 1);                         \
+            const uint32_t id_pos = kHalf ? idesc_f16(2 * kTile, kTile, false) : idesc_tf32(2 * kTile, kTile, false);
+            const uint32_t id_neg = kHalf ? idesc_f16(2 * kTile, kTile, true) : idesc_tf32(2 * kTile, kTile, true);
+            const uint32_t id_g = kHalf ? idesc_f16(2 * kTile, gN, false) : idesc_tf32(2 * kTile, gN, false);
+            const int q_neg = g.C1p / (kElems / 4);                 // first K step (32 bytes of a row) of branch 2 (subtracted)
+            // the four K steps of one box; q0 = index of the first among all K steps (the branch boundary is a multiple of
+            // 32 channels, so it can fall inside an FP16 box but never inside a K step)
+#define MMA4_SS(dcol, ad, bd, q0, acc0)                                                                        \
+            do {                                                                                               \
+                mma_ss_pair<kHalf>(dcol, (ad), (bd), (q0) >= q_neg ? id_neg : id_pos, acc0);                   \
+                mma_ss_pair<kHalf>(dcol, (ad) + 2, (bd) + 2, (q0) + 1 >= q_neg ? id_neg : id_pos, 1);          \
+                mma_ss_pair<kHalf>(dcol, (ad) + 4, (bd) + 4, (q0) + 2 >= q_neg ? id_neg : id_pos, 1);          \
+                mma_ss_pair<kHalf>(dcol, (ad) + 6, (bd) + 6, (q0) + 3 >= q_neg ? id_neg : id_pos, 1);          \
             } while (0)
             auto gemm_d = [&](int jj) {
                 const int buf = jj & 1;
@@ -845,11 +888,10 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                                 const uint64_t a_lo = kResident ? q_desc + (uint64_t)(nkc + kc) * kBoxDesc : ub + kBoxDesc;
                                 const uint64_t b_hi = kResident ? ub : ub + kParts * kBoxDesc;
                                 const uint64_t b_lo = b_hi + kKDesc;
-                                const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
-                                MMA4_SS(dcol, a_hi, b_hi, id, kc != 0);
+                                MMA4_SS(dcol, a_hi, b_hi, 4 * kc, kc != 0);
                                 if (kSplit) {
-                                    MMA4_SS(dcol, a_hi, b_lo, id, 1);
-                                    MMA4_SS(dcol, a_lo, b_hi, id, 1);
+                                    MMA4_SS(dcol, a_hi, b_lo, 4 * kc, 1);
+                                    MMA4_SS(dcol, a_lo, b_hi, 4 * kc, 1);
                                 }
                             }
                         }
@@ -863,7 +905,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 const int buf = jj & 1;
                 const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
                 mbar_wait(&p_full[buf], (jj >> 1) & 1, 15);
-                for (int jc0 = 0; jc0 < kTile / kChunk; jc0 += 2) {
+                for (int jc0 = 0; jc0 < kVB; jc0 += 2) {
                     mbar_wait(&full[slot], ph, 13);
                     const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
                     const int ss = slot;
@@ -872,13 +914,14 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     if (elect_one()) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const uint32_t acol = pcol + (uint32_t)((jc0 + h) * kChunk);
+                            // TF32: 32 sign columns per box; FP16: box h = positions [64h, 64h+64) = 32 packed columns at 64h
+                            const uint32_t acol = pcol + (uint32_t)((jc0 + h) * (kHalf ? 64 : kChunk));
                             const uint64_t bd = sd + (uint64_t)h * kBoxDesc;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts_pair(tmem, acol + ks * 8, bd + 2 * ks, id_g, (jj | (jc0 + h) | ks) != 0);
+                            for (int ks = 0; ks < 4; ++ks) mma_ts_pair<kHalf>(tmem, acol + ks * 8, bd + 2 * ks, id_g, (jj | (jc0 + h) | ks) != 0);
                         }
                         umma_commit_pair(&empty[ss]);
-                        if (last && jc0 + 2 >= kTile / kChunk) umma_commit_pair(o_full);
+                        if (last && jc0 + 2 >= kVB) umma_commit_pair(o_full);
                     }
                     __syncwarp();
                 }
@@ -895,7 +938,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         EpiCtx c;
         c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
         c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
-        epilogue_role<true, true>(g, a, c);
+        epilogue_role<true, true, kHalf>(g, a, c);
     }
 #undef RING_ADVANCE
 
@@ -1014,15 +1057,16 @@ EncodeTiledFn encode_fn() {
     return g_encode;
 }
 
-// rows x cols fp32 matrix, row-major; box = 128 rows x 32 columns, 128-byte swizzle
-int make_map(CUtensorMap *m, const float *base, uint64_t rows, uint64_t cols, int box_rows = kTile) {
+// rows x cols matrix (fp32, or fp16 with `half`), row-major; box = box_rows rows x 128 bytes, 128-byte swizzle;
+// columns past `cols` read as zero
+int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, int box_rows = kTile, bool half = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) DSRL_FAIL(DSRL_ERR_CUDA, "FA(position): cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {cols * (half ? 2 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(half ? 2 * kChunk : kChunk), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+    const CUresult r = enc(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DSRL_FAIL(DSRL_ERR_CUDA, "FA(position): cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -1045,16 +1089,19 @@ size_t fa_pos_saved_bytes(int B, int C1, int C2, int H, int W, int k) {
 
 size_t fa_pos_workspace_bytes(int B, int C1, int C2, int H, int W, int k) {
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, 1, g)) return 0;     // sized for the 3xTF32 layout (the query has no precision)
-    return make_ws(g).total;
+    if (!make_geom(B, C1, C2, H, W, k, 1, g)) return 0;     // the query has no precision: the larger of the 3xTF32 and FP16 layouts
+    const size_t split_total = make_ws(g).total;
+    if (!make_geom(B, C1, C2, H, W, k, 0, g, 1)) return 0;
+    const size_t half_total = make_ws(g).total;
+    return split_total > half_total ? split_total : half_total;
 }
 
 int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
                    int need_grad, float *loss_out, void *saved_v, size_t saved_bytes, void *ws_v, size_t ws_bytes, cudaStream_t st) {
-    if (precision != DSRL_PREC_TF32 && precision != DSRL_PREC_FP32)
-        DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass) or FP32 (3xTF32 split)");
+    if (precision != DSRL_PREC_TF32 && precision != DSRL_PREC_FP32 && precision != DSRL_PREC_F16)
+        DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass), F16 (kind::f16 operands) or FP32 (3xTF32 split)");
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, precision == DSRL_PREC_FP32, g))
+    if (!make_geom(B, C1, C2, H, W, k, precision == DSRL_PREC_FP32, g, precision == DSRL_PREC_F16 && need_grad))
         DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry B=%d C=(%d,%d) H=%d W=%d k=%d (channels per branch <= 256)", B, C1, C2, H, W, k);
     const PosWs wo = make_ws(g);
     const PosSaved so = make_saved(g);
@@ -1069,7 +1116,9 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     const size_t pack_smem = (size_t)g.Kc * 33 * 4;
     int rc = opt_in_smem(fa_pos_pack, pack_smem);
     if (rc) return rc;
-    fa_pos_pack<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, Fpm, Fcm, nrm);
+    __half *FpmH = g.half ? reinterpret_cast<__half *>(ws + wo.FpmH) : nullptr;
+    __half *FcmH = g.half ? reinterpret_cast<__half *>(ws + wo.FcmH) : nullptr;
+    fa_pos_pack<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, Fpm, Fcm, nrm, FpmH, FcmH);
     DSRL_LAUNCH_CHECK();
 
     CUtensorMap tm_pm, tm_cm;
@@ -1095,6 +1144,13 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
         const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];
         if (same) {
             CUtensorMap tm_k, tm_v;
+            if (g.half) {
+                if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
+                if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
+                if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
+                if ((rc = opt_in_smem(fa_pos_tiles_pair<false, true, true>, g.half_smem_bytes))) return rc;
+                fa_pos_tiles_pair<false, true, true><<<grid, kThreads, g.half_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
+            } else {
             if ((rc = make_map(&tm_k, Fpm, (uint64_t)(1 + g.split) * B * g.Npad, (uint64_t)g.Kc, kTile / 2))) return rc;
             if ((rc = make_map(&tm_v, Fcm, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2))) return rc;
 #define LAUNCH_PAIR(SP, RS)                                                                               \
@@ -1105,6 +1161,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
             if (g.split) { if (g.q_resident) LAUNCH_PAIR(true, true); else LAUNCH_PAIR(true, false); }
             else         { if (g.q_resident) LAUNCH_PAIR(false, true); else LAUNCH_PAIR(false, false); }
 #undef LAUNCH_PAIR
+            }
             DSRL_LAUNCH_CHECK();
             if (g.jsplit > 1) {
                 if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;

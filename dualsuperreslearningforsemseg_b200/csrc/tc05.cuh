@@ -102,6 +102,13 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool negate_a) {
          | ((uint32_t)(N >> 3) << 17)      // N / 8
          | ((uint32_t)(M >> 4) << 24);     // M / 16
 }
+// Instruction descriptor, kind::f16 with FP16 operands, FP32 accumulate, both operands K-major (K = 16 per instruction).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool negate_a) {
+    return (1u << 4)                       // D format  F32;  A / B format fields 0 = F16
+         | ((negate_a ? 1u : 0u) << 13)    // negate A
+         | ((uint32_t)(N >> 3) << 17)      // N / 8
+         | ((uint32_t)(M >> 4) << 24);     // M / 16
+}
 // D[tmem] (+)= A[smem] * B[smem]^T      (one thread issues)
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -139,6 +146,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
           "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
           "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
           "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+// 32 lanes x 16 columns (a 32-column strip of 16-bit values packed two per column: low half = even element)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -198,6 +213,29 @@ __device__ __forceinline__ void mma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tme
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// FP16-operand forms (kind::f16, K = 16): A from TMEM holds two consecutive k per 32-bit column
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool kF16>
+__device__ __forceinline__ void mma_ss_pair(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    if (kF16) mma_f16_ss_pair(d, a, b, id, acc); else mma_tf32_ss_pair(d, a, b, id, acc);
+}
+template <bool kF16>
+__device__ __forceinline__ void mma_ts_pair(uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    if (kF16) mma_f16_ts_pair(d, a, b, id, acc); else mma_tf32_ts_pair(d, a, b, id, acc);
 }
 
 }  // namespace tc

@@ -14,7 +14,7 @@ from . import _lib
 
 _RED = {"none": _lib.REDUCE_NONE, "mean": _lib.REDUCE_MEAN, "sum": _lib.REDUCE_SUM}
 _MODE = {"reference": _lib.FA_REFERENCE, "position": _lib.FA_POSITION}
-_PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32}
+_PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "f16": _lib.PREC_F16}
 
 
 class FAPlan:

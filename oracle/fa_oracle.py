@@ -199,6 +199,13 @@ def round_tf32(x: np.ndarray) -> np.ndarray:
     return u.astype(np.uint32).view(np.float32).astype(np.float64)
 
 
+def round_f16(x: np.ndarray) -> np.ndarray:
+    """float32 -> IEEE binary16 (round to nearest even, what ``cvt.rn.f16.f32`` / ``__float2half_rn`` do): the same 11-bit
+    significand as TF32 for |x| >= 2^-14; smaller values lose relative precision (absolute error <= 2^-25), which for
+    unit-norm feature vectors is far below the ordinary rounding error.  Returned as float64."""
+    return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float64)
+
+
 def fa_position(x1, x2, k: int = 8, reduction: str = "mean", grad_out=None, need_grad: bool = True,
                 chunk: int = 1024, operand_rounding: str | None = None):
     """Position-affinity FA loss: ``S = Fh^T Fh`` (N x N, Fh = channel-L2-normalised pooled features),
@@ -226,8 +233,10 @@ def fa_position(x1, x2, k: int = 8, reduction: str = "mean", grad_out=None, need
     F2, Fh2, n2 = _position_normalise(P2)
     if operand_rounding == "tf32":
         Fh1, Fh2 = round_tf32(Fh1), round_tf32(Fh2)
+    elif operand_rounding == "f16":
+        Fh1, Fh2 = round_f16(Fh1), round_f16(Fh2)
     elif operand_rounding is not None:
-        raise ValueError("operand_rounding must be None or 'tf32'")
+        raise ValueError("operand_rounding must be None, 'tf32' or 'f16'")
     Z = float(B * N * N) if reduction == "mean" else 1.0
     go = 1.0 if grad_out is None else float(grad_out)
     total = 0.0
@@ -271,6 +280,8 @@ def fa_position_rows(x1, x2, rows, k: int = 8, reduction: str = "mean", operand_
     rows = np.asarray(rows, dtype=np.int64)
     F1, Fh1, n1 = _position_normalise(x1[:1])
     F2, Fh2, n2 = _position_normalise(x2[:1])
+    if operand_rounding == "f16":
+        Fh1, Fh2 = round_f16(Fh1), round_f16(Fh2)
     if operand_rounding == "tf32":
         Fh1, Fh2 = round_tf32(Fh1), round_tf32(Fh2)
     Z = float(B * N * N) if reduction == "mean" else 1.0
