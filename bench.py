@@ -580,16 +580,23 @@ def cpu_seg_counts(maps=2, threads=None):
 # ----------------------------------------------------------------------------------------------------------------
 STRESS_B, STRESS_HW, STRESS_K = 8, (128, 256), 1      # "128x256 feature positions ... batch 8, sharded over 1/2/4/8 B200"
 STRESS_C = 256                                        # channels per branch (decoder width, DSRL.py:115)
+# Operand type of the tcgen05 contractions in the primary line.  "f16": FP16 operands / FP32 accumulate -- the same 11-bit
+# significand as TF32 (the features are unit-norm, so FP16's exponent range is enough) at twice the tensor rate; held to the
+# same parity gates as "tf32" (tests/test_fa_position_gpu.py).  The TF32 kernels are reported under `extra`.
+STRESS_PRECISION = "f16"
+PRECISION_TEXT = {"tf32": ("tf32", "one tcgen05 kind::tf32 pass, FP32 accumulate in TMEM"),
+                  "f16": ("f16 operands, f32 accumulate", "one tcgen05 kind::f16 pass on FP16 operands (11-bit significand, as TF32), FP32 accumulate in TMEM"),
+                  "fp32": ("3xtf32", "3xTF32 split")}
 
 
-def measure_tf32_peak(dev):
-    """cuBLAS TF32 GEMM, 8192^3, best of 10 -- the same recipe MEASURED_PEAKS.json used for bf16 (it has no TF32 entry)."""
+def measure_tf32_peak(dev, dtype=torch.float32):
+    """cuBLAS TF32 (or, with dtype=torch.float16, FP16) GEMM, 8192^3, best of 10 -- the recipe MEASURED_PEAKS.json used for bf16."""
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         n = 8192
-        x = torch.randn((n, n), device=dev)
-        y = torch.randn((n, n), device=dev)
+        x = torch.randn((n, n), device=dev).to(dtype)
+        y = torch.randn((n, n), device=dev).to(dtype)
         for _ in range(3):
             x @ y
         best = 1e9
@@ -620,6 +627,7 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     steps = steps or args.steps
     warmup = max(3, warmup or args.warmup)
     C = C or STRESS_C
+    precision = precision or getattr(args, "precision", None) or STRESS_PRECISION
     sl = shard_slice(STRESS_B, rank, world)                      # batch shard: samples are independent
     b_local = sl.stop - sl.start
     if b_local == 0:
@@ -652,29 +660,32 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     res = {
         "metric": "fa_fwd_bwd_gpairs_per_s", "unit": "Gpairs/s",
         "value": pairs_total / (step_ms * 1e-3) / 1e9,
-        "ms_per_step": step_ms, "steps": steps, "dtype": "tf32" if precision in (None, "tf32") else "3xtf32",
+        "ms_per_step": step_ms, "steps": steps, "dtype": PRECISION_TEXT[precision][0],
         "scaling": "strong",
         "config": {"workload": f"fa_stress: BASELINE configs[3] -- FA loss fwd+bwd, position semantics (N x N affinity never materialised), "
                                f"{H}x{W} positions (N={N}), batch {STRESS_B} sharded over {world} GPU(s), C={C} per branch, subsample_factor={STRESS_K}",
                    "shape_per_gpu": [b_local, C, H, W], "pairs_total": pairs_total,
-                   "precision": "one tcgen05 kind::tf32 pass, FP32 accumulate in TMEM" if precision in (None, "tf32") else "3xTF32 split",
+                   "precision": PRECISION_TEXT[precision][1],
                    "l2": "working set per step (1.6 GB per sample) larger than L2, no flush",
                    "parallelism": f"dp{world} (batch shard, no data-path collective; scalar loss all-reduced for reporting only)",
                    "loss_rank0": loss_local},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic().get("fa_stress"),
-                     "peak_source": peaks["source"] + " dense bf16 burst; the kernel runs kind::tf32, whose hardware rate is half of bf16",
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": load_traffic().get({"f16": "fa_stress_f16", "tf32": "fa_stress"}.get(precision, "-")) if C == STRESS_C else None,
+                     "peak_source": peaks["source"] + (" dense bf16 burst (kind::f16 runs at the bf16 hardware rate)" if precision == "f16" else
+                                                       " dense bf16 burst; the kernel runs kind::tf32, whose hardware rate is half of bf16"),
                      "algorithmic_flops_per_step_per_gpu": alg_flops_rank, "executed_tensor_flops_per_step_per_gpu": exec_flops_rank,
                      "executed_tflops": exec_flops_rank / (step_ms * 1e-3) / 1e12,
-                     "kernel": "fa_pos_tiles (timed together with fa_pos_pack + fa_pos_unpool: one step = 3 launches)"},
+                     "kernel": "fa_pos_tiles_pair (timed together with fa_pos_pack + fa_pos_unpool: one step = 3 launches)"},
         "gpu_launches": int(sum_over_ranks(launches_per_step * steps, world, dev)),
         "clocks": clk.summary(),
     }
     if not light:
-        tf32_peak = measure_tf32_peak(dev)
-        res["roofline"]["tf32_peak_measured"] = tf32_peak
-        res["roofline"]["frac_of_tf32_peak"] = achieved / tf32_peak
-        res["roofline"]["executed_frac_of_tf32_peak"] = res["roofline"]["executed_tflops"] / tf32_peak
+        # cuBLAS GEMM of the same operand type, timed in this very run (same box, same thermal / power state)
+        key = "f16" if precision == "f16" else "tf32"
+        lib_peak = measure_tf32_peak(dev, torch.float16 if precision == "f16" else torch.float32)
+        res["roofline"][f"{key}_peak_measured"] = lib_peak
+        res["roofline"][f"frac_of_{key}_peak"] = achieved / lib_peak
+        res["roofline"][f"executed_frac_of_{key}_peak"] = res["roofline"]["executed_tflops"] / lib_peak
 
     # end to end through the drop-in FALoss from pinned host buffers (H2D of both feature maps + D2H of the loss)
     loss_fn = FALoss(subsample_factor=STRESS_K, affinity="position", precision=precision)
@@ -863,6 +874,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fa_stress", choices=["fa_train", "seg_counts", "fa_stress"])
+    ap.add_argument("--precision", default=None, choices=["f16", "tf32", "fp32"],
+                    help=f"fa_stress: operand type of the tensor-core contractions (default {STRESS_PRECISION})")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -932,7 +945,10 @@ def main():
         if args.workload != "fa_stress":
             attempt("fa_stress", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, light=True))
         else:
+            other = "tf32" if (args.precision or STRESS_PRECISION) == "f16" else "f16"
+            attempt(f"fa_stress_c256_{other}", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=5, warmup=3, precision=other))
             attempt("fa_stress_c128", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=5, warmup=3, C=128, light=True))
+            attempt(f"fa_stress_c128_{other}", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=5, warmup=3, C=128, precision=other, light=True))
             attempt("fa_stress_c256_3xtf32", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, precision="fp32", light=True))
         if rank == 0 and world == 1:
             for name in ("fa_train", "seg_counts", "seg_logits"):

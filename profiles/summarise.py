@@ -3,7 +3,7 @@
    <tag>_<workload>_launches.md   per-kernel launch counts / device time / share (ncu gpu__time_duration, cold-cache, serialised)
    <tag>_<workload>_full.md       selected `ncu --set full` metrics of the top kernel + top stall sites
    roofline_traffic.json          dram bytes per launch of the dominant kernels (read by bench.py)
-Usage: python profiles/summarise.py <tag>"""
+Usage: python profiles/summarise.py <tag> [traffic-key suffix, e.g. _f16 when the tag profiled the FP16-operand stress]"""
 import csv
 import json
 import os
@@ -19,6 +19,7 @@ FULL = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
         'sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+        'sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
         'sm__inst_executed_pipe_tc.sum', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -89,6 +90,7 @@ def full(tag, wl):
 
 def main():
     tag = sys.argv[1]
+    suffix = sys.argv[2] if len(sys.argv) > 2 else ""
     traffic_path = os.path.join(PROF, "roofline_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for wl in ("fa_stress", "seg_counts", "fa_train"):
@@ -98,8 +100,8 @@ def main():
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             rd = float(v['dram__bytes_read.sum'][0].replace(',', '')) * scale[v['dram__bytes_read.sum'][1]]
             wr = float(v['dram__bytes_write.sum'][0].replace(',', '')) * scale[v['dram__bytes_write.sum'][1]]
-            traffic[wl] = rd + wr
-            traffic[wl + "_source"] = f"profiles/{tag}_{wl}_full.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+            traffic[wl + suffix] = rd + wr
+            traffic[wl + suffix + "_source"] = f"profiles/{tag}_{wl}_full.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     print(json.dumps(traffic, indent=1))
 

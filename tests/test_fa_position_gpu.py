@@ -16,7 +16,10 @@ reproduces the GPU numbers to 4 digits).  Therefore:
     TF32 pass; there it is held to 1e-3 against the oracle on the same rounded operands.  The 3xTF32 path keeps 1e-3
     against the unrounded oracle everywhere.)
   * RANDOM inputs: loss <= 1e-4 (both precisions); gradients within the flip-limited bounds below, plus -- for
-    the single TF32 pass -- agreement with the oracle fed the same TF32-rounded operands."""
+    the single TF32 pass -- agreement with the oracle fed the same TF32-rounded operands.
+
+precision='f16' (FP16 operands, tcgen05 kind::f16, FP32 accumulate) carries the same 11-bit significand as TF32 and is
+held to exactly the TF32 gates, with the oracle's operand_rounding='f16' where the rounded-operand oracle is used."""
 import numpy as np
 import pytest
 import torch
@@ -72,6 +75,11 @@ def test_matches_autograd_golden(name):
     # forward-only path (symmetric tiles, no gradient contraction) gives the same loss
     assert abs(run(x1, x2, k, red, need_grad=False, precision="fp32")[0] - ref) <= LOSS_RTOL * abs(ref)
     assert abs(run(x1, x2, k, red, need_grad=False, precision="tf32")[0] - tl) <= LOSS_RTOL * abs(tl)
+    hl, _, _ = fa_oracle.fa_position(x1, x2, k, red, need_grad=False, operand_rounding="f16")
+    loss, d1, d2 = run(x1, x2, k, red, precision="f16")
+    assert abs(loss - hl) <= LOSS_RTOL * abs(hl), (loss, hl)
+    assert abs(loss - ref) <= 1e-3 * abs(ref), (loss, ref)
+    assert relnorm(d1, g1) <= RANDOM_GRAD_TF32 and relnorm(d2, g2) <= RANDOM_GRAD_TF32, (relnorm(d1, g1), relnorm(d2, g2))
 
 
 CASES = [
@@ -94,9 +102,10 @@ def test_margin_inputs_match_float64_oracle(s1, s2, k, red):
     x1, x2 = pos_margin_inputs(s1[0], s1[1], s2[1], s1[2], s1[3], 54321)
     go = 0.37
     ol, o1, o2 = fa_oracle.fa_position(x1, x2, k, red, grad_out=go)
-    tl, t1, t2 = fa_oracle.fa_position(x1, x2, k, red, grad_out=go, operand_rounding="tf32")
-    for prec in ("fp32", "tf32"):
+    rounded = {p: fa_oracle.fa_position(x1, x2, k, red, grad_out=go, operand_rounding=p) for p in ("tf32", "f16")}
+    for prec in ("fp32", "tf32", "f16"):
         loss, d1, d2 = run(x1, x2, k, red, go=go, precision=prec)
+        _, t1, t2 = rounded["f16" if prec == "f16" else "tf32"]
         # one TF32 pass with fewer than 128 channels: the margins of the construction are only ~2 sigma wide, a few 1e-5 of
         # the entries stay ambiguous under operand rounding (C = 20: 1.3 % on that branch, reproduced to 4 digits by the
         # rounded-operand oracle) -- there the kernel is held to 1e-3 against the oracle on the SAME rounded operands
@@ -124,6 +133,12 @@ def test_random_inputs(s1, s2, k, red):
     assert abs(loss - tl) <= 1e-5 * abs(tl), (loss, tl)
     assert relnorm(d1, t1) <= RANDOM_GRAD_TF32_SAME and relnorm(d2, t2) <= RANDOM_GRAD_TF32_SAME, (relnorm(d1, t1), relnorm(d2, t2))
     assert relnorm(d1, o1) <= RANDOM_GRAD_TF32 and relnorm(d2, o2) <= RANDOM_GRAD_TF32, (relnorm(d1, o1), relnorm(d2, o2))
+    hl, h1, h2 = fa_oracle.fa_position(x1, x2, k, red, operand_rounding="f16")
+    loss, d1, d2 = run(x1, x2, k, red, precision="f16")
+    assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
+    assert abs(loss - hl) <= 1e-5 * abs(hl), (loss, hl)
+    assert relnorm(d1, h1) <= RANDOM_GRAD_TF32_SAME and relnorm(d2, h2) <= RANDOM_GRAD_TF32_SAME, (relnorm(d1, h1), relnorm(d2, h2))
+    assert relnorm(d1, o1) <= RANDOM_GRAD_TF32 and relnorm(d2, o2) <= RANDOM_GRAD_TF32, (relnorm(d1, o1), relnorm(d2, o2))
 
 
 def test_full_size_sample_of_config4():
@@ -131,9 +146,10 @@ def test_full_size_sample_of_config4():
     32 channels per branch so the float64 oracle still finishes in well under a minute on the host."""
     x1, x2 = pos_margin_inputs(1, 32, 32, 128, 256, 54321)
     ol, o1, o2 = fa_oracle.fa_position(x1, x2, 1, "mean", chunk=512)
-    loss, d1, d2 = run(x1, x2, 1, "mean", precision="tf32")
-    assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
-    assert relnorm(d1, o1) <= 3e-3 and relnorm(d2, o2) <= 3e-3, (relnorm(d1, o1), relnorm(d2, o2))
+    for prec in ("tf32", "f16"):
+        loss, d1, d2 = run(x1, x2, 1, "mean", precision=prec)
+        assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (prec, loss, ol)
+        assert relnorm(d1, o1) <= 3e-3 and relnorm(d2, o2) <= 3e-3, (prec, relnorm(d1, o1), relnorm(d2, o2))
     loss, d1, d2 = run(x1, x2, 1, "mean", precision="fp32")
     assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
     assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
@@ -153,6 +169,10 @@ def test_column_split_variants_agree(jsplit, monkeypatch):
         loss, d1, d2 = run(x1, x2, 1, "mean", precision="fp32")
         assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
         assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
+        if shape2 is not None:                        # FP16 pair kernel through the same partial-accumulator path (C >= 128: tight)
+            loss, d1, d2 = run(x1, x2, 1, "mean", precision="f16")
+            assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
+            assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
 
 
 def test_repeatable_and_one_sided_grad():
@@ -175,8 +195,10 @@ def test_identical_branches_give_zero_loss():
     # S1 - S2 is accumulated as ONE contraction (branch-2 products subtracted), so identical branches cancel to FP32
     # accumulation noise rather than to an exact 0 (typical losses are 0.05-0.2)
     x1, _ = pos_inputs((1, 64, 16, 16), (1, 64, 16, 16), 3)
-    for prec in ("tf32", "fp32"):
+    for prec in ("tf32", "fp32", "f16"):
         loss, _, _ = run(x1, x1.copy(), 1, "mean", precision=prec)
+        assert 0.0 <= loss <= 1e-6, loss
+        loss, _, _ = run(x1, x1.copy(), 1, "mean", need_grad=True, precision=prec)
         assert 0.0 <= loss <= 1e-6, loss
 
 
@@ -222,6 +244,11 @@ def test_full_size_c256_sampled_rows():
     g1 = d1[0].reshape(256, -1)[:, rows]
     g2 = d2[0].reshape(256, -1)[:, rows]
     assert relnorm(g1, o1) <= GRAD_RTOL and relnorm(g2, o2) <= GRAD_RTOL, (relnorm(g1, o1), relnorm(g2, o2))
+    loss_h, d1, d2 = run(x1, x2, 1, "mean", precision="f16")          # the bench's kernel at the bench's size
+    g1 = d1[0].reshape(256, -1)[:, rows]
+    g2 = d2[0].reshape(256, -1)[:, rows]
+    assert relnorm(g1, o1) <= GRAD_RTOL and relnorm(g2, o2) <= GRAD_RTOL, (relnorm(g1, o1), relnorm(g2, o2))
+    assert abs(loss_h - loss) <= LOSS_RTOL * abs(loss), (loss_h, loss)
     loss_ng, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="tf32")
     loss_32, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="fp32")
     assert abs(loss - loss_ng) <= 1e-6 * abs(loss) and abs(loss - loss_32) <= LOSS_RTOL * abs(loss), (loss, loss_ng, loss_32)

@@ -134,3 +134,20 @@ def test_position_sampled_rows_match_full_oracle():
     allrows, _, _ = fa_oracle.fa_position_rows(x1[:1], x2[:1], np.arange(128), 1, "sum")
     l0, _, _ = fa_oracle.fa_position(x1[:1], x2[:1], 1, "sum", need_grad=False)
     np.testing.assert_allclose(allrows, l0, rtol=1e-12)
+
+
+def test_f16_operand_rounding_matches_tf32_width():
+    """round_f16 is IEEE binary16 (what the FP16-operand kernel feeds the tensor cores): on unit-norm feature entries it
+    has the 11-bit significand of TF32, so the two roundings differ by at most one unit in the last place."""
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(4096) / 16).astype(np.float32)
+    h, t = fa_oracle.round_f16(x), fa_oracle.round_tf32(x)
+    assert np.array_equal(h, x.astype(np.float16).astype(np.float64))
+    big = np.abs(x) >= 2.0 ** -14
+    assert np.all(np.abs(h - t)[big] <= np.abs(x[big]) * 2.0 ** -10)
+    assert np.all(np.abs(h - x)[big] <= np.abs(x[big]) * 2.0 ** -11)
+    assert np.all(np.abs(h - x)[~big] <= 2.0 ** -25)
+    x1 = rng.standard_normal((1, 8, 8, 8)).astype(np.float32); x2 = rng.standard_normal((1, 8, 8, 8)).astype(np.float32)
+    l0 = fa_oracle.fa_position(x1, x2, 1, "mean", need_grad=False)[0]
+    lh = fa_oracle.fa_position(x1, x2, 1, "mean", need_grad=False, operand_rounding="f16")[0]
+    assert abs(lh - l0) <= 1e-3 * abs(l0) and lh != l0
