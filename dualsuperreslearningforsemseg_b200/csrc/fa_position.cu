@@ -21,6 +21,8 @@
 //                   [0,256) gradient accumulator, [256,512) two D / sign tiles (double buffered).
 //   fa_pos_tiles_pair  the same for a cluster of two CTAs (two row tiles) with tcgen05 cta_group::2, M = 256: each CTA
 //                   supplies half of every B tile, which halves the B-operand shared-memory traffic (the hot variant)
+//                   With kHalf the operands are FP16 (kind::f16, same 11-bit significand as TF32 on unit-norm features):
+//                   twice the tensor rate, half the operand bytes, own rows always resident (precision 'f16')
 //   fa_pos_jacobian sums the partial accumulators when the column range of a row tile is split over several CTAs
 //   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)
 #include <cuda.h>

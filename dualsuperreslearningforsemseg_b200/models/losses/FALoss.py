@@ -15,9 +15,13 @@ PyTorch/CPU fallback: CPU tensors raise.
 Keyword-only extensions (defaults preserve the reference behaviour):
   affinity='reference' | 'position'   'position' = the paper's N x N position affinity (not in the reference; the two
                                       inputs may then differ in C; reduction 'mean' or 'sum')
-  precision=None | 'tf32' | 'fp32'    tensor-core arithmetic of 'position': 'tf32' (default) = one tcgen05 kind::tf32 pass
-                                      with FP32 accumulation; 'fp32' = 3xTF32 split (hi*hi + hi*lo + lo*hi), about FP32
-                                      accuracy at ~2x the time.  The reference semantics always runs in FP32 FMA.
+  precision=None | 'tf32' | 'f16' | 'fp32'
+                                      tensor-core arithmetic of 'position': 'tf32' (default) = one tcgen05 kind::tf32 pass
+                                      with FP32 accumulation; 'f16' = FP16 operands (the normalised features are unit
+                                      vectors, FP16 keeps the 11-bit significand of TF32), kind::f16, FP32 accumulation:
+                                      the accuracy of 'tf32' at about half the time; 'fp32' = 3xTF32 split (hi*hi +
+                                      hi*lo + lo*hi), about FP32 accuracy at ~2x the time of 'tf32'.  The reference
+                                      semantics always runs in FP32 FMA.
 """
 from __future__ import annotations
 
