@@ -58,17 +58,75 @@ class FAPlan:
                                                self.H, self.W, self.k, self.red, self._p(self.ws), self.ws_bytes, st))
         return self.dx1, self.dx2
 
-    def forward_backward(self, x1, x2, grad_out):
+    def forward_backward(self, x1, x2, grad_out, out=None):
         """x1, x2: contiguous fp32 CUDA tensors of the planned shapes; grad_out: fp32 CUDA tensor (1 element for
-        mean/sum).  Returns (loss, dx1, dx2) -- the plan's own buffers, overwritten by the next call.  For mean/sum this
-        is ``dsrl_fa_forward_backward`` (one kernel launch at the reference model's training shapes)."""
+        mean/sum).  Returns (loss, dx1, dx2) -- the plan's own buffers, overwritten by the next call, or the tensors
+        given as ``out=(loss, dx1, dx2)`` (mean/sum only).  For mean/sum this is ``dsrl_fa_forward_backward`` (one
+        kernel launch at the reference model's training shapes)."""
         if self.red == _lib.REDUCE_NONE:
             self.forward(x1, x2, True)
             self.backward(x1, x2, grad_out)
             return self.loss, self.dx1, self.dx2
+        loss, dx1, dx2 = out if out is not None else (self.loss, self.dx1, self.dx2)
         st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         _lib.check(_lib.lib().dsrl_fa_forward_backward(self.mode, self.prec, self._p(x1), self._p(x2), self.B, self.C1, self.C2,
-                                                       self.H, self.W, self.k, self.red, self._p(grad_out), self._p(self.loss),
-                                                       self._p(self.dx1), self._p(self.dx2), self._p(self.saved), self.saved_bytes,
+                                                       self.H, self.W, self.k, self.red, self._p(grad_out), self._p(loss),
+                                                       self._p(dx1), self._p(dx2), self._p(self.saved), self.saved_bytes,
                                                        self._p(self.ws), self.ws_bytes, st))
-        return self.loss, self.dx1, self.dx2
+        return loss, dx1, dx2
+
+
+class FAHostPipeline:
+    """FA loss forward+backward for feature maps that live in pinned HOST memory.
+
+    Samples are independent units of the loss, so the batch is cut into chunks of ``chunk`` samples: chunk
+    i+1 travels host -> device on a copy stream while the kernels work on chunk i on the caller's stream (two streams,
+    one event per chunk, no host synchronisation).  ``__call__(x1_host, x2_host, grad_out=1.0)`` returns
+    ``(loss, dx1, dx2)`` as device tensors owned by the pipeline: the batch loss ('mean' or 'sum') and the gradients
+    w.r.t. both inputs -- the same values ``FALoss`` + ``backward()`` give on the whole batch."""
+
+    def __init__(self, shape1, shape2=None, subsample_factor=8, reduction="mean", affinity="reference", precision=None,
+                 chunk=2, device=None):
+        if reduction not in ("mean", "sum"):
+            raise ValueError("FAHostPipeline: reduction must be 'mean' or 'sum'")
+        shape2 = tuple(shape2 or shape1)
+        self.B = int(shape1[0])
+        self.reduction = reduction
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        chunk = max(1, min(int(chunk), self.B))
+        self.bounds = [(i, min(i + chunk, self.B)) for i in range(0, self.B, chunk)]
+        self.plans = {}
+        for lo, hi in self.bounds:                          # one plan per distinct chunk size (the last chunk may be shorter)
+            n = hi - lo
+            if n not in self.plans:
+                self.plans[n] = FAPlan((n,) + tuple(shape1[1:]), (n,) + tuple(shape2[1:]), subsample_factor, reduction,
+                                       affinity, precision, dev)
+        self.x1 = torch.empty(tuple(shape1), dtype=torch.float32, device=dev)
+        self.x2 = torch.empty(tuple(shape2), dtype=torch.float32, device=dev)
+        self.dx1 = torch.empty_like(self.x1)
+        self.dx2 = torch.empty_like(self.x2)
+        self.losses = torch.zeros(len(self.bounds), dtype=torch.float32, device=dev)
+        # chunk means -> batch mean: weight n_chunk / B on the loss and on the upstream gradient; sums add up unweighted
+        w = [((hi - lo) / self.B if reduction == "mean" else 1.0) for lo, hi in self.bounds]
+        self.weights = torch.tensor(w, dtype=torch.float32, device=dev)
+        self.go = torch.empty(len(self.bounds), dtype=torch.float32, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in self.bounds]
+
+    def __call__(self, x1_host, x2_host, grad_out=1.0):
+        if x1_host.is_cuda or x2_host.is_cuda or not (x1_host.is_pinned() and x2_host.is_pinned()):
+            raise ValueError("FAHostPipeline: inputs must be pinned host tensors (use FALoss / FAPlan for device tensors)")
+        cur = torch.cuda.current_stream(self.dev)
+        torch.mul(self.weights, float(grad_out), out=self.go)
+        self.copy_stream.wait_stream(cur)                   # the previous call's kernels are done with the staging buffers
+        with torch.cuda.stream(self.copy_stream):
+            for i, (lo, hi) in enumerate(self.bounds):
+                self.x1[lo:hi].copy_(x1_host[lo:hi], non_blocking=True)
+                self.x2[lo:hi].copy_(x2_host[lo:hi], non_blocking=True)
+                self.events[i].record(self.copy_stream)
+        for i, (lo, hi) in enumerate(self.bounds):
+            cur.wait_event(self.events[i])
+            self.plans[hi - lo].forward_backward(self.x1[lo:hi], self.x2[lo:hi], self.go[i:i + 1],
+                                                 out=(self.losses[i:i + 1], self.dx1[lo:hi], self.dx2[lo:hi]))
+        return torch.dot(self.losses, self.weights), self.dx1, self.dx2

@@ -17,7 +17,7 @@ def _autograd(x1, x2, k, go, **kw):
     return loss.detach(), a.grad, b.grad
 
 
-@pytest.mark.parametrize("mode", ["reference", "position_tf32", "position_fp32"])
+@pytest.mark.parametrize("mode", ["reference", "position_tf32", "position_fp32", "position_f16"])
 def test_plan_matches_autograd_and_replays_in_a_graph(mode):
     from dualsuperreslearningforsemseg_b200.functional import FAPlan
     dev = torch.device("cuda", 0)
@@ -48,3 +48,30 @@ def test_plan_matches_autograd_and_replays_in_a_graph(mode):
     torch.cuda.synchronize()
     l2, e1, e2 = _autograd(y1, y2, k, go, **kw)
     assert float(plan.loss) == float(l2) and torch.equal(plan.dx1, e1) and torch.equal(plan.dx2, e2)
+
+
+@pytest.mark.parametrize("mode,red,chunk", [("reference", "mean", 2), ("reference", "sum", 4), ("position_f16", "mean", 2),
+                                             ("position_tf32", "sum", 3), ("position_f16", "mean", 8)])
+def test_host_pipeline_matches_whole_batch(mode, red, chunk):
+    """FAHostPipeline (chunked H2D on a copy stream overlapped with the kernels) == FALoss on the whole batch on the device:
+    chunk means weighted n/B, per-sample gradients untouched by the chunking.  Called twice: the staging buffers are reused."""
+    from dualsuperreslearningforsemseg_b200.functional import FAHostPipeline
+    dev = torch.device("cuda", 0)
+    if mode == "reference":
+        x1, x2 = fa_inputs((6, 2, 64, 128), "relu", 54321)
+        k, kw = 8, {}
+    else:
+        x1, x2 = pos_margin_inputs(5, 64, 64, 16, 32, 54321)          # 5 samples: ragged last chunk for chunk = 2, 3
+        k, kw = 1, {"affinity": "position", "precision": mode.split("_")[1]}
+    h1, h2 = torch.from_numpy(x1).pin_memory(), torch.from_numpy(x2).pin_memory()
+    go = 0.25
+    ref_loss, ref_d1, ref_d2 = _autograd(h1.to(dev), h2.to(dev), k, go, reduction=red, **kw)
+    pipe = FAHostPipeline(tuple(h1.shape), tuple(h2.shape), subsample_factor=k, reduction=red, chunk=chunk, device=dev, **kw)
+    for _ in range(2):
+        loss, d1, d2 = pipe(h1, h2, go)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(ref_loss)) <= 2e-6 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+        for d, r in ((d1, ref_d1), (d2, ref_d2)):
+            assert float((d - r).norm() / r.norm()) <= 2e-6
+    with pytest.raises(ValueError):
+        pipe(h1.to(dev), h2.to(dev))                                   # device tensors belong to FALoss / FAPlan
