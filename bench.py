@@ -774,12 +774,13 @@ class _TorchFALoss(torch.nn.Module):
 
 def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6):
     from harness.train_step import Stage3Step, synthetic_batch
-    from dualsuperreslearningforsemseg_b200.models.losses import FALoss
+    from dualsuperreslearningforsemseg_b200.models.losses import FALoss, CrossEntropyLoss
     from dualsuperreslearningforsemseg_b200 import _lib
     img, org, target = synthetic_batch(batch, dev, SEED + rank)
     out = {}
-    for name, fa in (("dsrl_b200", FALoss()), ("pytorch_eager_fa", _TorchFALoss())):
-        step = Stage3Step(fa, dev, ddp=world > 1)
+    for name, fa, ce in (("dsrl_b200", FALoss(), None), ("pytorch_eager_fa", _TorchFALoss(), None),
+                         ("dsrl_b200_fa_and_ce", FALoss(), CrossEntropyLoss(ignore_index=255))):
+        step = Stage3Step(fa, dev, ddp=world > 1, ce_loss=ce)
         n0 = _lib.launch_count()
         for _ in range(max(3, warmup)):
             losses = step(img, org, target)
@@ -816,9 +817,93 @@ def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6)
                                    f"random-init weights, synthetic 256x512 -> 512x1024, batch {batch} per GPU, "
                                    f"{'torch DDP over NCCL' if world > 1 else 'single GPU'}; model = harness/dsrl_model.py (cuDNN fp32)",
                        "fa_inputs": [batch, 1, 64, 128]},
-            "with_dsrl_b200_fa": ours, "with_pytorch_eager_fa": ref,
+            "with_dsrl_b200_fa": ours, "with_pytorch_eager_fa": ref, "with_dsrl_b200_fa_and_ce": out["dsrl_b200_fa_and_ce"],
             "fa_speedup_in_step": ref["fa_fwd_bwd_ms"] / ours["fa_fwd_bwd_ms"],
             "step_speedup": ref["ms_per_step"] / ours["ms_per_step"]}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload: ce_loss -- cross-entropy fwd+bwd on the reference's SSSR output shape, one pass each
+# ----------------------------------------------------------------------------------------------------------------
+def bench_ce_loss(args, rank, world, dev, peaks, steps=20, warmup=3, batch=6):
+    from dualsuperreslearningforsemseg_b200.models.losses import CrossEntropyLoss
+    from dualsuperreslearningforsemseg_b200 import _lib
+    C, H, W = 19, 512, 1024
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + rank)
+    x = torch.randn((batch, C, H, W), device=dev, generator=g) * 3
+    t = torch.randint(0, C, (batch, H, W), device=dev, generator=g).to(torch.uint8)
+    t[torch.rand((batch, H, W), device=dev, generator=g) < 0.1] = 255
+    px = batch * H * W
+    flush = L2Flusher(dev)
+
+    def timed(fn, tgt):
+        a = x.clone().requires_grad_(True)
+        for _ in range(warmup):
+            a.grad = None
+            fn(a, tgt).backward()
+        tot = 0.0
+        for _ in range(steps):
+            a.grad = None
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = fn(a, tgt)
+            loss.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / steps, float(loss), a.grad
+
+    ms_module, loss, grad = timed(CrossEntropyLoss(ignore_index=255), t)
+    # the two kernels back to back through the C-ABI on preallocated buffers (what a captured step issues): the roofline number
+    import ctypes
+    L = _lib.lib()
+    vp = lambda z: ctypes.c_void_p(z.data_ptr())
+    sbytes = int(L.dsrl_ce_saved_bytes(batch, H * W))
+    saved = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    loss_d = torch.empty((), dtype=torch.float32, device=dev)
+    go = torch.ones((), dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def raw():
+        _lib.check(L.dsrl_ce_forward(vp(x), vp(t), _lib.U8, batch, C, H * W, 255, _lib.REDUCE_MEAN, vp(loss_d), vp(saved), sbytes, st))
+        _lib.check(L.dsrl_ce_backward(vp(x), vp(t), _lib.U8, batch, C, H * W, 255, _lib.REDUCE_MEAN, vp(saved), sbytes, vp(go), vp(dx), st))
+
+    n0 = _lib.launch_count()
+    for _ in range(warmup):
+        raw()
+    ms = 0.0
+    for _ in range(steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        raw()
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    ms /= steps
+    launches = _lib.launch_count() - n0
+    assert float(loss_d) == loss and torch.equal(dx, grad), "C-ABI path != module path"
+    t_long = t.long()
+    ms_torch, loss_t, grad_t = timed(torch.nn.CrossEntropyLoss(ignore_index=255), t_long)
+    ms_torch_cast, _, _ = timed(lambda a, tt: torch.nn.functional.cross_entropy(a, tt.long(), ignore_index=255), t)
+    assert abs(loss - loss_t) <= 1e-5 * abs(loss_t) and float((grad - grad_t).norm() / grad_t.norm()) <= 1e-5, "CE != torch CE"
+    ms = max_over_ranks(ms, world, dev)
+    bytes_alg = px * ((4 * C + 1 + 4) + (4 * C + 4 * C + 4 + 1))       # forward: logits + target + lse; backward: logits + dlogits + lse + target
+    achieved = bytes_alg / (ms * 1e-3) / 1e9
+    return {"metric": "ce_fwd_bwd_gpx_per_s", "unit": "Gpx/s", "value": world * px / (ms * 1e-3) / 1e9, "ms_per_step": ms, "steps": steps,
+            "dtype": "f32", "scaling": "weak",
+            "config": {"workload": f"ce_loss: SURVEY 8f-3 -- CrossEntropyLoss(ignore_index=255) forward + backward on the stage-3 SSSR output, "
+                                   f"({batch},{C},{H},{W}) fp32 logits, uint8 target with 10% ignored (train_or_resume.py:116,435)",
+                       "l2": "flushed before every step (256 MiB fill outside the event pair)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_px": bytes_alg / px},
+            "via_autograd_module_ms": ms_module,
+            "pytorch_eager_same_gpu": {"ms_per_step": ms_torch, "ms_per_step_incl_target_long_cast": ms_torch_cast,
+                                       "speedup_module_vs_module": ms_torch_cast / ms_module},
+            "gpu_launches": int(launches), "loss": loss}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -962,6 +1047,7 @@ def main():
             attempt("seg_counts", lambda: bench_seg_counts(args, rank, world, dev, peaks, steps=5, warmup=3))
         attempt("seg_logits", lambda: bench_seg_logits(args, rank, world, dev, peaks))
         attempt("train_step", lambda: bench_train_step(args, rank, world, dev, peaks))
+        attempt("ce_loss", lambda: bench_ce_loss(args, rank, world, dev, peaks))
         if args.workload != "fa_stress":
             attempt("fa_stress", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, light=True))
         else:

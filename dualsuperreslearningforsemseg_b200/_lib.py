@@ -23,6 +23,7 @@ EXPORTS = (
     "dsrl_version", "dsrl_last_error", "dsrl_launch_count",
     "dsrl_fa_saved_bytes", "dsrl_fa_workspace_bytes", "dsrl_fa_forward", "dsrl_fa_backward", "dsrl_fa_forward_backward",
     "dsrl_seg_counts", "dsrl_seg_counts_from_logits",
+    "dsrl_ce_saved_bytes", "dsrl_ce_forward", "dsrl_ce_backward",
 )
 
 
@@ -59,6 +60,12 @@ def _declare(lib):
     lib.dsrl_seg_counts.argtypes = [vp, i, vp, i, vp, i64, i64, i, i, vp, vp]
     lib.dsrl_seg_counts_from_logits.restype = i
     lib.dsrl_seg_counts_from_logits.argtypes = [vp, vp, i, vp, i64, i64, i64, i, i, vp, vp, vp]
+    lib.dsrl_ce_saved_bytes.restype = sz
+    lib.dsrl_ce_saved_bytes.argtypes = [i, i64]
+    lib.dsrl_ce_forward.restype = i
+    lib.dsrl_ce_forward.argtypes = [vp, vp, i, i, i, i64, i64, i, vp, vp, sz, vp]
+    lib.dsrl_ce_backward.restype = i
+    lib.dsrl_ce_backward.argtypes = [vp, vp, i, i, i, i64, i64, i, vp, sz, vp, vp, vp]
 
 
 def lib():

@@ -24,20 +24,23 @@ def synthetic_batch(batch, device, seed, in_hw=(256, 512), num_classes=19):
 
 
 class Stage3Step:
-    def __init__(self, fa_loss, device, seed=54321, num_classes=19, ddp=False):
+    def __init__(self, fa_loss, device, seed=54321, num_classes=19, ddp=False, ce_loss=None):
         torch.manual_seed(seed)                                   # all ranks build the same weights (train_or_resume.py:31)
         self.model = DSRL(3, num_classes).to(device).train()
         self.core = self.model
         if ddp:
             self.model = nn.parallel.DistributedDataParallel(self.model, device_ids=[device.index])
-        self.ce = nn.CrossEntropyLoss(ignore_index=IGNORE)
+        # ce_loss: a replacement for the reference's t.nn.CrossEntropyLoss(ignore_index=...) (train_or_resume.py:116), e.g. the
+        # one-pass dsrl-b200 CrossEntropyLoss, which also takes the uint8 target as is (no .long() copy)
+        self.ce = ce_loss if ce_loss is not None else nn.CrossEntropyLoss(ignore_index=IGNORE)
+        self.ce_takes_uint8 = ce_loss is not None
         self.mse = nn.MSELoss()
         self.fa = fa_loss
         self.opt = torch.optim.SGD(self.model.parameters(), lr=LR, momentum=MOMENTUM, weight_decay=WEIGHT_DECAY)
 
     def losses(self, img, org, target):
         sssr, sisr, sssr_t, sisr_t = self.model(img)
-        ce = self.ce(sssr, target.long())
+        ce = self.ce(sssr, target if self.ce_takes_uint8 else target.long())
         mse = W1 * self.mse(sisr, org)
         fa = W2 * self.fa(sssr_t, sisr_t)
         return ce, mse, fa, (sssr, sisr, sssr_t, sisr_t)

@@ -123,6 +123,24 @@ int dsrl_seg_counts_from_logits(const float *logits, const void *target, int tar
                                 int64_t num_updates, int64_t batch, int64_t hw, int num_classes,
                                 int ignore_label, int64_t *counts, int64_t *pred_out, dsrl_stream_t stream);
 
+/* ---- cross-entropy with an ignore label (the caller-side loss next to FA; replaces
+ *      `t.nn.CrossEntropyLoss(ignore_index=IGNORE_CLASS_LABEL)`, train_or_resume.py:116,435, i.e. torch's
+ *      log_softmax + nll_loss forward and their two backward kernels, by one pass each) ----------------------- */
+
+/* logits: (B, C, HW) fp32 NCHW; target: (B, HW) of `target_dtype` (uint8 as the dataset delivers it, or the
+ * int64 of `target.long()`).  Pixels whose target equals ignore_index -- or lies outside [0, C): torch raises a
+ * device assert there, this library treats them as ignored -- contribute neither loss nor gradient.
+ * reduction: DSRL_REDUCE_MEAN (sum / number of valid pixels; NaN when there is none, like torch) or DSRL_REDUCE_SUM.
+ * saved: dsrl_ce_saved_bytes(B, HW) bytes, 16-byte aligned; holds the per-pixel log-sum-exp and the valid count
+ * for dsrl_ce_backward, which writes dlogits = grad_out * dloss/dlogits (grad_out: 1 device float). */
+size_t dsrl_ce_saved_bytes(int B, int64_t HW);
+int dsrl_ce_forward(const float *logits, const void *target, int target_dtype, int B, int C, int64_t HW,
+                    int64_t ignore_index, int reduction, float *loss_out, void *saved, size_t saved_bytes,
+                    dsrl_stream_t stream);
+int dsrl_ce_backward(const float *logits, const void *target, int target_dtype, int B, int C, int64_t HW,
+                     int64_t ignore_index, int reduction, const void *saved, size_t saved_bytes,
+                     const float *grad_out, float *dlogits, dsrl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,27 @@ def expand_pooled(gp, k, H, W):
     out = np.zeros((B, C, H, W), dtype=gp.dtype)
     out[:, :, : h * k, : w * k] = np.repeat(np.repeat(gp, k, 2), k, 3)
     return out
+
+
+# ---- cross-entropy cases: name -> (shape (B,C,H,W), target dtype, ignore_index, reduction, logits scale, fraction ignored)
+CE_CASES = {
+    "plain_mean":  ((2, 19, 12, 20), "uint8", 255, "mean", 1.0, 0.1),
+    "plain_sum":   ((2, 19, 12, 20), "uint8", 255, "sum", 1.0, 0.1),
+    "long_m100":   ((3, 19, 8, 16), "int64", -100, "mean", 1.0, 0.2),
+    "ragged":      ((3, 5, 7, 9), "uint8", 255, "mean", 1.0, 0.1),
+    "int32_sum":   ((1, 3, 9, 11), "int32", 255, "sum", 1.0, 0.0),
+    "one_class":   ((2, 1, 4, 8), "uint8", 255, "mean", 1.0, 0.3),
+    "big_logits":  ((2, 19, 8, 8), "uint8", 255, "mean", 40.0, 0.1),
+    "all_ignored": ((1, 19, 4, 8), "uint8", 255, "mean", 1.0, 1.0),
+    "all_ign_sum": ((1, 19, 4, 8), "uint8", 255, "sum", 1.0, 1.0),
+}
+
+
+def ce_case(name, seed=54321):
+    shape, tdt, ignore, red, scale, frac = CE_CASES[name]
+    rng = np.random.default_rng([seed, sorted(CE_CASES).index(name)])
+    B, C, H, W = shape
+    x = (rng.standard_normal(shape) * scale).astype(np.float32)
+    t = rng.integers(0, C, (B, H, W)).astype(np.int64)
+    t[rng.random((B, H, W)) < frac] = ignore
+    return x, t.astype(np.dtype(tdt)), ignore, red

@@ -226,8 +226,30 @@ def make_seg():
     np.savez_compressed(os.path.join(HERE, "seg_golden.npz"), **out)
 
 
+def make_ce():
+    """torch.nn.CrossEntropyLoss(ignore_index=...) in float64 -- the third-party arithmetic behind train_or_resume.py:116,435."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from _inputs import CE_CASES, ce_case
+    out, names = {}, []
+    for name in CE_CASES:
+        x, t, ignore, red = ce_case(name)
+        a = torch.from_numpy(x).double().requires_grad_(True)
+        loss = torch.nn.CrossEntropyLoss(ignore_index=ignore, reduction=red)(a, torch.from_numpy(t.astype(np.int64)))
+        (loss * 0.7).backward()
+        out[f"{name}/loss64"] = np.float64(loss.item())
+        out[f"{name}/grad64"] = a.grad.numpy()
+        names.append(name)
+    out["names"] = np.array(names)
+    out["grad_out"] = np.float64(0.7)
+    np.savez_compressed(os.path.join(HERE, "ce_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if sys.argv[1:] == ["ce"]:
+        make_ce()
+        sys.exit(0)
     make_seg()
     make_pos()
     make_fa()
+    make_ce()
