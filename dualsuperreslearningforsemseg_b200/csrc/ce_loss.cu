@@ -29,7 +29,7 @@ inline size_t ce_lse_off(int B, long long HW) { return (kCePartialsOff + ce_bloc
 template <typename T> __device__ __forceinline__ long long ce_load_target(const T *t, long long i) { return (long long)t[i]; }
 
 // One thread = VEC consecutive pixels of one image; channel c of those pixels is one VEC*4-byte load, coalesced across the warp.
-template <typename TT, int VEC>
+template <typename TT, int VEC, int kCeChunk = 5>
 __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__restrict__ logits, const TT *__restrict__ target,
                                                                 int C, long long HW, long long ignore_index, int mean,
                                                                 unsigned char *__restrict__ saved, size_t lse_off, unsigned *ticket,
@@ -47,21 +47,38 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
         long long t[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { m[v] = -3.402823466e38f; s[v] = 0.f; xt[v] = 0.f; t[v] = (p0 + v < HW) ? ce_load_target(target, (long long)b * HW + p0 + v) : ignore_index; }
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
-            float xv[VEC];
-            if (VEC == 4) {
-                const uint4 q = ldg_stream_u4(x + (size_t)c * HW);
-                xv[0] = __uint_as_float(q.x); xv[1 % VEC] = __uint_as_float(q.y); xv[2 % VEC] = __uint_as_float(q.z); xv[3 % VEC] = __uint_as_float(q.w);
-            } else {
-                xv[0] = ldg_stream_f32(x + (size_t)c * HW);
+        // kCeChunk channels per round: all their loads are issued before any arithmetic, then one branch-free online-softmax
+        // update per pixel (chunk sizes 4..20 measured within 10 % of each other at the training shape; 5 was the fastest)
+        for (int c0 = 0; c0 < C; c0 += kCeChunk) {
+            float xv[kCeChunk][VEC];
+#pragma unroll
+            for (int u = 0; u < kCeChunk; ++u) {
+                if (c0 + u < C) {
+                    if (VEC == 4) {
+                        const uint4 q = ldg_stream_u4(x + (size_t)(c0 + u) * HW);
+                        xv[u][0] = __uint_as_float(q.x); xv[u][1 % VEC] = __uint_as_float(q.y); xv[u][2 % VEC] = __uint_as_float(q.z); xv[u][3 % VEC] = __uint_as_float(q.w);
+                    } else {
+                        xv[u][0] = ldg_stream_f32(x + (size_t)(c0 + u) * HW);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) xv[u][v] = -3.402823466e38f;
+                }
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float xn = xv[v];
-                if (xn > m[v]) { s[v] = s[v] * __expf(m[v] - xn) + 1.f; m[v] = xn; }     // m starts at -FLT_MAX (finite): -inf logits add exp(-inf) = 0
-                else s[v] += __expf(xn - m[v]);
-                if ((long long)c == t[v]) xt[v] = xn;
+                float cm = xv[0][v];
+#pragma unroll
+                for (int u = 1; u < kCeChunk; ++u) cm = fmaxf(cm, xv[u][v]);
+                const float mn = fmaxf(m[v], cm);
+                float acc = s[v] * __expf(m[v] - mn);
+#pragma unroll
+                for (int u = 0; u < kCeChunk; ++u) {
+                    acc += __expf(xv[u][v] - mn);              // padding channels: exp(-FLT_MAX - mn) = 0
+                    if ((long long)(c0 + u) == t[v]) xt[v] = xv[u][v];
+                }
+                s[v] = acc;
+                m[v] = mn;
             }
         }
         float lse[VEC];
@@ -128,20 +145,32 @@ __global__ void __launch_bounds__(kCeThreads) ce_backward_kernel(const float *__
         const bool valid = t[v] != ignore_index && t[v] >= 0 && t[v] < C;
         sc[v] = valid ? scale : 0.f;
     }
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) {
-        float xv[VEC], o[VEC];
-        if (VEC == 4) {
-            const uint4 q = ldg_stream_u4(x + (size_t)c * HW);
-            xv[0] = __uint_as_float(q.x); xv[1 % VEC] = __uint_as_float(q.y); xv[2 % VEC] = __uint_as_float(q.z); xv[3 % VEC] = __uint_as_float(q.w);
-        } else {
-            xv[0] = ldg_stream_f32(x + (size_t)c * HW);
+    // 4 channels per round: a read + write stream wants resident threads more than registers (8 per round measured slower)
+    constexpr int kCh = 4;
+    for (int c0 = 0; c0 < C; c0 += kCh) {
+        float xv[kCh][VEC];
+#pragma unroll
+        for (int u = 0; u < kCh; ++u) {
+            if (c0 + u < C) {
+                if (VEC == 4) {
+                    const uint4 q = ldg_stream_u4(x + (size_t)(c0 + u) * HW);
+                    xv[u][0] = __uint_as_float(q.x); xv[u][1 % VEC] = __uint_as_float(q.y); xv[u][2 % VEC] = __uint_as_float(q.z); xv[u][3 % VEC] = __uint_as_float(q.w);
+                } else {
+                    xv[u][0] = ldg_stream_f32(x + (size_t)(c0 + u) * HW);
+                }
+            }
         }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            o[v] = sc[v] != 0.f ? (__expf(xv[v] - lse[v]) - ((long long)c == t[v] ? 1.f : 0.f)) * sc[v] : 0.f;
-        if (VEC == 4) __stcs(reinterpret_cast<float4 *>(g + (size_t)c * HW), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
-        else g[(size_t)c * HW] = o[0];
+        for (int u = 0; u < kCh; ++u) {
+            if (c0 + u < C) {
+                float o[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    o[v] = sc[v] != 0.f ? (__expf(xv[u][v] - lse[v]) - ((long long)(c0 + u) == t[v] ? 1.f : 0.f)) * sc[v] : 0.f;
+                if (VEC == 4) __stcs(reinterpret_cast<float4 *>(g + (size_t)(c0 + u) * HW), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
+                else g[(size_t)(c0 + u) * HW] = o[0];
+            }
+        }
     }
 }
 
