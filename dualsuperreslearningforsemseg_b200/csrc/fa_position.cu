@@ -62,8 +62,9 @@ struct PosGeom {
     int q_resident, stages;
     int jsplit;             // gradient variant: the column tiles of one row tile are spread over jsplit CTAs (small grids)
     int pair, pair_stages;  // CTA-pair form of the gradient variant usable for this geometry; its ring depth
-    int half, nkh, half_stages;   // FP16-operand pair form (kind::f16): usable + requested; Kc / 64 chunks; its ring depth
-    size_t smem_bytes, pair_smem_bytes, half_smem_bytes;
+    int half, nkh, half_stages;   // FP16 operands (kind::f16) requested; Kc / 64 chunks; ring depth of the pair form
+    int half_pair, half1_stages;  // pair form usable for this geometry; ring depth of the single-CTA form
+    size_t smem_bytes, pair_smem_bytes, half_smem_bytes, half1_smem_bytes;
 };
 
 struct PosWs { size_t Fpm, Fcm, FpmH, FcmH, nrm, partials, opart, total; };
@@ -121,14 +122,20 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     }
     // FP16 operands: 64 channels per 128-byte row, so the CTA's own rows (<= 8 boxes) are always resident
     g.nkh = (g.Kc + 63) / 64;
-    g.half = half && !g.split && g.pair && (g.G == 1 || g.gcnt[0] == g.gcnt[1]);
+    g.half = half && !g.split;
+    g.half_pair = g.half && g.pair && (g.G == 1 || g.gcnt[0] == g.gcnt[1]);
+    {
+        g.half1_stages = (avail - g.nkh) / 2;
+        if (g.half1_stages > 6) g.half1_stages = 6;
+        g.half1_smem_bytes = 1024 + (size_t)g.nkh * kBoxBytes + (size_t)g.half1_stages * 2 * kBoxBytes + kSmemAux;
+    }
     {
         const size_t qbytes = (size_t)g.nkh * kBoxBytes;
         g.half_stages = (int)((kSmemBudget - 1024 - kSmemAux - qbytes) / (2 * kBoxBytes));
         if (g.half_stages > 6) g.half_stages = 6;
         if (const char *e = getenv("DSRL_POS_STAGES")) { const int v = atoi(e); if (v >= 2 && v < g.half_stages) g.half_stages = v; }
         g.half_smem_bytes = 1024 + qbytes + (size_t)g.half_stages * 2 * kBoxBytes + kSmemAux;
-        if (g.half_stages < 2) g.half = 0;
+        if (g.half_stages < 2) g.half_pair = 0;
     }
     if (const char *force = getenv("DSRL_POS_JSPLIT")) {          // test hook: force 1, 2 or 4 (when it divides the tile count)
         const int s = atoi(force);
@@ -461,17 +468,20 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
 // kGrad:     also accumulate the gradient contraction (otherwise loss only, tiles j >= i by symmetry)
 // kSplit:    3xTF32 -- D = hi*hi + hi*lo + lo*hi with the lo parts as extra operand boxes
 // kResident: the CTA's own operand rows Q_i stay in shared memory for all tiles (otherwise streamed with K_j)
-template <bool kGrad, bool kSplit, bool kResident>
+// kHalf:     FP16 operands (kind::f16, K = 16; 64 elements per 128-byte operand row), see fa_pos_tiles_pair
+template <bool kGrad, bool kSplit, bool kResident, bool kHalf = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ CUtensorMap tm_cm, const PosGeom g, const PosArgs a) {
     extern __shared__ unsigned char smraw[];
     const uint32_t raw = smem_u32(smraw);
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);     // 1024-byte aligned: swizzle-128B tiles
+    static_assert(!kHalf || (kResident && !kSplit), "FP16 form: resident rows, single pass");
+    constexpr int kElems = kHalf ? 64 : kChunk;                 // operand elements per 128-byte row
     constexpr int kSB = stage_boxes(kResident);                 // boxes per stage
     constexpr int kStageBytes = kSB * kBoxBytes;
     constexpr int kU = (kResident ? 0 : (kSplit ? 2 : 1)) + (kSplit ? 2 : 1);   // operand boxes per 32-channel chunk: [Q hi, Q lo,] K hi [, K lo]
     constexpr int kUPS = kSB / kU;                              // chunks per stage
-    const int S = g.stages, nkc = g.nkc, nq = kResident ? nkc * (kSplit ? 2 : 1) : 0;
+    const int S = kHalf ? g.half1_stages : g.stages, nkc = kHalf ? g.nkh : g.nkc, nq = kResident ? nkc * (kSplit ? 2 : 1) : 0;
     unsigned char *qreg = sm;
     unsigned char *ring = sm + (size_t)nq * kBoxBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
@@ -525,7 +535,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, (uint32_t)nq * kBoxBytes);
                 for (int kc = 0; kc < nq; ++kc)
-                    tma_load_2d(qreg + (size_t)kc * kBoxBytes, &tm_pm, q_full, (kc % nkc) * kChunk, row_q + (kc / nkc) * lo_rows);
+                    tma_load_2d(qreg + (size_t)kc * kBoxBytes, &tm_pm, q_full, (kc % nkc) * kElems, row_q + (kc / nkc) * lo_rows);
             }
             __syncwarp();
         }
@@ -549,7 +559,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
                 const int nu = min(kUPS, nkc - kc0);
                 STAGE_FILL(nu * kU, {
                     for (int u = 0; u < nu; ++u) {
-                        const int c0 = (kc0 + u) * kChunk;
+                        const int c0 = (kc0 + u) * kElems;
                         unsigned char *d = dst + (size_t)u * kU * kBoxBytes;
                         if (!kResident) {
                             tma_load_2d(d, &tm_pm, bar, c0, row_q); d += kBoxBytes;
@@ -563,13 +573,13 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         };
         // B boxes of the gradient contraction, flattened over (32-position chunk jc, 128-channel box bx), kSB per stage
         auto load_v = [&](int j) {
-            const int nb = (kTile / kChunk) * nbox;          // 4 or 8
+            const int nb = (kTile / kElems) * nbox;          // 4 or 8 (FP16: 2 or 4)
             for (int i0 = 0; i0 < nb; i0 += kSB) {
                 const int n = min(kSB, nb - i0);
                 STAGE_FILL(n, {
                     for (int h = 0; h < n; ++h) {
                         const int jc = (i0 + h) / nbox, bx = (i0 + h) - jc * nbox;
-                        tma_load_2d(dst + (size_t)h * kBoxBytes, &tm_cm, bar, j * kTile + jc * kChunk, b * g.Kc + gbeg + bx * kTile);
+                        tma_load_2d(dst + (size_t)h * kBoxBytes, &tm_cm, bar, j * kTile + jc * kElems, b * g.Kc + gbeg + bx * kTile);
                     }
                 });
             }
@@ -598,11 +608,13 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         const long long t_begin = clock64();
         constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kStageDesc = kStageBytes >> 4;    // in descriptor address units (16 B)
         const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
-        const uint32_t id_pos = idesc_tf32(kTile, kTile, false), id_neg = idesc_tf32(kTile, kTile, true);
+        const uint32_t id_pos = kHalf ? idesc_f16(kTile, kTile, false) : idesc_tf32(kTile, kTile, false);
+        const uint32_t id_neg = kHalf ? idesc_f16(kTile, kTile, true) : idesc_tf32(kTile, kTile, true);
         const int last_rows = gN - (nbox - 1) * kTile;                                   // last channel box may be narrower
-        const uint32_t id_last = idesc_tf32(kTile, last_rows, false), id_wide = idesc_tf32(kTile, 2 * kTile, false);
+        const uint32_t id_last = kHalf ? idesc_f16(kTile, last_rows, false) : idesc_tf32(kTile, last_rows, false);
+        const uint32_t id_wide = kHalf ? idesc_f16(kTile, 2 * kTile, false) : idesc_tf32(kTile, 2 * kTile, false);
         const bool wide = nbox == 2 && last_rows == kTile;                               // 256 channels: N = 256 instructions
-        const int kc_neg = g.C1p / kChunk;                                               // first chunk of branch 2 (subtracted)
+        const int q_neg = g.C1p / (kElems / 4);                                          // first K step of branch 2 (subtracted)
 #define RING_TAKE(desc_out, slot_out)                                                      \
         do {                                                                               \
             TWAIT(w_full, mbar_wait(&full[slot], ph, 2));                                  \
@@ -610,12 +622,12 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             slot_out = slot;                                                               \
             RING_ADVANCE();                                                                \
         } while (0)
-#define MMA4_SS(dcol, ad, bd, id, acc0)                                                    \
-        do {                                                                               \
-            mma_tf32_ss(dcol, (ad), (bd), id, acc0);                                       \
-            mma_tf32_ss(dcol, (ad) + 2, (bd) + 2, id, 1);                                  \
-            mma_tf32_ss(dcol, (ad) + 4, (bd) + 4, id, 1);                                  \
-            mma_tf32_ss(dcol, (ad) + 6, (bd) + 6, id, 1);                                  \
+#define MMA4_SS(dcol, ad, bd, q0, acc0)                                                                    \
+        do {                                                                                               \
+            mma_ss<kHalf>(dcol, (ad), (bd), (q0) >= q_neg ? id_neg : id_pos, acc0);                        \
+            mma_ss<kHalf>(dcol, (ad) + 2, (bd) + 2, (q0) + 1 >= q_neg ? id_neg : id_pos, 1);               \
+            mma_ss<kHalf>(dcol, (ad) + 4, (bd) + 4, (q0) + 2 >= q_neg ? id_neg : id_pos, 1);               \
+            mma_ss<kHalf>(dcol, (ad) + 6, (bd) + 6, (q0) + 3 >= q_neg ? id_neg : id_pos, 1);               \
         } while (0)
         // D(i, j0+jj) -> TMEM columns kColD + (jj&1)*128
         auto gemm_d = [&](int jj) {
@@ -636,11 +648,10 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
                             const uint64_t a_lo = kResident ? q_desc + (uint64_t)(nkc + kc) * kBoxDesc : ub + kBoxDesc;
                             const uint64_t b_hi = kResident ? ub : ub + (kSplit ? 2 : 1) * kBoxDesc;
                             const uint64_t b_lo = b_hi + kBoxDesc;
-                            const uint32_t id = kc >= kc_neg ? id_neg : id_pos;
-                            MMA4_SS(dcol, a_hi, b_hi, id, kc != 0);
+                            MMA4_SS(dcol, a_hi, b_hi, 4 * kc, kc != 0);
                             if (kSplit) {
-                                MMA4_SS(dcol, a_hi, b_lo, id, 1);
-                                MMA4_SS(dcol, a_lo, b_hi, id, 1);
+                                MMA4_SS(dcol, a_hi, b_lo, 4 * kc, 1);
+                                MMA4_SS(dcol, a_lo, b_hi, 4 * kc, 1);
                             }
                         }
                     }
@@ -655,7 +666,8 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
             const int buf = jj & 1;
             const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
             TWAIT(w_p, mbar_wait(&p_full[buf], (jj >> 1) & 1, 5));
-            const int nb = (kTile / kChunk) * nbox;
+            const int nb = (kTile / kElems) * nbox;
+            constexpr int kPCols = kHalf ? 64 : kChunk;      // sign-tile columns per V box: TF32 32; FP16 box jc = packed columns [64 jc, 64 jc + 32)
             for (int i0 = 0; i0 < nb; i0 += kSB) {
                 uint64_t bd; int sb;
                 RING_TAKE(bd, sb);
@@ -666,10 +678,10 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 #pragma unroll
                         for (int pr = 0; pr < kSB / 2; ++pr) {
                             const int jc = (i0 >> 1) + pr;
-                            const uint32_t acol = pcol + (uint32_t)(jc * kChunk);
+                            const uint32_t acol = pcol + (uint32_t)(jc * kPCols);
                             const uint64_t bp = bd + (uint64_t)(2 * pr) * kBoxDesc;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) mma_tf32_ts(tmem, acol + ks * 8, bp + 2 * ks, id_wide, (jj | jc | ks) != 0);
+                            for (int ks = 0; ks < 4; ++ks) mma_ts<kHalf>(tmem, acol + ks * 8, bp + 2 * ks, id_wide, (jj | jc | ks) != 0);
                         }
                     } else {
 #pragma unroll
@@ -679,8 +691,8 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
                                 const uint32_t id = bx == nbox - 1 ? id_last : id_pos;
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
-                                    mma_tf32_ts(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kChunk + ks * 8),
-                                                bd + (uint64_t)h * kBoxDesc + 2 * ks, id, (jj | jc | ks) != 0);
+                                    mma_ts<kHalf>(tmem + (uint32_t)bx * kTile, pcol + (uint32_t)(jc * kPCols + ks * 8),
+                                                  bd + (uint64_t)h * kBoxDesc + 2 * ks, id, (jj | jc | ks) != 0);
                             }
                         }
                     }
@@ -715,7 +727,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         EpiCtx c;
         c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
         c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
-        epilogue_role<kGrad, false>(g, a, c);
+        epilogue_role<kGrad, false, kHalf>(g, a, c);
     }
 #undef RING_ADVANCE
 
@@ -1103,7 +1115,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     if (precision != DSRL_PREC_TF32 && precision != DSRL_PREC_FP32 && precision != DSRL_PREC_F16)
         DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass), F16 (kind::f16 operands) or FP32 (3xTF32 split)");
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, precision == DSRL_PREC_FP32, g, precision == DSRL_PREC_F16 && need_grad))
+    if (!make_geom(B, C1, C2, H, W, k, precision == DSRL_PREC_FP32, g, precision == DSRL_PREC_F16))
         DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry B=%d C=(%d,%d) H=%d W=%d k=%d (channels per branch <= 256)", B, C1, C2, H, W, k);
     const PosWs wo = make_ws(g);
     const PosSaved so = make_saved(g);
@@ -1141,7 +1153,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     a.loss_div = Z;
     a.grad_scale = (float)(2.0 / Z);
     const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
-    if (need_grad && g.pair) {
+    if (need_grad && g.pair && (!g.half || g.half_pair)) {
         // both channel groups have the same width when there are two (C1p == C2p) or the V box height would differ per group
         const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];
         if (same) {
@@ -1178,6 +1190,24 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
         if ((rc = opt_in_smem(fa_pos_tiles<GR, SP, RS>, g.smem_bytes))) return rc;                        \
         fa_pos_tiles<GR, SP, RS><<<grid, kThreads, g.smem_bytes, st>>>(tm_pm, tm_cm, g, a);               \
     } while (0)
+    if (g.half) {                  // FP16 operands on the single-CTA kernel: forward only, odd tile counts, unequal channel groups
+        if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
+        if ((rc = make_map(&tm_cm, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, kTile, true))) return rc;
+        if (need_grad) {
+            if ((rc = opt_in_smem(fa_pos_tiles<true, false, true, true>, g.half1_smem_bytes))) return rc;
+            fa_pos_tiles<true, false, true, true><<<grid, kThreads, g.half1_smem_bytes, st>>>(tm_pm, tm_cm, g, a);
+        } else {
+            if ((rc = opt_in_smem(fa_pos_tiles<false, false, true, true>, g.half1_smem_bytes))) return rc;
+            fa_pos_tiles<false, false, true, true><<<grid, kThreads, g.half1_smem_bytes, st>>>(tm_pm, tm_cm, g, a);
+        }
+        DSRL_LAUNCH_CHECK();
+        if (need_grad && g.jsplit > 1) {
+            if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
+            fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, Fcm, nrm, a.grad_scale, a.dP);
+            DSRL_LAUNCH_CHECK();
+        }
+        return DSRL_OK;
+    }
     const int variant = (need_grad ? 4 : 0) | (g.split ? 2 : 0) | (g.q_resident ? 1 : 0);
     switch (variant) {
         case 0: LAUNCH_TILES(false, false, false); break;

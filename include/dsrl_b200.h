@@ -52,8 +52,7 @@ enum dsrl_precision {
     DSRL_PREC_TF32 = 1,   /* position mode default: one tcgen05 kind::tf32 pass, FP32 accumulate in TMEM */
     DSRL_PREC_BF16 = 2,   /* reserved: rejected with DSRL_ERR_UNSUPPORTED (a single BF16 pass misses the loss tolerance) */
     DSRL_PREC_F16 = 3     /* position mode: FP16 operands (the 11-bit significand of TF32; unit-norm features need no more
-                             exponent range), tcgen05 kind::f16 at twice the TF32 rate, FP32 accumulate.  Used by the
-                             CTA-pair gradient kernel; geometries it does not cover run the TF32 kernels */
+                             exponent range), tcgen05 kind::f16 at twice the TF32 rate, FP32 accumulate */
 };
 
 enum dsrl_dtype { DSRL_U8 = 0, DSRL_I32 = 1, DSRL_I64 = 2 };

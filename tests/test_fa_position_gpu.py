@@ -249,6 +249,8 @@ def test_full_size_c256_sampled_rows():
     g2 = d2[0].reshape(256, -1)[:, rows]
     assert relnorm(g1, o1) <= GRAD_RTOL and relnorm(g2, o2) <= GRAD_RTOL, (relnorm(g1, o1), relnorm(g2, o2))
     assert abs(loss_h - loss) <= LOSS_RTOL * abs(loss), (loss_h, loss)
+    loss_hn, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="f16")     # forward-only FP16 kernel (single CTA, symmetric tiles)
+    assert abs(loss_hn - loss_h) <= 1e-6 * abs(loss_h), (loss_hn, loss_h)
     loss_ng, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="tf32")
     loss_32, _, _ = run(x1, x2, 1, "mean", need_grad=False, precision="fp32")
     assert abs(loss - loss_ng) <= 1e-6 * abs(loss) and abs(loss - loss_32) <= LOSS_RTOL * abs(loss), (loss, loss_ng, loss_32)
