@@ -331,22 +331,40 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
 #pragma unroll
                 for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
             }
+            // |D| sum; the smallest magnitude tells whether any entry is exactly zero (the forced diagonal, exact ties), the
+            // only entries whose sign is 0: everything else takes the short path, sign bit OR 1.0 -- one logic op per entry
+            // (FP16: per pair of entries) instead of a compare + select each
+            float zmin = 3.0e38f;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
                 const float x = __uint_as_float(v[e]);
                 tsum += fabsf(x);
-                if (kGrad) v[e] = (v[e] & 0x80000000u) | (x != 0.f ? 0x3f800000u : 0u);     // sign(x) as a TF32 value
+                zmin = fminf(zmin, fabsf(x));
             }
-            if (kGrad && !kHalf) tmem_st32(taddr, v);
+            if (kGrad && !kHalf) {
+                if (zmin != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = (v[e] & 0x80000000u) | 0x3f800000u;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = (v[e] & 0x80000000u) | ((v[e] & 0x7fffffffu) ? 0x3f800000u : 0u);   // sign(x) as a TF32 value
+                }
+                tmem_st32(taddr, v);
+            }
             if (kGrad && kHalf) {
                 // FP16 sign tile, two positions per 32-bit column.  The columns a warp writes ([64*half, 64*half + 32) of
                 // the tile) lie inside the column range it has already read, so the two halves never race.
                 uint32_t pk[16];
+                if (zmin != 0.f) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const uint32_t lo = v[2 * e], hi = v[2 * e + 1];     // already +-1.0f / 0 as FP32 bit patterns
-                    pk[e] = ((lo >> 16) & 0x8000u) | ((lo & 0x7fffffffu) ? 0x3c00u : 0u) |
-                            ((((hi >> 16) & 0x8000u) | ((hi & 0x7fffffffu) ? 0x3c00u : 0u)) << 16);
+                    for (int e = 0; e < 16; ++e) pk[e] = (__byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u) | 0x3c003c00u;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
+                        pk[e] = ((lo >> 16) & 0x8000u) | ((lo & 0x7fffffffu) ? 0x3c00u : 0u) |
+                                ((((hi >> 16) & 0x8000u) | ((hi & 0x7fffffffu) ? 0x3c00u : 0u)) << 16);
+                    }
                 }
                 tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + half * 64 + (cg & 1) * 16), pk);
             }
