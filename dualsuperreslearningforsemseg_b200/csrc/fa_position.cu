@@ -371,7 +371,8 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         }
         if (kGrad) tmem_st_wait();
         fence_before_sync();
-        if (kPair) mbar_arrive_leader(&p_full[buf]); else mbar_arrive(&p_full[buf]);
+        __syncwarp();                     // every lane's tcgen05.st has completed and is fenced: one arrival per warp
+        if (lane == 0) { if (kPair) mbar_arrive_leader(&p_full[buf]); else mbar_arrive(&p_full[buf]); }
         acc += (double)tsum * ((kGrad || diag) ? 1.0 : 2.0);
     }
 #ifdef DSRL_POS_TIMING
@@ -528,7 +529,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         prefetch_tmap(&tm_cm);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], kEpiThreads); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], kEpiWarps); }
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -814,7 +815,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         prefetch_tmap(&tm_v);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 2 * kEpiThreads); }     // both CTAs' epilogue threads
+        for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&p_full[i], 2 * kEpiWarps); }       // one arrival per epilogue warp of both CTAs
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
