@@ -244,13 +244,13 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
     for (int c = warp; c < g.Kc; c += 8) {            // channel-major rows: 128 contiguous bytes per warp store
         const int br = c >= g.C1p;
         const float f = T[c * 33 + lane] * s_inv[br][lane];
-        Fcm[((size_t)b * g.Kc + c) * g.Npad + p] = round_tf32(f);
+        if (Fcm) Fcm[((size_t)b * g.Kc + c) * g.Npad + p] = round_tf32(f);
         if (FcmH) FcmH[((size_t)b * g.Kc + c) * g.Npad + p] = __float2half_rn(f);
     }
     for (int q = warp; q < 32; q += 8) {              // position-major rows: Kc contiguous floats per position
         float *dst = Fpm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
         float *dst_lo = dst + (size_t)g.B * g.Npad * g.Kc;
-        for (int c = lane; c < g.Kc; c += 32) {
+        for (int c = lane; Fpm && c < g.Kc; c += 32) {
             const float f = T[c * 33 + q] * s_inv[c >= g.C1p][q], hi = round_tf32(f);
             dst[c] = hi;
             if (g.split) dst_lo[c] = round_tf32(f - hi);
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
 // ---------------------------------------------------------------------------------------------------------------
 struct PosArgs {
     const float *Fpm;
+    const __half *FpmH;  // FP16 form: the only position-major copy that exists
     const float *nrm;
     float *dP;
     float *opart;       // jsplit > 1: raw partial accumulators (jsplit, B, Npad, Kc)
@@ -297,6 +298,15 @@ struct EpiCtx {
     uint32_t tmem;
     int itile, js, grp, b, j0, nt, gN, gbeg, T;
 };
+
+// four consecutive channels of the normalised feature row at channel c (fp32 copy, or the FP16 copy of the FP16 form)
+template <bool kHalf>
+__device__ __forceinline__ float4 load_f4(const float *frow, const __half *frow_h, int c) {
+    if (!kHalf) return __ldg(reinterpret_cast<const float4 *>(frow + c));
+    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(frow_h + c));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&q.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 template <bool kGrad, bool kPair, bool kHalf = false>
 __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a, const EpiCtx &c) {
@@ -404,6 +414,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         fence_after_sync();
         const int row = itile * kTile + r;
         const float *frow = a.Fpm + ((size_t)b * g.Npad + row) * g.Kc;
+        const __half *frow_h = a.FpmH + ((size_t)b * g.Npad + row) * g.Kc;
         for (int br = 0; br < 2; ++br) {
             const int cb = br ? g.C1p : 0, ce = br ? g.Kc : g.C1p;         // channel range of the branch
             if (cb < gbeg || ce > gbeg + gN) continue;                     // not in this CTA's group
@@ -416,7 +427,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
                 tmem_ld_wait();
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
+                    const float4 f = load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
                     proj = fmaf(f.x, __uint_as_float(v[e4 * 4 + 0]), proj);
                     proj = fmaf(f.y, __uint_as_float(v[e4 * 4 + 1]), proj);
                     proj = fmaf(f.z, __uint_as_float(v[e4 * 4 + 2]), proj);
@@ -438,7 +449,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
                 float *dst = a.dP + ((size_t)b * g.Kc + c0) * g.Npad + row;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 f = __ldg(reinterpret_cast<const float4 *>(frow + c0) + e4);
+                    const float4 f = load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
                     dst[(size_t)(e4 * 4 + 0) * g.Npad] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale;
                     dst[(size_t)(e4 * 4 + 1) * g.Npad] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale;
                     dst[(size_t)(e4 * 4 + 2) * g.Npad] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale;
@@ -984,7 +995,9 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 // jsplit > 1: sum the partial accumulators, apply the normalisation Jacobian, store dP channel-major
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
-                                                      const float *__restrict__ nrm, float grad_scale, float *__restrict__ dP) {
+                                                      const __half *__restrict__ FcmH, const float *__restrict__ nrm, float grad_scale,
+                                                      float *__restrict__ dP) {
+    auto feat = [&](size_t o) { return Fcm ? Fcm[o] : __half2float(FcmH[o]); };      // FP16 form: only the FP16 copy exists
     extern __shared__ float T[];                     // [Kc][33] summed accumulator of a 32-position strip
     __shared__ float s_proj[2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1000,7 +1013,7 @@ __global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *_
     if (warp < 2) {                                   // proj = <Fh_i, O_i> over the channels of branch `warp`
         const int c0 = warp ? g.C1p : 0, c1 = warp ? g.Kc : g.C1p;
         float s = 0.f;
-        for (int c = c0; c < c1; ++c) s = fmaf(Fcm[((size_t)b * g.Kc + c) * g.Npad + p0 + lane], T[c * 33 + lane], s);
+        for (int c = c0; c < c1; ++c) s = fmaf(feat(((size_t)b * g.Kc + c) * g.Npad + p0 + lane), T[c * 33 + lane], s);
         const float n = nrm[((size_t)b * 2 + warp) * g.Npad + p0 + lane];
         s_proj[warp][lane] = n > 1e-12f ? s : 0.f;    // F/eps branch of the clamp: no projection
     }
@@ -1010,7 +1023,7 @@ __global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *_
         const float n = nrm[((size_t)b * 2 + br) * g.Npad + p0 + lane];
         const float scale = (br ? -grad_scale : grad_scale) / fmaxf(n, 1e-12f);
         const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
-        dP[o] = (T[c * 33 + lane] - Fcm[o] * s_proj[br][lane]) * scale;
+        dP[o] = (T[c * 33 + lane] - feat(o) * s_proj[br][lane]) * scale;
     }
 }
 
@@ -1151,7 +1164,8 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     if (rc) return rc;
     __half *FpmH = g.half ? reinterpret_cast<__half *>(ws + wo.FpmH) : nullptr;
     __half *FcmH = g.half ? reinterpret_cast<__half *>(ws + wo.FcmH) : nullptr;
-    fa_pos_pack<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, Fpm, Fcm, nrm, FpmH, FcmH);
+    // FP16 form: the FP16 copies are the only ones written (and read back by the normalisation Jacobian)
+    fa_pos_pack<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH);
     DSRL_LAUNCH_CHECK();
 
     CUtensorMap tm_pm, tm_cm;
@@ -1161,7 +1175,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     unsigned *ticket = next_ticket_slot();
     if (!ticket) return DSRL_ERR_CUDA;
     PosArgs a;
-    a.Fpm = Fpm; a.nrm = nrm;
+    a.Fpm = Fpm; a.FpmH = FpmH; a.nrm = nrm;
     a.dP = reinterpret_cast<float *>(saved + so.dP);
     a.opart = reinterpret_cast<float *>(ws + wo.opart);
     a.partials = reinterpret_cast<double *>(ws + wo.partials);
@@ -1198,7 +1212,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
             DSRL_LAUNCH_CHECK();
             if (g.jsplit > 1) {
                 if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-                fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, Fcm, nrm, a.grad_scale, a.dP);
+                fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP);
                 DSRL_LAUNCH_CHECK();
             }
             return DSRL_OK;
@@ -1222,7 +1236,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
         DSRL_LAUNCH_CHECK();
         if (need_grad && g.jsplit > 1) {
             if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-            fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, Fcm, nrm, a.grad_scale, a.dP);
+            fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP);
             DSRL_LAUNCH_CHECK();
         }
         return DSRL_OK;
@@ -1242,7 +1256,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     DSRL_LAUNCH_CHECK();
     if (need_grad && g.jsplit > 1) {
         if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-        fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, Fcm, nrm, a.grad_scale, a.dP);
+        fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP);
     }
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
