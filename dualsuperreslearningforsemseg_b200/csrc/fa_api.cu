@@ -21,6 +21,9 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
 int fa_pos_backward(int precision, const float *x1, const float *x2, const void *saved, size_t saved_bytes,
                     const float *grad_out, float *dx1, float *dx2, int B, int C1, int C2, int H, int W, int k,
                     int reduction, void *ws, size_t ws_bytes, cudaStream_t st);
+int fa_pos_forward_backward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k,
+                            int reduction, const float *grad_out, float *loss_out, float *dx1, float *dx2, void *saved,
+                            size_t saved_bytes, void *ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace dsrl
 
 using namespace dsrl;
@@ -90,6 +93,9 @@ extern "C" int dsrl_fa_forward_backward(int mode, int precision, const float *x1
                                      workspace_bytes, st);
         if (rc != DSRL_ERR_UNSUPPORTED) return rc;       // DSRL_OK or a real error; otherwise fall through to the two-call path
     }
+    if (mode == DSRL_FA_POSITION)
+        return fa_pos_forward_backward(precision, x1, x2, B, C1, C2, H, W, k, reduction, grad_out, loss_out, dx1, dx2, saved, saved_bytes,
+                                       workspace, workspace_bytes, st);
     rc = dsrl_fa_forward(mode, precision, x1, x2, B, C1, C2, H, W, k, reduction, 1, loss_out, saved, saved_bytes, workspace,
                          workspace_bytes, stream);
     if (rc) return rc;

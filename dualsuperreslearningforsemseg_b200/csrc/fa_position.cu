@@ -278,6 +278,10 @@ struct PosArgs {
     float *loss_out;
     double loss_div;
     float grad_scale;   // 2 / Z
+    // fused forward + backward without pooling (k == 1): the finished gradient goes straight to dX, scaled by *go
+    float *dx[2];
+    const float *go;
+    int direct;
 };
 
 #ifdef DSRL_POS_TIMING
@@ -441,19 +445,26 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
             proj = projbuf[r] + projbuf[kTile + r];
             const bool dead = !(n > 1e-12f);                                // F/eps branch of the clamp: no projection
             const float scale = sgn / fmaxf(n, 1e-12f);
+            const float gmul = a.direct ? __ldg(a.go) : 1.f;            // applied as a second multiply: the bits fa_pos_unpool would produce
             if (dead) proj = 0.f;
+            const int Cr = br ? g.C2 : g.C1;
             for (int c0 = cb + 32 * half; c0 < ce; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(tmem + lane_addr + (uint32_t)(c0 - gbeg), v);
                 tmem_ld_wait();
-                float *dst = a.dP + ((size_t)b * g.Kc + c0) * g.Npad + row;
+                // dP (channel-major, padded), or -- fused forward + backward without pooling -- dX itself: (B, C, N), real
+                // channels and positions only
+                const size_t pitch = a.direct ? (size_t)g.N : (size_t)g.Npad;
+                float *dst = a.direct ? a.dx[br] + ((size_t)b * Cr + (c0 - cb)) * pitch + row
+                                      : a.dP + ((size_t)b * g.Kc + c0) * pitch + row;
+                const int nreal = a.direct ? (row < g.N ? Cr - (c0 - cb) : 0) : 32;      // channels of this strip that exist in dX
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
                     const float4 f = load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
-                    dst[(size_t)(e4 * 4 + 0) * g.Npad] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale;
-                    dst[(size_t)(e4 * 4 + 1) * g.Npad] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale;
-                    dst[(size_t)(e4 * 4 + 2) * g.Npad] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale;
-                    dst[(size_t)(e4 * 4 + 3) * g.Npad] = (__uint_as_float(v[e4 * 4 + 3]) - f.w * proj) * scale;
+                    if (e4 * 4 + 0 < nreal) dst[(size_t)(e4 * 4 + 0) * pitch] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale * gmul;
+                    if (e4 * 4 + 1 < nreal) dst[(size_t)(e4 * 4 + 1) * pitch] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale * gmul;
+                    if (e4 * 4 + 2 < nreal) dst[(size_t)(e4 * 4 + 2) * pitch] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale * gmul;
+                    if (e4 * 4 + 3 < nreal) dst[(size_t)(e4 * 4 + 3) * pitch] = (__uint_as_float(v[e4 * 4 + 3]) - f.w * proj) * scale * gmul;
                 }
             }
         }
@@ -996,7 +1007,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
                                                       const __half *__restrict__ FcmH, const float *__restrict__ nrm, float grad_scale,
-                                                      float *__restrict__ dP) {
+                                                      float *__restrict__ dP, float *dx1, float *dx2, const float *go) {
     auto feat = [&](size_t o) { return Fcm ? Fcm[o] : __half2float(FcmH[o]); };      // FP16 form: only the FP16 copy exists
     extern __shared__ float T[];                     // [Kc][33] summed accumulator of a 32-position strip
     __shared__ float s_proj[2][32];
@@ -1023,7 +1034,11 @@ __global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *_
         const float n = nrm[((size_t)b * 2 + br) * g.Npad + p0 + lane];
         const float scale = (br ? -grad_scale : grad_scale) / fmaxf(n, 1e-12f);
         const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
-        dP[o] = (T[c * 33 + lane] - feat(o) * s_proj[br][lane]) * scale;
+        const float val = (T[c * 33 + lane] - feat(o) * s_proj[br][lane]) * scale;
+        if (!go) { dP[o] = val; continue; }
+        // fused forward + backward without pooling: dX itself, real channels and positions only
+        const int cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
+        if (cc < Cr && p0 + lane < g.N) (br ? dx2 : dx1)[((size_t)b * Cr + cc) * g.N + p0 + lane] = val * __ldg(go);
     }
 }
 
@@ -1127,6 +1142,9 @@ int opt_in_smem(K kern, size_t bytes) {
 
 }  // namespace
 
+int fa_pos_backward(int precision, const float *, const float *, const void *saved_v, size_t saved_bytes, const float *grad_out,
+                    float *dx1, float *dx2, int B, int C1, int C2, int H, int W, int k, int, void *, size_t, cudaStream_t st);
+
 size_t fa_pos_saved_bytes(int B, int C1, int C2, int H, int W, int k) {
     PosGeom g;
     if (!make_geom(B, C1, C2, H, W, k, 0, g)) return 0;
@@ -1142,8 +1160,11 @@ size_t fa_pos_workspace_bytes(int B, int C1, int C2, int H, int W, int k) {
     return split_total > half_total ? split_total : half_total;
 }
 
-int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
-                   int need_grad, float *loss_out, void *saved_v, size_t saved_bytes, void *ws_v, size_t ws_bytes, cudaStream_t st) {
+// go / dx1 / dx2 (all non-null, k == 1): fused forward + backward -- the gradient kernel writes dX directly (scaled by *go) and the
+// saved blob's dP is not produced; *fused_out tells the caller that no backward launch is needed.
+int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
+                        int need_grad, float *loss_out, void *saved_v, size_t saved_bytes, void *ws_v, size_t ws_bytes, cudaStream_t st,
+                        const float *go, float *dx1, float *dx2, int *fused_out) {
     if (precision != DSRL_PREC_TF32 && precision != DSRL_PREC_FP32 && precision != DSRL_PREC_F16)
         DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass), F16 (kind::f16 operands) or FP32 (3xTF32 split)");
     PosGeom g;
@@ -1185,6 +1206,9 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)B * (double)g.N * (double)g.N : 1.0;
     a.loss_div = Z;
     a.grad_scale = (float)(2.0 / Z);
+    a.direct = need_grad && go && dx1 && dx2 && k == 1;
+    a.dx[0] = dx1; a.dx[1] = dx2; a.go = go;
+    if (fused_out) *fused_out = a.direct;
     const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
     if (need_grad && g.pair && (!g.half || g.half_pair)) {
         // both channel groups have the same width when there are two (C1p == C2p) or the V box height would differ per group
@@ -1212,7 +1236,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
             DSRL_LAUNCH_CHECK();
             if (g.jsplit > 1) {
                 if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-                fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP);
+                fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
                 DSRL_LAUNCH_CHECK();
             }
             return DSRL_OK;
@@ -1236,7 +1260,7 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
         DSRL_LAUNCH_CHECK();
         if (need_grad && g.jsplit > 1) {
             if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-            fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP);
+            fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
             DSRL_LAUNCH_CHECK();
         }
         return DSRL_OK;
@@ -1256,10 +1280,26 @@ int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C
     DSRL_LAUNCH_CHECK();
     if (need_grad && g.jsplit > 1) {
         if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-        fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP);
+        fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
     }
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
+}
+
+int fa_pos_forward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
+                   int need_grad, float *loss_out, void *saved_v, size_t saved_bytes, void *ws_v, size_t ws_bytes, cudaStream_t st) {
+    return fa_pos_forward_impl(precision, x1, x2, B, C1, C2, H, W, k, reduction, need_grad, loss_out, saved_v, saved_bytes, ws_v, ws_bytes, st,
+                               nullptr, nullptr, nullptr, nullptr);
+}
+
+int fa_pos_forward_backward(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
+                            const float *grad_out, float *loss_out, float *dx1, float *dx2, void *saved_v, size_t saved_bytes, void *ws_v,
+                            size_t ws_bytes, cudaStream_t st) {
+    int fused = 0;
+    int rc = fa_pos_forward_impl(precision, x1, x2, B, C1, C2, H, W, k, reduction, 1, loss_out, saved_v, saved_bytes, ws_v, ws_bytes, st,
+                                 grad_out, dx1, dx2, &fused);
+    if (rc || fused) return rc;
+    return fa_pos_backward(precision, x1, x2, saved_v, saved_bytes, grad_out, dx1, dx2, B, C1, C2, H, W, k, reduction, ws_v, ws_bytes, st);
 }
 
 int fa_pos_backward(int precision, const float *, const float *, const void *saved_v, size_t saved_bytes, const float *grad_out,

@@ -91,8 +91,10 @@ int dsrl_fa_backward(int mode, int precision, const float *x1, const float *x2, 
 
 /* Forward + backward in one call for callers that already know the upstream gradient (a captured training step with a
  * constant loss weight, cf. `w2 * FALoss()(..)` at train_or_resume.py:437): same results as dsrl_fa_forward(need_grad=1)
- * followed by dsrl_fa_backward.  Reference mode at the training shapes runs it as ONE kernel launch; every other case
- * is the two calls back to back.  reduction must be mean or sum; grad_out points to 1 float on the device. */
+ * followed by dsrl_fa_backward.  Reference mode at the training shapes runs it as ONE kernel launch; position mode
+ * without pooling (k == 1, both dx given) writes dX from the gradient kernel itself (no backward launch); every other
+ * case is the two calls back to back.  reduction must be mean or sum; grad_out points to 1 float on the device.
+ * `saved` is scratch here: do not pass it to dsrl_fa_backward afterwards. */
 int dsrl_fa_forward_backward(int mode, int precision, const float *x1, const float *x2, int B, int C1, int C2, int H,
                              int W, int k, int reduction, const float *grad_out, float *loss_out, float *dx1,
                              float *dx2, void *saved, size_t saved_bytes, void *workspace, size_t workspace_bytes,

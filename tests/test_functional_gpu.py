@@ -75,3 +75,24 @@ def test_host_pipeline_matches_whole_batch(mode, red, chunk):
             assert float((d - r).norm() / r.norm()) <= 2e-6
     with pytest.raises(ValueError):
         pipe(h1.to(dev), h2.to(dev))                                   # device tensors belong to FALoss / FAPlan
+
+
+@pytest.mark.parametrize("jsplit", ["1", "2"])
+@pytest.mark.parametrize("prec", ["tf32", "f16"])
+def test_fused_position_call_writes_dx_directly(jsplit, prec, monkeypatch):
+    """Position mode without pooling: dsrl_fa_forward_backward lets the gradient kernel (or fa_pos_jacobian when the column
+    range is split) write dX itself.  Ragged N (not a multiple of 128) and padded channel counts (40 and 33 -> 64 each):
+    bit-identical to forward + backward through autograd, and nothing is written outside the real channels / positions."""
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    monkeypatch.setenv("DSRL_POS_JSPLIT", jsplit)
+    dev = torch.device("cuda", 0)
+    x1, x2 = pos_margin_inputs(2, 40, 33, 25, 30, 54321)              # N = 750 -> 6 row tiles, last one ragged
+    x1, x2 = torch.from_numpy(x1).to(dev), torch.from_numpy(x2).to(dev)
+    go = torch.full((), 0.3, device=dev)
+    kw = {"affinity": "position", "precision": prec}
+    ref_loss, ref_d1, ref_d2 = _autograd(x1, x2, 1, go, **kw)
+    plan = FAPlan(tuple(x1.shape), tuple(x2.shape), subsample_factor=1, device=dev, **kw)
+    plan.dx1.fill_(float("nan")); plan.dx2.fill_(float("nan"))
+    loss, d1, d2 = plan.forward_backward(x1, x2, go)
+    torch.cuda.synchronize()
+    assert float(loss) == float(ref_loss) and torch.equal(d1, ref_d1) and torch.equal(d2, ref_d2)
