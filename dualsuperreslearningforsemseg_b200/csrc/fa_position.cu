@@ -17,7 +17,7 @@
 //                     Fpm (B, Npad, Kc) position-major  -> K-major operand tiles of the D contraction
 //                     Fcm (B, Kc, Npad) channel-major   -> K-major B tiles of the gradient contraction
 //   fa_pos_tiles    one CTA per (128-row tile i, channel group, sample): warp 0 = TMA producer, warp 1 = MMA issuer,
-//                   warps 2..5 = epilogue (|D| sum, sign tile, final normalisation Jacobian).  TMEM: columns
+//                   warps 2..9 = epilogue (|D| sum, sign tile, final normalisation Jacobian).  TMEM: columns
 //                   [0,256) gradient accumulator, [256,512) two D / sign tiles (double buffered).
 //   fa_pos_tiles_pair  the same for a cluster of two CTAs (two row tiles) with tcgen05 cta_group::2, M = 256: each CTA
 //                   supplies half of every B tile, which halves the B-operand shared-memory traffic (the hot variant)
@@ -290,7 +290,7 @@ struct PosArgs {
 #define TWAIT(acc, stmt) do { stmt; } while (0)
 #endif
 
-// Epilogue role, shared by the single-CTA and the CTA-pair tile kernels (warps 2..5 of a CTA): per column tile turn D into
+// Epilogue role, shared by the single-CTA and the CTA-pair tile kernels (warps 2..9 of a CTA): per column tile turn D into
 // |D| (loss partial) and sign(D) (in place, operand of the gradient MMAs); after the last tile finish the gradient
 // accumulator (normalisation Jacobian, or the raw partial rows when the column range is split); finally the loss.
 // kPair: the barrier the MMA issuer waits on lives in the leader CTA of the pair.
