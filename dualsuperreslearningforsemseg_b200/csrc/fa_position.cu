@@ -327,6 +327,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
     const int half = (warp - 2) >> 2;                          // which half of the columns / channel chunks this warp converts
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     double acc = 0.0;
+    float facc = 0.f;
     long long w_d = 0;
     const long long t_begin = clock64();
     for (int jj = 0; jj < nt; ++jj) {
@@ -387,8 +388,12 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         fence_before_sync();
         __syncwarp();                     // every lane's tcgen05.st has completed and is fenced: one arrival per warp
         if (lane == 0) { if (kPair) mbar_arrive_leader(&p_full[buf]); else mbar_arrive(&p_full[buf]); }
-        acc += (double)tsum * ((kGrad || diag) ? 1.0 : 2.0);
+        // tile sums are gathered in FP32 over eight tiles (<= 2 * 64 * 8 per thread: rounding ~1e-7 of the running sum) before
+        // they enter the FP64 total -- a DADD per tile was a quarter of the epilogue warps' stall samples (FP64 pipe)
+        facc += (kGrad || diag) ? tsum : 2.f * tsum;
+        if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
     }
+    acc += (double)facc;
 #ifdef DSRL_POS_TIMING
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
         long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
