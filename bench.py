@@ -891,7 +891,7 @@ def bench_ce_loss(args, rank, world, dev, peaks, steps=20, warmup=3, batch=6):
     ms_torch_cast, _, _ = timed(lambda a, tt: torch.nn.functional.cross_entropy(a, tt.long(), ignore_index=255), t)
     assert abs(loss - loss_t) <= 1e-5 * abs(loss_t) and float((grad - grad_t).norm() / grad_t.norm()) <= 1e-5, "CE != torch CE"
     ms = max_over_ranks(ms, world, dev)
-    bytes_alg = px * ((4 * C + 1 + 4) + (4 * C + 4 * C + 4 + 1))       # forward: logits + target + lse; backward: logits + dlogits + lse + target
+    bytes_alg = px * ((4 * C + 1 + 8) + (4 * C + 4 * C + 8 + 1))       # forward: logits + target + (m, log2 s); backward: logits + dlogits + (m, log2 s) + target
     achieved = bytes_alg / (ms * 1e-3) / 1e9
     return {"metric": "ce_fwd_bwd_gpx_per_s", "unit": "Gpx/s", "value": world * px / (ms * 1e-3) / 1e9, "ms_per_step": ms, "steps": steps,
             "dtype": "f32", "scaling": "weak",

@@ -4,10 +4,10 @@
 // backward kernels, about seven passes over the logits-sized tensor; here:
 //
 //   ce_forward   ONE pass over the logits: online log-sum-exp per pixel, picks x[target], sums the loss and the number of
-//                valid pixels (deterministic two-level reduction, last CTA by ticket), keeps lse per pixel (4 B/px)
-//   ce_backward  ONE pass: dlogits = (exp(x - lse) - [c == target]) * grad_out / valid   (0 at ignored pixels)
+//                valid pixels (deterministic two-level reduction, last CTA by ticket), keeps (max, log2 sum) per pixel (8 B/px)
+//   ce_backward  ONE pass: dlogits = (2^((x - max) log2 e - log2 sum) - [c == target]) * grad_out / valid   (0 at ignored pixels)
 //
-// Algorithmic bytes per pixel: forward 4C + sizeof(target) + 4 (lse), backward 4C + 4C + 4 + sizeof(target).
+// Algorithmic bytes per pixel: forward 4C + sizeof(target) + 8, backward 4C + 4C + 8 + sizeof(target).
 #include "common.cuh"
 
 namespace dsrl {
@@ -26,27 +26,49 @@ constexpr size_t kCePartialsOff = 64;
 inline size_t ce_blocks(int B, long long HW) { return (size_t)B * (size_t)((HW + kCeThreads - 1) / kCeThreads); }   // VEC = 1 worst case
 inline size_t ce_lse_off(int B, long long HW) { return (kCePartialsOff + ce_blocks(B, HW) * sizeof(CePartial) + 255) / 256 * 256; }
 
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+// 2^x on the SFU, no range fix-up code around it (inputs are <= 0 here; -inf -> 0)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <typename T> __device__ __forceinline__ long long ce_load_target(const T *t, long long i) { return (long long)t[i]; }
 
 // One thread = VEC consecutive pixels of one image; channel c of those pixels is one VEC*4-byte load, coalesced across the warp.
 template <typename TT, int VEC, int kCeChunk = 5>
 __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__restrict__ logits, const TT *__restrict__ target,
-                                                                int C, long long HW, long long ignore_index, int mean,
+                                                                int nimg, int C, long long HW, long long ignore_index, int mean,
                                                                 unsigned char *__restrict__ saved, size_t lse_off, unsigned *ticket,
                                                                 float *__restrict__ loss_out) {
     __shared__ double s_sum[33];
     __shared__ long long s_cnt[33];
     __shared__ int s_last;
-    const int b = blockIdx.y;
-    const long long p0 = ((long long)blockIdx.x * kCeThreads + threadIdx.x) * VEC;
+    // persistent CTAs: tile = (image, strip of kCeThreads * VEC pixels); one block-level reduction per CTA at the end
+    const long long strips = (HW + (long long)kCeThreads * VEC - 1) / ((long long)kCeThreads * VEC), tiles = strips * nimg;
     float lsum = 0.f;
     int lcnt = 0;
-    if (p0 < HW) {
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int b = (int)(tile / strips);
+        const long long p0 = ((tile - (long long)b * strips) * kCeThreads + threadIdx.x) * VEC;
+        if (p0 >= HW) continue;
         const float *x = logits + (size_t)b * C * HW + p0;
+        // running maximum m and s = sum of 2^((x - m) log2 e): a subtract, a multiply, one SFU op and an add per logit.  x - m is
+        // exact near the maximum (where the term matters), and x == m gives exactly 1, so a one-class problem has loss 0.
         float m[VEC], s[VEC], xt[VEC];
-        long long t[VEC];
+        int t[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { m[v] = -3.402823466e38f; s[v] = 0.f; xt[v] = 0.f; t[v] = (p0 + v < HW) ? ce_load_target(target, (long long)b * HW + p0 + v) : ignore_index; }
+        for (int v = 0; v < VEC; ++v) {
+            m[v] = -3.402823466e38f; s[v] = 0.f; xt[v] = 0.f;
+            const long long tl = (p0 + v < HW) ? ce_load_target(target, (long long)b * HW + p0 + v) : ignore_index;
+            t[v] = (tl != ignore_index && tl >= 0 && tl < C) ? (int)tl : -1;          // -1: ignored
+        }
         // kCeChunk channels per round: all their loads are issued before any arithmetic, then one branch-free online-softmax
         // update per pixel (chunk sizes 4..20 measured within 10 % of each other at the training shape; 5 was the fastest)
         for (int c0 = 0; c0 < C; c0 += kCeChunk) {
@@ -71,31 +93,36 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
 #pragma unroll
                 for (int u = 1; u < kCeChunk; ++u) cm = fmaxf(cm, xv[u][v]);
                 const float mn = fmaxf(m[v], cm);
-                float acc = s[v] * __expf(m[v] - mn);
+                float acc = s[v] * ex2_fast((m[v] - mn) * kLog2e);
 #pragma unroll
                 for (int u = 0; u < kCeChunk; ++u) {
-                    acc += __expf(xv[u][v] - mn);              // padding channels: exp(-FLT_MAX - mn) = 0
-                    if ((long long)(c0 + u) == t[v]) xt[v] = xv[u][v];
+                    acc += ex2_fast((xv[u][v] - mn) * kLog2e);         // padding channels: 2^-inf = 0
+                    if (c0 + u == t[v]) xt[v] = xv[u][v];
                 }
                 s[v] = acc;
                 m[v] = mn;
             }
         }
-        float lse[VEC];
+        // per pixel the pair (m, log2 s) is kept for the backward kernel rather than their sum: probabilities and the loss then
+        // carry ~1e-7 relative error at any logit magnitude
+        float l2s[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            lse[v] = m[v] + __logf(s[v]);
-            const bool valid = t[v] != ignore_index && t[v] >= 0 && t[v] < C;
-            if (valid) { lsum += lse[v] - xt[v]; ++lcnt; }
+            l2s[v] = lg2_fast(s[v]);
+            if (t[v] >= 0) { lsum += l2s[v] * kLn2 + (m[v] - xt[v]); ++lcnt; }
         }
-        float *lp = reinterpret_cast<float *>(saved + lse_off) + (size_t)b * HW + p0;
-        if (VEC == 4) *reinterpret_cast<float4 *>(lp) = make_float4(lse[0], lse[1 % VEC], lse[2 % VEC], lse[3 % VEC]);
-        else lp[0] = lse[0];
+        float2 *lp = reinterpret_cast<float2 *>(saved + lse_off) + (size_t)b * HW + p0;
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(lp) = make_float4(m[0], l2s[0], m[1 % VEC], l2s[1 % VEC]);
+            *reinterpret_cast<float4 *>(lp + 2) = make_float4(m[2 % VEC], l2s[2 % VEC], m[3 % VEC], l2s[3 % VEC]);
+        } else {
+            lp[0] = make_float2(m[0], l2s[0]);
+        }
     }
     const double bsum = block_sum<double>((double)lsum, s_sum);
     const long long bcnt = block_sum<long long>((long long)lcnt, s_cnt);
     CePartial *parts = reinterpret_cast<CePartial *>(saved + kCePartialsOff);
-    const unsigned nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned nblk = gridDim.x, blk = blockIdx.x;
     if (threadIdx.x == 0) {
         parts[blk].sum = bsum;
         parts[blk].valid = bcnt;
@@ -130,19 +157,22 @@ __global__ void __launch_bounds__(kCeThreads) ce_backward_kernel(const float *__
     const float scale = mean ? (float)((double)__ldg(grad_out) / (double)h->valid) : __ldg(grad_out);
     const float *x = logits + (size_t)b * C * HW + p0;
     float *g = dlogits + (size_t)b * C * HW + p0;
-    const float *lp = reinterpret_cast<const float *>(saved + lse_off) + (size_t)b * HW + p0;
-    float lse[VEC], sc[VEC];
-    long long t[VEC];
+    const float2 *lp = reinterpret_cast<const float2 *>(saved + lse_off) + (size_t)b * HW + p0;
+    float m2[VEC], l2s[VEC], sc[VEC];                        // (m, log2 s) as the forward kernel left them
+    int t[VEC];
     if (VEC == 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(lp));
-        lse[0] = q.x; lse[1 % VEC] = q.y; lse[2 % VEC] = q.z; lse[3 % VEC] = q.w;
+        const float4 q0 = __ldg(reinterpret_cast<const float4 *>(lp)), q1 = __ldg(reinterpret_cast<const float4 *>(lp + 2));
+        m2[0] = q0.x; l2s[0] = q0.y; m2[1 % VEC] = q0.z; l2s[1 % VEC] = q0.w;
+        m2[2 % VEC] = q1.x; l2s[2 % VEC] = q1.y; m2[3 % VEC] = q1.z; l2s[3 % VEC] = q1.w;
     } else {
-        lse[0] = __ldg(lp);
+        const float2 q = __ldg(lp);
+        m2[0] = q.x; l2s[0] = q.y;
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        t[v] = (p0 + v < HW) ? ce_load_target(target, (long long)b * HW + p0 + v) : ignore_index;
-        const bool valid = t[v] != ignore_index && t[v] >= 0 && t[v] < C;
+        const long long tl = (p0 + v < HW) ? ce_load_target(target, (long long)b * HW + p0 + v) : ignore_index;
+        const bool valid = tl != ignore_index && tl >= 0 && tl < C;
+        t[v] = valid ? (int)tl : -1;
         sc[v] = valid ? scale : 0.f;
     }
     // 4 channels per round: a read + write stream wants resident threads more than registers (8 per round measured slower)
@@ -166,7 +196,7 @@ __global__ void __launch_bounds__(kCeThreads) ce_backward_kernel(const float *__
                 float o[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    o[v] = sc[v] != 0.f ? (__expf(xv[u][v] - lse[v]) - ((long long)(c0 + u) == t[v] ? 1.f : 0.f)) * sc[v] : 0.f;
+                    o[v] = t[v] >= 0 ? (ex2_fast((xv[u][v] - m2[v]) * kLog2e - l2s[v]) - (c0 + u == t[v] ? 1.f : 0.f)) * sc[v] : 0.f;
                 if (VEC == 4) __stcs(reinterpret_cast<float4 *>(g + (size_t)(c0 + u) * HW), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
                 else g[(size_t)(c0 + u) * HW] = o[0];
             }
@@ -189,7 +219,7 @@ using namespace dsrl;
 
 extern "C" size_t dsrl_ce_saved_bytes(int B, int64_t HW) {
     if (B < 0 || HW < 0) return 0;
-    return ce_lse_off(B, HW) + (size_t)B * (size_t)HW * 4 + 16;
+    return ce_lse_off(B, HW) + (size_t)B * (size_t)HW * 8 + 16;      // (m, log2 s) per pixel
 }
 
 #define CE_DISPATCH(KERNEL, ...)                                                                                     \
@@ -228,7 +258,11 @@ extern "C" int dsrl_ce_forward(const float *logits, const void *target, int targ
     if (!ticket) return DSRL_ERR_CUDA;
     const size_t lse_off = ce_lse_off(B, HW);
     unsigned char *sv = static_cast<unsigned char *>(saved);
-    CE_DISPATCH(ce_forward_kernel, C, (long long)HW, (long long)ignore_index, reduction == DSRL_REDUCE_MEAN, sv, lse_off, ticket, loss_out);
+    {
+        const long long tiles = (long long)grid.x * B, cap = (long long)device_sm_count() * 8;
+        const dim3 grid((unsigned)(tiles < cap ? tiles : cap));          // shadows the (strips, B) grid the backward kernel uses
+        CE_DISPATCH(ce_forward_kernel, B, C, (long long)HW, (long long)ignore_index, reduction == DSRL_REDUCE_MEAN, sv, lse_off, ticket, loss_out);
+    }
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
 }
