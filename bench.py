@@ -696,7 +696,7 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     p1, p2 = x1.cpu().pin_memory(), x2.cpu().pin_memory()
     del plan
     torch.cuda.empty_cache()
-    chunk = 2 if b_local >= 2 else 1
+    chunk = 2 if b_local >= 4 else 1
     pipe = FAHostPipeline((b_local, C, H, W), subsample_factor=STRESS_K, affinity="position", precision=precision, chunk=chunk, device=dev)
 
     def e2e_pipe():
@@ -728,7 +728,7 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     mod_ms = time_e2e(e2e_module)
     res["e2e"] = {"value": pairs_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
                   "h2d_bytes_per_step": int(p1.numel() * 4 + p2.numel() * 4), "d2h_bytes_per_step": 4,
-                  "note": f"functional.FAHostPipeline(chunk={chunk}) forward + backward from pinned host memory each step: H2D of chunk i+1 on a copy "
+                  "note": f"functional.FAHostPipeline(chunk={chunk}, ramp: first two chunks single samples) forward + backward from pinned host memory each step: H2D of chunk i+1 on a copy "
                           "stream overlaps the kernels of chunk i; loss read back with .item()",
                   "via_faloss_module": {"value": pairs_total / (mod_ms * 1e-3) / 1e9, "ms_per_step": mod_ms,
                                          "note": "FALoss(affinity='position') + backward() on tensors copied from pinned host memory first (no overlap)"}}

@@ -81,12 +81,12 @@ class FAHostPipeline:
 
     Samples are independent units of the loss, so the batch is cut into chunks of ``chunk`` samples: chunk
     i+1 travels host -> device on a copy stream while the kernels work on chunk i on the caller's stream (two streams,
-    one event per chunk, no host synchronisation).  ``__call__(x1_host, x2_host, grad_out=1.0)`` returns
+    one event per chunk, no host synchronisation; with ``ramp`` the first two chunks are single samples).  ``__call__(x1_host, x2_host, grad_out=1.0)`` returns
     ``(loss, dx1, dx2)`` as device tensors owned by the pipeline: the batch loss ('mean' or 'sum') and the gradients
     w.r.t. both inputs -- the same values ``FALoss`` + ``backward()`` give on the whole batch."""
 
     def __init__(self, shape1, shape2=None, subsample_factor=8, reduction="mean", affinity="reference", precision=None,
-                 chunk=2, device=None):
+                 chunk=2, ramp=True, device=None):
         if reduction not in ("mean", "sum"):
             raise ValueError("FAHostPipeline: reduction must be 'mean' or 'sum'")
         shape2 = tuple(shape2 or shape1)
@@ -95,7 +95,14 @@ class FAHostPipeline:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
         chunk = max(1, min(int(chunk), self.B))
-        self.bounds = [(i, min(i + chunk, self.B)) for i in range(0, self.B, chunk)]
+        # ramp: the first two chunks are single samples, so the kernels start after one sample's copy instead of `chunk`
+        sizes, left = [], self.B
+        while left > 0:
+            n = 1 if (ramp and len(sizes) < 2) else chunk
+            sizes.append(min(n, left))
+            left -= sizes[-1]
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        self.bounds = [(lo, lo + n) for lo, n in zip(starts, sizes)]
         self.plans = {}
         for lo, hi in self.bounds:                          # one plan per distinct chunk size (the last chunk may be shorter)
             n = hi - lo
