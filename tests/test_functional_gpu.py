@@ -96,3 +96,20 @@ def test_fused_position_call_writes_dx_directly(jsplit, prec, monkeypatch):
     loss, d1, d2 = plan.forward_backward(x1, x2, go)
     torch.cuda.synchronize()
     assert float(loss) == float(ref_loss) and torch.equal(d1, ref_d1) and torch.equal(d2, ref_d2)
+
+
+def test_host_pipeline_graph_replay():
+    """FAHostPipeline.capture(): copies, kernel and loss read-back as one CUDA graph; new inputs are written into the captured
+    pinned buffers between replays."""
+    from dualsuperreslearningforsemseg_b200.functional import FAHostPipeline
+    dev = torch.device("cuda", 0)
+    x1, x2 = fa_inputs((6, 1, 64, 128), "relu", 54321)
+    h1, h2 = torch.from_numpy(x1).pin_memory(), torch.from_numpy(x2).pin_memory()
+    pipe = FAHostPipeline(tuple(h1.shape), subsample_factor=8, chunk=6, ramp=False, device=dev).capture(h1, h2, 0.5)
+    for seed in (54321, 7):
+        y1, y2 = fa_inputs((6, 1, 64, 128), "relu", seed)
+        h1.copy_(torch.from_numpy(y1)); h2.copy_(torch.from_numpy(y2))
+        loss = float(pipe.replay())
+        ref_loss, ref_d1, ref_d2 = _autograd(torch.from_numpy(y1).to(dev), torch.from_numpy(y2).to(dev), 8, 0.5)
+        assert abs(loss - float(ref_loss)) <= 1e-6 * abs(float(ref_loss))
+        assert float((pipe.dx1 - ref_d1).norm() / ref_d1.norm()) <= 1e-6 and float((pipe.dx2 - ref_d2).norm() / ref_d2.norm()) <= 1e-6
