@@ -71,17 +71,20 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
         }
         // kCeChunk channels per round: all their loads are issued before any arithmetic, then one branch-free online-softmax
         // update per pixel (chunk sizes 4..20 measured within 10 % of each other at the training shape; 5 was the fastest)
+        const float *xp = x;                                // walks the channel planes: one 64-bit add per load, no index arithmetic
         for (int c0 = 0; c0 < C; c0 += kCeChunk) {
             float xv[kCeChunk][VEC];
+            const bool whole = c0 + kCeChunk <= C;          // all but the last chunk: no per-channel guard
 #pragma unroll
             for (int u = 0; u < kCeChunk; ++u) {
-                if (c0 + u < C) {
+                if (whole || c0 + u < C) {
                     if (VEC == 4) {
-                        const uint4 q = ldg_stream_u4(x + (size_t)(c0 + u) * HW);
+                        const uint4 q = ldg_stream_u4(xp);
                         xv[u][0] = __uint_as_float(q.x); xv[u][1 % VEC] = __uint_as_float(q.y); xv[u][2 % VEC] = __uint_as_float(q.z); xv[u][3 % VEC] = __uint_as_float(q.w);
                     } else {
-                        xv[u][0] = ldg_stream_f32(x + (size_t)(c0 + u) * HW);
+                        xv[u][0] = ldg_stream_f32(xp);
                     }
+                    xp += HW;
                 } else {
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) xv[u][v] = -3.402823466e38f;
@@ -177,28 +180,33 @@ __global__ void __launch_bounds__(kCeThreads) ce_backward_kernel(const float *__
     }
     // 4 channels per round: a read + write stream wants resident threads more than registers (8 per round measured slower)
     constexpr int kCh = 4;
+    const float *xp = x;                                    // walk the channel planes: one 64-bit add per access
+    float *gp = g;
     for (int c0 = 0; c0 < C; c0 += kCh) {
         float xv[kCh][VEC];
+        const bool whole = c0 + kCh <= C;
 #pragma unroll
         for (int u = 0; u < kCh; ++u) {
-            if (c0 + u < C) {
+            if (whole || c0 + u < C) {
                 if (VEC == 4) {
-                    const uint4 q = ldg_stream_u4(x + (size_t)(c0 + u) * HW);
+                    const uint4 q = ldg_stream_u4(xp);
                     xv[u][0] = __uint_as_float(q.x); xv[u][1 % VEC] = __uint_as_float(q.y); xv[u][2 % VEC] = __uint_as_float(q.z); xv[u][3 % VEC] = __uint_as_float(q.w);
                 } else {
-                    xv[u][0] = ldg_stream_f32(x + (size_t)(c0 + u) * HW);
+                    xv[u][0] = ldg_stream_f32(xp);
                 }
+                xp += HW;
             }
         }
 #pragma unroll
         for (int u = 0; u < kCh; ++u) {
-            if (c0 + u < C) {
+            if (whole || c0 + u < C) {
                 float o[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
                     o[v] = t[v] >= 0 ? (ex2_fast((xv[u][v] - m2[v]) * kLog2e - l2s[v]) - (c0 + u == t[v] ? 1.f : 0.f)) * sc[v] : 0.f;
-                if (VEC == 4) __stcs(reinterpret_cast<float4 *>(g + (size_t)(c0 + u) * HW), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
-                else g[(size_t)(c0 + u) * HW] = o[0];
+                if (VEC == 4) __stcs(reinterpret_cast<float4 *>(gp), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
+                else gp[0] = o[0];
+                gp += HW;
             }
         }
     }
