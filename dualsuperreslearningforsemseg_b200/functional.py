@@ -76,6 +76,19 @@ class FAPlan:
         return loss, dx1, dx2
 
 
+def chunk_bounds(batch, chunk, ramp=True):
+    """[lo, hi) sample ranges of the host pipeline's chunks.  With ``ramp`` the first two chunks are single samples, so the
+    kernels start after one sample's copy instead of ``chunk``; the last chunk may be shorter."""
+    chunk = max(1, min(int(chunk), int(batch)))
+    sizes, left = [], int(batch)
+    while left > 0:
+        n = 1 if (ramp and len(sizes) < 2) else chunk
+        sizes.append(min(n, left))
+        left -= sizes[-1]
+    starts = [sum(sizes[:i]) for i in range(len(sizes))]
+    return [(lo, lo + n) for lo, n in zip(starts, sizes)]
+
+
 class FAHostPipeline:
     """FA loss forward+backward for feature maps that live in pinned HOST memory.
 
@@ -94,15 +107,7 @@ class FAHostPipeline:
         self.reduction = reduction
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        chunk = max(1, min(int(chunk), self.B))
-        # ramp: the first two chunks are single samples, so the kernels start after one sample's copy instead of `chunk`
-        sizes, left = [], self.B
-        while left > 0:
-            n = 1 if (ramp and len(sizes) < 2) else chunk
-            sizes.append(min(n, left))
-            left -= sizes[-1]
-        starts = [sum(sizes[:i]) for i in range(len(sizes))]
-        self.bounds = [(lo, lo + n) for lo, n in zip(starts, sizes)]
+        self.bounds = chunk_bounds(self.B, chunk, ramp)
         self.plans = {}
         for lo, hi in self.bounds:                          # one plan per distinct chunk size (the last chunk may be shorter)
             n = hi - lo

@@ -101,3 +101,17 @@ def test_dataset_level_miou_accessor():
     assert pooled == tot_i.sum() / tot_u.sum() * 100.0
     assert per_class == np.nanmean(tot_i / tot_u) * 100.0
     assert len(m.ious) == 3                                   # the per-update list (the reference's definition) is untouched
+
+
+def test_host_pipeline_chunk_schedule():
+    """functional.chunk_bounds: contiguous cover of the batch, ramped start, ragged tail."""
+    from dualsuperreslearningforsemseg_b200.functional import chunk_bounds
+    assert chunk_bounds(8, 2) == [(0, 1), (1, 2), (2, 4), (4, 6), (6, 8)]
+    assert chunk_bounds(8, 3, ramp=False) == [(0, 3), (3, 6), (6, 8)]
+    assert chunk_bounds(1, 4) == [(0, 1)] and chunk_bounds(2, 1) == [(0, 1), (1, 2)]
+    for B in range(1, 12):
+        for c in (1, 2, 3, 5, 64):
+            for ramp in (True, False):
+                b = chunk_bounds(B, c, ramp)
+                assert b[0][0] == 0 and b[-1][1] == B and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+                assert all(0 < hi - lo <= max(1, min(c, B)) for lo, hi in b)
