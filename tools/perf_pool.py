@@ -6,7 +6,7 @@ from torch.profiler import profile, ProfilerActivity
 B, C, H, W, k = 2, 64, 1024, 2048, 8
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 x1 = torch.relu(torch.randn((B, C, H, W), device='cuda', generator=g)); x2 = torch.relu(torch.randn((B, C, H, W), device='cuda', generator=g))
-plan = FAPlan((B, C, H, W), subsample_factor=k, affinity='position')
+plan = FAPlan((B, C, H, W), subsample_factor=k, affinity='position', precision=(sys.argv[1] if len(sys.argv) > 1 else None))
 go = torch.ones((), device='cuda')
 for _ in range(2): plan.forward_backward(x1, x2, go)
 torch.cuda.synchronize()
