@@ -1094,7 +1094,7 @@ __global__ void __launch_bounds__(256) fa_pos_unpool(PosGeom g, const float *__r
                 o = make_float4(p0 < w ? __ldg(src + p0) * scale : 0.f, p1 < w ? __ldg(src + p1) * scale : 0.f,
                                 p2 < w ? __ldg(src + p2) * scale : 0.f, p3 < w ? __ldg(src + p3) * scale : 0.f);
             }
-            reinterpret_cast<float4 *>(dst)[xv] = o;
+            __stcs(reinterpret_cast<float4 *>(dst) + xv, o);         // written once, read by nobody here: streaming store
         } else {
             const int px = xv / k;
             dst[xv] = px < w ? __ldg(src + px) * scale : 0.f;
