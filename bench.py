@@ -272,14 +272,19 @@ def bench_fa_train(args, rank, world, dev, peaks):
     e2e_ms = time_e2e(e2e_graph_step)
 
     # what a user runs today on the same GPU: the reference algorithm in eager PyTorch (BASELINE.md plan item 3)
-    from oracle import fa_torch_port
+    eager = _TorchFALoss()
+
+    def eager_step():
+        u, v = a_c.detach().clone().requires_grad_(True), b_c.detach().clone().requires_grad_(True)
+        eager(u, v).backward()
+
     for _ in range(3):
-        fa_torch_port.fwd_bwd(a_c, b_c, FA_K)
+        eager_step()
     torch.cuda.synchronize()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(20):
-        fa_torch_port.fwd_bwd(a_c, b_c, FA_K)
+        eager_step()
     g1.record()
     torch.cuda.synchronize()
     eager_ms = g0.elapsed_time(g1) / 20
@@ -784,11 +789,19 @@ def cpu_fa_stress(budget_s=15.0, threads=None, C=None, rows=256):
 # workload: train_step (BASELINE configs[4]) -- the caller of the hot path, harness/ (plain PyTorch + torch DDP)
 # ----------------------------------------------------------------------------------------------------------------
 class _TorchFALoss(torch.nn.Module):
-    """What a user runs without this library: the reference FALoss restated in eager PyTorch, on the GPU."""
+    """What a user runs without this library: the algorithm of the reference FALoss (FALoss.py:8-34) in eager PyTorch on the
+    GPU -- the comparison arm of the GPU legs.  Written out here: nothing under oracle/ runs on the GPU legs except as a checker."""
+
+    @staticmethod
+    def _similarity(x, k):
+        p = torch.nn.functional.avg_pool2d(x, kernel_size=k)
+        p = p / torch.linalg.matrix_norm(p, ord=2, keepdim=True)
+        return torch.matmul(p.transpose(2, 3), p)
 
     def forward(self, a, b):
-        from oracle import fa_torch_port
-        return fa_torch_port.fa_loss(a, b, FA_K, "mean")
+        s1, s2 = self._similarity(a, FA_K).flatten(2), self._similarity(b, FA_K).flatten(2)
+        n = s1.shape[2]
+        return torch.nn.functional.l1_loss(s1.repeat_interleave(n, dim=2), s2.repeat(1, 1, n), reduction="mean")
 
 
 def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6):
