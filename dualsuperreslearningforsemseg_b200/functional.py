@@ -62,7 +62,8 @@ class FAPlan:
         """x1, x2: contiguous fp32 CUDA tensors of the planned shapes; grad_out: fp32 CUDA tensor (1 element for
         mean/sum).  Returns (loss, dx1, dx2) -- the plan's own buffers, overwritten by the next call, or the tensors
         given as ``out=(loss, dx1, dx2)`` (mean/sum only).  For mean/sum this is ``dsrl_fa_forward_backward`` (one
-        kernel launch at the reference model's training shapes)."""
+        kernel launch at the reference model's training shapes; position mode without pooling writes dX from the gradient
+        kernel, so the plan's `saved` blob is scratch afterwards: do not follow this call with `backward()`)."""
         if self.red == _lib.REDUCE_NONE:
             self.forward(x1, x2, True)
             self.backward(x1, x2, grad_out)
