@@ -65,6 +65,23 @@ def test_argument_validation_happens_before_device_probe(lib):
     assert lib.dsrl_fa_forward(7, 0, p, p, 1, 1, 1, 8, 8, 8, 1, 1, p, p, 64, p, 64, None) == _lib.ERR_BAD_ARG
 
 
+def test_cross_entropy_entry_points_validate_and_fail_loudly(lib):
+    from dualsuperreslearningforsemseg_b200 import _lib
+    buf = (ctypes.c_char * 65536)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    need = lib.dsrl_ce_saved_bytes(2, 64)
+    assert need >= 2 * 64 * 8 and lib.dsrl_ce_saved_bytes(-1, 64) == 0
+    # argument validation happens before the device probe
+    assert lib.dsrl_ce_forward(None, p, _lib.U8, 2, 19, 64, 255, _lib.REDUCE_MEAN, p, p, need, None) == _lib.ERR_BAD_ARG
+    assert lib.dsrl_ce_forward(p, p, _lib.U8, 2, 19, 64, 255, _lib.REDUCE_NONE, p, p, need, None) == _lib.ERR_UNSUPPORTED
+    assert lib.dsrl_ce_forward(p, p, _lib.U8, 2, 0, 64, 255, _lib.REDUCE_MEAN, p, p, need, None) == _lib.ERR_BAD_SHAPE
+    assert lib.dsrl_ce_forward(p, p, _lib.U8, 2, 19, 64, 255, _lib.REDUCE_MEAN, p, p, need - 1, None) == _lib.ERR_BAD_ARG
+    assert lib.dsrl_ce_backward(p, p, _lib.U8, 2, 19, 64, 255, _lib.REDUCE_SUM, p, need, None, p, None) == _lib.ERR_BAD_ARG
+    if not torch.cuda.is_available():
+        assert lib.dsrl_ce_forward(p, p, _lib.U8, 2, 19, 64, 255, _lib.REDUCE_MEAN, p, p, need, None) == _lib.ERR_CUDA
+        assert b"no CPU fallback" in lib.dsrl_last_error()
+
+
 def test_missing_library_fails_loudly(tmp_path):
     """No silent fallback: with the shared library absent the first use raises and says how to build it."""
     import subprocess
