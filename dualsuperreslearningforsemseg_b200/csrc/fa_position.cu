@@ -13,7 +13,7 @@
 // (A-from-TMEM), like P = softmax(S) in an attention kernel.
 //
 // Kernels:
-//   fa_pos_pack     pool + per-position L2 normalise, TF32 rounding, two layouts:
+//   fa_pos_pack     pool + per-position L2 normalise, TF32 rounding (or FP16 copies only, precision 'f16'), two layouts:
 //                     Fpm (B, Npad, Kc) position-major  -> K-major operand tiles of the D contraction
 //                     Fcm (B, Kc, Npad) channel-major   -> K-major B tiles of the gradient contraction
 //   fa_pos_tiles    one CTA per (128-row tile i, channel group, sample): warp 0 = TMA producer, warp 1 = MMA issuer,
@@ -24,7 +24,8 @@
 //                   With kHalf the operands are FP16 (kind::f16, same 11-bit significand as TF32 on unit-norm features):
 //                   twice the tensor rate, half the operand bytes, own rows always resident (precision 'f16')
 //   fa_pos_jacobian sums the partial accumulators when the column range of a row tile is split over several CTAs
-//   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)
+//   fa_pos_unpool   backward proper: dX = grad_out / k^2 * unpool(dP)   (not launched by the fused forward + backward call
+//                   without pooling: there the gradient kernel / fa_pos_jacobian write dX themselves)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
