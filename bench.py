@@ -690,6 +690,8 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
                                f"{H}x{W} positions (N={N}), batch {STRESS_B} sharded over {world} GPU(s), C={C} per branch, subsample_factor={STRESS_K}",
                    "shape_per_gpu": [b_local, C, H, W], "pairs_total": pairs_total,
                    "precision": PRECISION_TEXT[precision][1],
+                   "parity_gate": "tests/test_fa_position_gpu.py: loss <= 1e-4 relative, gradient <= 1e-3 relative-norm against the float64 oracle "
+                                  "(same tests and tolerances for f16, tf32 and 3xtf32)",
                    "l2": "working set per step (1.6 GB per sample) larger than L2, no flush",
                    "parallelism": f"dp{world} (batch shard, no data-path collective; scalar loss all-reduced for reporting only)",
                    "loss_rank0": loss_local},
