@@ -859,6 +859,8 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
     if (warp == 0) {
         // ===================================== TMA producer (both CTAs, each for its own shared memory) =====================================
+        long long w_empty = 0;
+        const long long t_begin = clock64();
         if (kResident) {
             if (elect_one()) {
                 if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nq * kBoxBytes);
@@ -869,7 +871,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
 #define STAGE_FILL(bytes_per_cta, ...)                                                                   \
         do {                                                                                             \
-            mbar_wait(&empty[slot], ph ^ 1, 11);                                                         \
+            TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 11));                                         \
             if (elect_one()) {                                                                           \
                 unsigned char *dst = ring + (size_t)slot * kStageBytes;                                  \
                 uint64_t *bar = &full[slot];                                                             \
@@ -912,9 +914,19 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             load_v(j0 + jj);
         }
 #undef STAGE_FILL
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
+            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            tm[0] = clock64() - t_begin; tm[1] = w_empty;
+        }
+#else
+        (void)t_begin; (void)w_empty;
+#endif
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================================
         if (leader) {
+            long long w_full = 0, w_p = 0;
+            const long long t_begin = clock64();
             constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
             const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
             const uint32_t id_pos = kHalf ? idesc_f16(2 * kTile, kTile, false) : idesc_tf32(2 * kTile, kTile, false);
@@ -934,7 +946,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 const int buf = jj & 1;
                 const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
                 for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
-                    mbar_wait(&full[slot], ph, 12);
+                    TWAIT(w_full, mbar_wait(&full[slot], ph, 12));
                     const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
                     const int ss = slot;
                     RING_ADVANCE();
@@ -965,9 +977,9 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             auto gemm_g = [&](int jj, bool last) {
                 const int buf = jj & 1;
                 const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile;
-                mbar_wait(&p_full[buf], (jj >> 1) & 1, 15);
+                TWAIT(w_p, mbar_wait(&p_full[buf], (jj >> 1) & 1, 15));
                 for (int jc0 = 0; jc0 < kVB; jc0 += 2) {
-                    mbar_wait(&full[slot], ph, 13);
+                    TWAIT(w_full, mbar_wait(&full[slot], ph, 13));
                     const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
                     const int ss = slot;
                     RING_ADVANCE();
@@ -994,6 +1006,14 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 gemm_g(jj, jj == nt - 1);
             }
 #undef MMA4_SS
+#ifdef DSRL_POS_TIMING
+            if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
+                long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+                tm[2] = clock64() - t_begin; tm[3] = w_full; tm[4] = w_p; tm[5] = 0;
+            }
+#else
+            (void)t_begin; (void)w_full; (void)w_p;
+#endif
         }
     } else {
         EpiCtx c;
