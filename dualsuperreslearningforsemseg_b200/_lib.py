@@ -16,12 +16,14 @@ OK, ERR_BAD_SHAPE, ERR_BAD_DTYPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_BAD_ARG = 0, -1
 FA_REFERENCE, FA_POSITION = 0, 1
 REDUCE_NONE, REDUCE_MEAN, REDUCE_SUM = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_BF16, PREC_F16 = 0, 1, 2, 3
+PREC_EXACT_SIGNS = 16      # flag OR-ed onto a position-mode precision
 U8, I32, I64 = 0, 1, 2
 
 # every symbol include/dsrl_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
     "dsrl_version", "dsrl_last_error", "dsrl_launch_count",
     "dsrl_fa_saved_bytes", "dsrl_fa_workspace_bytes", "dsrl_fa_forward", "dsrl_fa_backward", "dsrl_fa_forward_backward",
+    "dsrl_fa_sign_stats", "dsrl_scale_grads",
     "dsrl_seg_counts", "dsrl_seg_counts_from_logits",
     "dsrl_ce_saved_bytes", "dsrl_ce_forward", "dsrl_ce_backward",
 )
@@ -47,9 +49,13 @@ def _declare(lib):
     lib.dsrl_launch_count.restype = c.c_uint64
     lib.dsrl_launch_count.argtypes = []
     lib.dsrl_fa_saved_bytes.restype = sz
-    lib.dsrl_fa_saved_bytes.argtypes = [i] * 7
+    lib.dsrl_fa_saved_bytes.argtypes = [i] * 8
     lib.dsrl_fa_workspace_bytes.restype = sz
-    lib.dsrl_fa_workspace_bytes.argtypes = [i] * 7
+    lib.dsrl_fa_workspace_bytes.argtypes = [i] * 8
+    lib.dsrl_fa_sign_stats.restype = i
+    lib.dsrl_fa_sign_stats.argtypes = [vp, c.POINTER(c.c_uint64), vp]
+    lib.dsrl_scale_grads.restype = i
+    lib.dsrl_scale_grads.argtypes = [vp, vp, i64, vp, i64, vp]
     lib.dsrl_fa_forward.restype = i
     lib.dsrl_fa_forward.argtypes = [i, i, vp, vp, i, i, i, i, i, i, i, i, vp, vp, sz, vp, sz, vp]
     lib.dsrl_fa_backward.restype = i

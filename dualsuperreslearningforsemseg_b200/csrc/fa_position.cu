@@ -54,6 +54,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 256;     // first column of the two D / sign tiles
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kSmemAux = 1536;   // barriers, TMEM pointer, reduction scratch, projection halves
+constexpr int kXchgBytes = 2 * 2 * 128 * 16;   // fa_pos_tiles_quad: two slots x (two column halves x 128 rows x 16 bytes of sign / zero bits)
 
 struct PosGeom {
     int B, C1, C2, H, W, k, h, w, N, Npad, C1p, C2p, Kc, G;
@@ -63,17 +64,22 @@ struct PosGeom {
     int q_resident, stages;
     int jsplit;             // gradient variant: the column tiles of one row tile are spread over jsplit CTAs (small grids)
     int pair, pair_stages;  // CTA-pair form of the gradient variant usable for this geometry; its ring depth
+    int quad, quad_stages;  // FP16 form, two channel groups: cluster of two CTA pairs that split the D tiles between them (fa_pos_tiles_quad)
+    size_t quad_smem_bytes;
     int half, nkh, half_stages;   // FP16 operands (kind::f16) requested; Kc / 64 chunks; ring depth of the pair form
     int half_pair, half1_stages;  // pair form usable for this geometry; ring depth of the single-CTA form
+    int exact, fnsub, fsub, fcap; // exact signs: near-tie entries of D are listed per row -- 2 * jsplit private sub-lists (one per
+                                  // epilogue thread that converts part of the row) of fsub entries, fcap in all -- and re-decided in FP64
+    int raw_o;                    // the tile kernel stores raw accumulator rows, fa_pos_finish completes them (jsplit > 1 or exact)
     size_t smem_bytes, pair_smem_bytes, half_smem_bytes, half1_smem_bytes;
 };
 
-struct PosWs { size_t Fpm, Fcm, FpmH, FcmH, nrm, partials, opart, total; };
+struct PosWs { size_t Fpm, Fcm, FpmH, FcmH, nrm, partials, opart, Ppm, inv64, tau, fcnt, fent, total; };
 struct PosSaved { size_t dP, total; };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, PosGeom &g, int half = 0) {
+inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, PosGeom &g, int half = 0, int exact = 0) {
     if (B < 1 || C1 < 1 || C2 < 1 || H < 1 || W < 1 || k < 1) return false;
     g.B = B; g.C1 = C1; g.C2 = C2; g.H = H; g.W = W; g.k = k;
     g.h = H / k; g.w = W / k;
@@ -142,26 +148,59 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         const int s = atoi(force);
         if ((s == 1 || s == 2 || s == 4) && g.tiles % s == 0) g.jsplit = s;
     }
+    // FP16 form with two equal channel groups: a cluster of two CTA pairs on the same two row tiles, each pair computing the D
+    // tiles of every other column tile and shipping their signs to the other pair (fa_pos_tiles_quad): needs an even number of
+    // column tiles per column share
+    {
+        const size_t qbytes = (size_t)g.nkh * kBoxBytes;
+        const long long room = (long long)kSmemBudget - 1024 - (long long)kSmemAux - (long long)qbytes - kXchgBytes;
+        g.quad_stages = room > 0 ? (int)(room / kBoxBytes) : 0;
+        if (g.quad_stages > 8) g.quad_stages = 8;
+        g.quad_smem_bytes = 1024 + qbytes + (size_t)g.quad_stages * kBoxBytes + kXchgBytes + kSmemAux;
+        g.quad = g.half_pair && g.G == 2 && g.gcnt[0] == g.gcnt[1] && (g.tiles / g.jsplit) % 2 == 0 && g.quad_stages >= 3;
+        if (const char *e = getenv("DSRL_POS_QUAD")) { if (atoi(e) == 0) g.quad = 0; }
+    }
+    // exact signs: about 1e-3 of a row's entries are near ties (|D| below ~3.5 sigma of the operand-rounding error, whatever
+    // C is: threshold and spread of D both scale like 1/sqrt(C)); the per-row list holds 4x that, at least 32 entries
+    g.exact = exact ? 1 : 0;
+    {
+        // sub-lists per row: column half x column share (x 2 when the two channel groups split the column tiles between them);
+        // expected N * 1.1e-3 / nsub entries each, room for 4x that + 16
+        const int nsub = g.fnsub = 2 * g.jsplit * (g.quad ? 2 : 1);
+        g.fsub = (int)align_up((size_t)(N / (200 * nsub)) + 16, 8);
+        if (g.fsub > 2048) g.fsub = 2048;
+        g.fcap = g.fsub * nsub;
+    }
+    g.raw_o = g.jsplit > 1 || g.exact;
     return true;
 }
 
+// Only the operand copies the chosen precision reads are reserved: fp32 (TF32-rounded) layouts for the tf32 kinds, FP16
+// layouts for kind::f16 (at BASELINE configs[3] that is 0.54 GB instead of the 2.2 GB a precision-blind maximum needs).
 inline PosWs make_ws(const PosGeom &g) {
     PosWs w;
     size_t off = 0;
-    w.Fpm = off;      off = align_up(off + (size_t)(1 + g.split) * g.B * g.Npad * g.Kc * 4, 1024);   // hi rows, then lo rows
-    w.Fcm = off;      off = align_up(off + ((size_t)g.B * g.Kc + kTile) * g.Npad * 4, 1024);   // + one box of slack rows
+    w.Fpm = off;      off = align_up(off + (g.half ? 0 : (size_t)(1 + g.split) * g.B * g.Npad * g.Kc * 4), 1024);   // hi rows, then lo rows
+    w.Fcm = off;      off = align_up(off + (g.half ? 0 : ((size_t)g.B * g.Kc + kTile) * g.Npad * 4), 1024);   // + one box of slack rows
     w.FpmH = off;     off = align_up(off + (g.half ? (size_t)g.B * g.Npad * g.Kc * 2 : 0), 1024);           // FP16 copies of both layouts
     w.FcmH = off;     off = align_up(off + (g.half ? ((size_t)g.B * g.Kc + kTile) * g.Npad * 2 : 0), 1024);
     w.nrm = off;      off = align_up(off + (size_t)g.B * 2 * g.Npad * 4, 256);
-    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * g.jsplit * 8 + 16384, 256);   // + debug timing area
-    w.opart = off;    off = align_up(off + (g.jsplit > 1 ? (size_t)g.jsplit * g.B * g.Npad * g.Kc * 4 : 0), 256);
+    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * g.jsplit * g.G * 8 + 16384, 256);   // + debug timing area
+    w.opart = off;    off = align_up(off + (g.raw_o ? (size_t)g.jsplit * g.B * g.Npad * g.Kc * 4 : 0), 256);
+    // exact signs: raw pooled features (position-major fp32), FP64 inverse norms, per-sample tie threshold, per-row tie lists
+    w.Ppm = off;      off = align_up(off + (g.exact ? (size_t)g.B * g.Npad * g.Kc * 4 : 0), 256);
+    w.inv64 = off;    off = align_up(off + (g.exact ? (size_t)g.B * 2 * g.Npad * 8 : 0), 256);
+    w.tau = off;      off = align_up(off + (g.exact ? (size_t)g.B * 4 : 0), 256);
+    w.fcnt = off;     off = align_up(off + (g.exact ? (size_t)g.B * g.Npad * g.fnsub * 4 : 0), 256);
+    w.fent = off;     off = align_up(off + (g.exact ? (size_t)g.B * g.Npad * g.fcap * 4 : 0), 256);
     w.total = off;
     return w;
 }
 
 inline PosSaved make_saved(const PosGeom &g) {
     PosSaved s;
-    s.dP = 256;   // [0,8) double: local sum of |D|
+    s.dP = 256;   // [0,8) double: local sum of |D|; exact signs: [8,16) ties listed, [16,24) signs corrected, [24,32) ties dropped
+                  // (list full), [32,36) float: largest |D_exact| / threshold among the corrected entries
     s.total = s.dP + (size_t)g.B * g.Kc * g.Npad * 4;
     return s;
 }
@@ -169,11 +208,17 @@ inline PosSaved make_saved(const PosGeom &g) {
 // ---------------------------------------------------------------------------------------------------------------
 // pack: pool, normalise over channels, round to TF32, write both operand layouts
 // ---------------------------------------------------------------------------------------------------------------
+// kExact (exact signs): the norm is summed in FP64, and the kernel also leaves what fa_pos_finish needs to re-decide near
+// ties: the raw pooled features position-major (Ppm), FP64 inverse norms and zeroed statistics.
+struct PackExact { float *Ppm; double *inv64; unsigned long long *stats; };
+
+template <bool kExact>
 __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1, const float *__restrict__ x2, PosGeom g,
                                                   float *__restrict__ Fpm, float *__restrict__ Fcm, float *__restrict__ nrm,
-                                                  __half *__restrict__ FpmH, __half *__restrict__ FcmH) {
+                                                  __half *__restrict__ FpmH, __half *__restrict__ FcmH, PackExact ex) {
     extern __shared__ float T[];                     // [Kc][33] pooled values of a 32-position strip
     __shared__ float s_inv[2][32];
+    __shared__ double s_part[kExact ? 2 : 1][kExact ? 8 : 1][kExact ? 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, p0 = blockIdx.x * 32, p = p0 + lane;
     const bool valid = p < g.N;
@@ -233,7 +278,26 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
         }
     }
     __syncthreads();
-    if (warp < 2) {                                   // per-position L2 norm over the channels of branch `warp`
+    if (kExact) {
+        // FP64 sums of squares, the channels spread over the eight warps (fixed order: deterministic)
+        double s1 = 0.0, s2 = 0.0;
+        for (int c = warp; c < g.Kc; c += 8) {
+            const double t = (double)T[c * 33 + lane];
+            if (c < g.C1p) s1 = fma(t, t, s1); else s2 = fma(t, t, s2);
+        }
+        s_part[0][warp][lane] = s1;
+        s_part[1][warp][lane] = s2;
+        __syncthreads();
+        if (warp < 2) {
+            double sq = 0.0;
+            for (int i = 0; i < 8; ++i) sq += s_part[warp][i][lane];
+            const double n = sqrt(sq), inv = 1.0 / fmax(n, 1e-12);
+            s_inv[warp][lane] = (float)inv;
+            nrm[((size_t)b * 2 + warp) * g.Npad + p] = (float)n;
+            ex.inv64[((size_t)b * 2 + warp) * g.Npad + p] = inv;
+        }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) ex.stats[threadIdx.x] = 0ull;
+    } else if (warp < 2) {                            // per-position L2 norm over the channels of branch `warp`
         const int c0 = warp ? g.C1p : 0, c1 = warp ? g.Kc : g.C1p;
         float s = 0.f;
         for (int c = c0; c < c1; ++c) { const float t = T[c * 33 + lane]; s = fmaf(t, t, s); }
@@ -261,7 +325,40 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
             for (int c = 2 * lane; c < g.Kc; c += 64)
                 dh[c >> 1] = __floats2half2_rn(T[c * 33 + q] * s_inv[c >= g.C1p][q], T[(c + 1) * 33 + q] * s_inv[c + 1 >= g.C1p][q]);
         }
+        if (kExact) {                                 // raw pooled features, position-major: what the FP64 re-decision reads
+            float *dp = ex.Ppm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
+            for (int c = lane; c < g.Kc; c += 32) dp[c] = T[c * 33 + q];
+        }
     }
+}
+
+// Exact signs: the tie threshold of one sample.  A single tensor-core pass rounds both operands of every product to an 11-bit
+// significand (relative error r ~ 2.1e-4 rms), so D_ij carries an error of variance 2 r^2 sum_c (f_ic f_jc)^2, which for
+// positions with independent features is 2 r^2 sum_c mu_c^2, mu_c = mean_i f_ic^2 (summed over both branches; e.g. 2/C for
+// relu(randn) features).  mu_c is estimated from up to 64 evenly spaced positions in a fixed order (deterministic);
+// `floor2` is the variance of the FP32 accumulation noise, the only term left for the 3xTF32 split.
+// tau = ksigma * sqrt(2 r^2 sum_c mu_c^2 + floor2).
+__global__ void __launch_bounds__(1024) fa_pos_tau(PosGeom g, const float *__restrict__ Ppm, const double *__restrict__ inv64,
+                                                   float r2, float floor2, float ksigma, float *__restrict__ tau) {
+    __shared__ float scratch[33];
+    __shared__ float s_mu[512];
+    const int b = blockIdx.x, c = threadIdx.x & 511, grp = threadIdx.x >> 9;         // two position groups x one thread per channel
+    const int M = g.N < 64 ? g.N : 64, step = g.N / M;
+    float mu = 0.f;
+    if (c < g.Kc) {
+        const double *inv = inv64 + ((size_t)b * 2 + (c >= g.C1p)) * g.Npad;
+#pragma unroll 8
+        for (int m = grp; m < M; m += 2) {
+            const int i = m * step;
+            const float f = Ppm[((size_t)b * g.Npad + i) * g.Kc + c] * (float)inv[i];
+            mu = fmaf(f, f, mu);
+        }
+    }
+    if (grp == 1) s_mu[c] = mu;
+    __syncthreads();
+    if (grp == 0) mu = (mu + s_mu[c]) / (float)M; else mu = 0.f;
+    const float v = block_sum(mu * mu, scratch);
+    if (threadIdx.x == 0) tau[b] = ksigma * sqrtf(2.f * r2 * v + floor2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -283,6 +380,9 @@ struct PosArgs {
     float *dx[2];
     const float *go;
     int direct;
+    // exact signs: per-sample tie threshold, per-row tie counters and lists (column | sign bit of the tensor-core value)
+    const float *tau;
+    unsigned *fcnt, *fent;
 };
 
 #ifdef DSRL_POS_TIMING
@@ -302,6 +402,8 @@ struct EpiCtx {
     float *proj;          // [2][128] partial projections of the two column halves
     uint32_t tmem;
     int itile, js, grp, b, j0, nt, gN, gbeg, T;
+    int part_index, nparts;     // this CTA's slot among the loss partials (-1: it has none), number of slots
+    int sub, nsub;              // exact signs: this CTA's sub-list pair (sub + column half) among a row's nsub sub-lists
 };
 
 // four consecutive channels of the normalised feature row at channel c (fp32 copy, or the FP16 copy of the FP16 form)
@@ -313,99 +415,22 @@ __device__ __forceinline__ float4 load_f4(const float *frow, const __half *frow_
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-template <bool kGrad, bool kPair, bool kHalf = false>
-__device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a, const EpiCtx &c) {
+// After the last column tile: the gradient accumulator -> raw rows (finished by fa_pos_finish) or the normalisation Jacobian
+// in place; then this CTA's loss partial, the whole loss being finished in a fixed order by the last CTA to arrive.
+template <bool kGrad, bool kHalf>
+__device__ __forceinline__ void epilogue_finish(const PosGeom &g, const PosArgs &a, const EpiCtx &c, double acc) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t *d_full = c.d_full, *p_full = c.p_full, *o_full = c.o_full;
+    uint64_t *o_full = c.o_full;
     double *red = c.red;
     int *flag = c.flag;
     float *projbuf = c.proj;
     const uint32_t tmem = c.tmem;
-    const int itile = c.itile, js = c.js, grp = c.grp, b = c.b, j0 = c.j0, nt = c.nt, gN = c.gN, gbeg = c.gbeg, T = c.T;
-    {
-    // ===================================== epilogue warps =====================================
-    const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
-    const int half = (warp - 2) >> 2;                          // which half of the columns / channel chunks this warp converts
+    const int itile = c.itile, js = c.js, b = c.b, gN = c.gN, gbeg = c.gbeg;
+    const int q = warp & 3, r = q * 32 + lane;
+    const int half = (warp - 2) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    double acc = 0.0;
-    float facc = 0.f;
-    long long w_d = 0;
-    const long long t_begin = clock64();
-    for (int jj = 0; jj < nt; ++jj) {
-        const int buf = jj & 1, j = j0 + jj;
-        TWAIT(w_d, mbar_wait(&d_full[buf], (jj >> 1) & 1, 3));
-        fence_after_sync();
-        const bool diag = j == itile;
-        float tsum = 0.f;
-#pragma unroll 1
-        for (int cg = 2 * half; cg < 2 * half + 2; ++cg) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32);
-            tmem_ld32(taddr, v);
-            tmem_ld_wait();
-            if (diag && cg == q) {                               // S_ii = 1 in both branches: a structural tie
-#pragma unroll
-                for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
-            }
-            // |D| sum; the smallest magnitude tells whether any entry is exactly zero (the forced diagonal, exact ties), the
-            // only entries whose sign is 0: everything else takes the short path, sign bit OR 1.0 -- one logic op per entry
-            // (FP16: per pair of entries) instead of a compare + select each
-            float zmin = 3.0e38f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float x = __uint_as_float(v[e]);
-                tsum += fabsf(x);
-                zmin = fminf(zmin, fabsf(x));
-            }
-            if (kGrad && !kHalf) {
-                if (zmin != 0.f) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = (v[e] & 0x80000000u) | 0x3f800000u;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = (v[e] & 0x80000000u) | ((v[e] & 0x7fffffffu) ? 0x3f800000u : 0u);   // sign(x) as a TF32 value
-                }
-                tmem_st32(taddr, v);
-            }
-            if (kGrad && kHalf) {
-                // FP16 sign tile, two positions per 32-bit column.  The columns a warp writes ([64*half, 64*half + 32) of
-                // the tile) lie inside the column range it has already read, so the two halves never race.
-                uint32_t pk[16];
-                if (zmin != 0.f) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) pk[e] = (__byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u) | 0x3c003c00u;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
-                        pk[e] = ((lo >> 16) & 0x8000u) | ((lo & 0x7fffffffu) ? 0x3c00u : 0u) |
-                                ((((hi >> 16) & 0x8000u) | ((hi & 0x7fffffffu) ? 0x3c00u : 0u)) << 16);
-                    }
-                }
-                tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + half * 64 + (cg & 1) * 16), pk);
-            }
-        }
-        if (kGrad) tmem_st_wait();
-        fence_before_sync();
-        __syncwarp();                     // every lane's tcgen05.st has completed and is fenced: one arrival per warp
-        if (lane == 0) { if (kPair) mbar_arrive_leader(&p_full[buf]); else mbar_arrive(&p_full[buf]); }
-        // tile sums are gathered in FP32 over eight tiles (<= 2 * 64 * 8 per thread: rounding ~1e-7 of the running sum) before
-        // they enter the FP64 total -- a DADD per tile was a quarter of the epilogue warps' stall samples (FP64 pipe)
-        facc += (kGrad || diag) ? tsum : 2.f * tsum;
-        if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
-    }
-    acc += (double)facc;
-#ifdef DSRL_POS_TIMING
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
-        long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
-        tm[6] = clock64() - t_begin; tm[7] = w_d;
-    }
-#else
-    (void)t_begin; (void)w_d;
-#endif
-
-    if (kGrad && g.jsplit > 1) {
-        // partial accumulator of this column share: raw rows to global memory, finished by fa_pos_jacobian
+    if (kGrad && g.raw_o) {
+        // partial accumulator of this column share: raw rows to global memory, finished by fa_pos_finish
         mbar_wait(o_full, 0, 7);
         fence_after_sync();
         const int row = itile * kTile + r;
@@ -477,7 +502,7 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
     }
 
     // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
-    if (grp == 0) {
+    if (c.part_index >= 0) {
         const int et = threadIdx.x - 64;                          // index among the epilogue threads
         double tot = warp_sum(acc);
         if (lane == 0) red[et >> 5] = tot;
@@ -485,15 +510,15 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         if (et == 0) {
             double s = 0.0;
             for (int i = 0; i < kEpiWarps; ++i) s += red[i];
-            a.partials[((size_t)js * gridDim.z + b) * T + itile] = s;
+            a.partials[c.part_index] = s;
             __threadfence();
-            const unsigned nparts = gridDim.x * gridDim.z;
+            const unsigned nparts = (unsigned)c.nparts;
             *flag = atomicInc(a.ticket, nparts - 1) == nparts - 1;      // self-resetting
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (*flag) {
             __threadfence();
-            const int nparts = (int)(gridDim.x * gridDim.z);
+            const int nparts = c.nparts;
             double s = 0.0;
             for (int i = et; i < nparts; i += kEpiThreads) s += __ldcg(a.partials + i);
             s = warp_sum(s);
@@ -508,9 +533,125 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
             }
         }
     }
-    }
 }
 
+template <bool kGrad, bool kPair, bool kHalf = false>
+__device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a, const EpiCtx &c) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *d_full = c.d_full, *p_full = c.p_full;
+    const uint32_t tmem = c.tmem;
+    const int itile = c.itile, grp = c.grp, b = c.b, j0 = c.j0, nt = c.nt;
+    {
+    // ===================================== epilogue warps =====================================
+    const int q = warp & 3, r = q * 32 + lane;                 // TMEM lane quarter of this warp, row inside the tile
+    const int half = (warp - 2) >> 2;                          // which half of the columns / channel chunks this warp converts
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    double acc = 0.0;
+    float facc = 0.f;
+    long long w_d = 0;
+    const long long t_begin = clock64();
+    // exact signs: entries with 0 < |D| < tau are listed for fa_pos_finish (once per entry: the channel groups of a row tile
+    // compute the same D, group 0 lists them)
+    // The list of a row is cut into private sub-lists, one per thread that converts part of the row (column half x column
+    // share [x channel-group CTA when the groups split the column tiles]): no atomics, no round trip on the conversion path -- an appended entry is one fire-and-forget store.
+    const bool listing = kGrad && g.exact && grp == 0;
+    const float tau = listing ? __ldg(a.tau + b) : 0.f;                    // 0: nothing is ever listed
+    const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * c.nsub + (size_t)(c.sub + half);
+    unsigned nlisted = 0;
+    for (int jj = 0; jj < nt; ++jj) {
+        const int buf = jj & 1, j = j0 + jj;
+        TWAIT(w_d, mbar_wait(&d_full[buf], (jj >> 1) & 1, 3));
+        fence_after_sync();
+        const bool diag = j == itile;
+        float tsum = 0.f;
+#pragma unroll 1
+        for (int cg = 2 * half; cg < 2 * half + 2; ++cg) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32);
+            tmem_ld32(taddr, v);
+            tmem_ld_wait();
+            if (diag && cg == q) {                               // S_ii = 1 in both branches: a structural tie
+#pragma unroll
+                for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+            }
+            // |D| sum; the smallest magnitude tells whether any entry is exactly zero (the forced diagonal, exact ties), the
+            // only entries whose sign is 0: everything else takes the short path, sign bit OR 1.0 -- one logic op per entry
+            // (FP16: per pair of entries) instead of a compare + select each
+            float zmin = 3.0e38f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float x = __uint_as_float(v[e]);
+                tsum += fabsf(x);
+                zmin = fminf(zmin, fabsf(x));
+            }
+            if (kGrad && zmin < tau) {
+                // near ties of this strip (about one strip in forty per thread): exact zeros -- the forced diagonal, padding,
+                // dead positions, identical branches -- keep sign 0 and are not listed
+                uint32_t m = 0u, neg = 0u;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float ax = fabsf(__uint_as_float(v[e]));
+                    m |= (ax < tau && ax != 0.f) ? (1u << e) : 0u;
+                    neg |= (v[e] >> 31) << e;
+                }
+                while (m) {
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (nlisted < (unsigned)g.fsub) a.fent[gsub * g.fsub + nlisted] = (uint32_t)(j * kTile + cg * 32 + e) | (((neg >> e) & 1u) << 31);
+                    ++nlisted;
+                }
+            }
+            if (kGrad && !kHalf) {
+                if (zmin != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = (v[e] & 0x80000000u) | 0x3f800000u;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = (v[e] & 0x80000000u) | ((v[e] & 0x7fffffffu) ? 0x3f800000u : 0u);   // sign(x) as a TF32 value
+                }
+                tmem_st32(taddr, v);
+            }
+            if (kGrad && kHalf) {
+                // FP16 sign tile, two positions per 32-bit column.  The columns a warp writes ([64*half, 64*half + 32) of
+                // the tile) lie inside the column range it has already read, so the two halves never race.
+                uint32_t pk[16];
+                if (zmin != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) pk[e] = (__byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u) | 0x3c003c00u;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
+                        pk[e] = ((lo >> 16) & 0x8000u) | ((lo & 0x7fffffffu) ? 0x3c00u : 0u) |
+                                ((((hi >> 16) & 0x8000u) | ((hi & 0x7fffffffu) ? 0x3c00u : 0u)) << 16);
+                    }
+                }
+                tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + half * 64 + (cg & 1) * 16), pk);
+            }
+        }
+        if (kGrad) tmem_st_wait();
+        fence_before_sync();
+        __syncwarp();                     // every lane's tcgen05.st has completed and is fenced: one arrival per warp
+        if (lane == 0) { if (kPair) mbar_arrive_leader(&p_full[buf]); else mbar_arrive(&p_full[buf]); }
+        // tile sums are gathered in FP32 over eight tiles (<= 2 * 64 * 8 per thread: rounding ~1e-7 of the running sum) before
+        // they enter the FP64 total -- a DADD per tile was a quarter of the epilogue warps' stall samples (FP64 pipe)
+        facc += (kGrad || diag) ? tsum : 2.f * tsum;
+        if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
+    }
+    acc += (double)facc;
+    if (listing) a.fcnt[gsub] = nlisted;
+#ifdef DSRL_POS_TIMING
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+        long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;      // saved[64..192): role clocks of CTA (0,0,0)
+        tm[6] = clock64() - t_begin; tm[7] = w_d;
+    }
+#else
+    (void)t_begin; (void)w_d;
+#endif
+
+    epilogue_finish<kGrad, kHalf>(g, a, c, acc);
+    }
+}
 
 // kGrad:     also accumulate the gradient contraction (otherwise loss only, tiles j >= i by symmetry)
 // kSplit:    3xTF32 -- D = hi*hi + hi*lo + lo*hi with the lo parts as extra operand boxes
@@ -643,7 +784,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 #undef STAGE_FILL
 #ifdef DSRL_POS_TIMING
         if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
-            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;      // saved[64..192): role clocks of CTA (0,0,0)
             tm[0] = clock64() - t_begin; tm[1] = w_empty;
         }
 #else
@@ -763,7 +904,7 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
 #undef RING_TAKE
 #ifdef DSRL_POS_TIMING
         if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
-            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;      // saved[64..192): role clocks of CTA (0,0,0)
             tm[2] = clock64() - t_begin; tm[3] = w_full; tm[4] = w_p; tm[5] = w_drain;
         }
 #else
@@ -774,6 +915,10 @@ fa_pos_tiles(const __grid_constant__ CUtensorMap tm_pm, const __grid_constant__ 
         EpiCtx c;
         c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
         c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
+        // every channel group computes the same D: group 0 reports the loss partial and lists the near ties
+        c.part_index = grp == 0 ? (js * (int)gridDim.z + b) * T + itile : -1;
+        c.nparts = (int)(gridDim.x * gridDim.z);
+        c.sub = 2 * js; c.nsub = g.fnsub;
         epilogue_role<kGrad, false, kHalf>(g, a, c);
     }
 #undef RING_ADVANCE
@@ -916,7 +1061,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #undef STAGE_FILL
 #ifdef DSRL_POS_TIMING
         if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
-            long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;      // saved[64..192): role clocks of CTA (0,0,0)
             tm[0] = clock64() - t_begin; tm[1] = w_empty;
         }
 #else
@@ -1008,7 +1153,7 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #undef MMA4_SS
 #ifdef DSRL_POS_TIMING
             if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
-                long long *tm = reinterpret_cast<long long *>(a.partials) + 1024;
+                long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;      // saved[64..192): role clocks of CTA (0,0,0)
                 tm[2] = clock64() - t_begin; tm[3] = w_full; tm[4] = w_p; tm[5] = 0;
             }
 #else
@@ -1019,6 +1164,9 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         EpiCtx c;
         c.d_full = d_full; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
         c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
+        c.part_index = grp == 0 ? (js * (int)gridDim.z + b) * T + itile : -1;
+        c.nparts = (int)(gridDim.x * gridDim.z);
+        c.sub = 2 * js; c.nsub = g.fnsub;
         epilogue_role<true, true, kHalf>(g, a, c);
     }
 #undef RING_ADVANCE
@@ -1029,11 +1177,544 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// jsplit > 1: sum the partial accumulators, apply the normalisation Jacobian, store dP channel-major
+// Two channel groups without computing D twice (FP16 form; cluster of 4 = two CTA pairs on the same two row tiles)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fa_pos_jacobian(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
-                                                      const __half *__restrict__ FcmH, const float *__restrict__ nrm, float grad_scale,
-                                                      float *__restrict__ dP, float *dx1, float *dx2, const float *go) {
+// With more than 256 channels in all, the gradient accumulator of a row tile does not fit the tensor memory of one SM next
+// to a D tile, so each channel group (= branch) has its own CTA pair.  fa_pos_tiles_pair lets both pairs compute every D
+// tile (executed work 12 C N^2 per sample instead of 8 C N^2).  Here the two pairs of a cluster split the column tiles:
+// pair `grp` computes D(i, j) for the tiles j = j0 + 2k + grp of round k, converts it as usual (|D| sum, near-tie listing,
+// packed FP16 sign tile in its own tensor memory) and ships the SIGNS -- one sign bit and one is-zero bit per entry, 4 KB per
+// tile and CTA -- to the CTA of the other pair that owns the same rows, through distributed shared memory.  That CTA
+// expands the bits into the spare columns of the same tensor-memory buffer, and each pair runs the gradient MMAs of BOTH
+// tiles of the round for its own channels.  Per round and pair: one D tile + two gradient tiles instead of two + two.
+//   x_full[slot]  (in the receiver)  the partner's bits of this round have landed       (st.async stores count their bytes on it)
+//   x_empty[slot] (in the sender)    the partner has consumed the bits written two rounds ago
+//   p_own / p_rem (in the pair leader) sign tile of the own / the received tile is in tensor memory (both CTAs' epilogue warps)
+// Sign / zero bits of a 32-entry strip travel as two 32-bit words laid out for a cheap expansion: bit e = entry 2e,
+// bit 16 + e = entry 2e + 1 (e < 16), so that the packed FP16 pair e is ((bits << (15 - e)) & 0x80008000) | 1.0|1.0.
+__device__ __forceinline__ void expand_signs(uint32_t neg, uint32_t zero, uint32_t (&pk)[16]) {
+    if (zero == 0u) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = ((neg << (15 - e)) & 0x80008000u) | 0x3c003c00u;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const uint32_t one = ~(zero << (15 - e)) & 0x80008000u;           // bit 15 / 31 set where the entry is NOT zero
+            pk[e] = ((neg << (15 - e)) & one) | ((one >> 1) - (one >> 5));    // 0x3c00 = 0x4000 - 0x0400 per nonzero half
+        }
+    }
+}
+
+constexpr int kQuadThreads = kThreads + 128;      // + warps 10..13: one per TMEM lane quarter, expand the received sign bits
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kQuadThreads, 1)
+fa_pos_tiles_quad(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                  const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t raw = smem_u32(smraw);
+    unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
+    constexpr int kElems = 64;                                      // FP16 operand elements per 128-byte row
+    constexpr int kStageBytes = kBoxBytes;                          // 16 KB: two K boxes (64 rows of K_j each) or one V box
+    const int S = g.quad_stages, nkc = g.nkh;
+    unsigned char *qreg = sm;
+    unsigned char *ring = sm + (size_t)nkc * kBoxBytes;
+    unsigned char *xchg = ring + (size_t)S * kStageBytes;           // [2 slots][2 halves][128 rows] x 16 bytes, written by the partner
+    uint64_t *full = reinterpret_cast<uint64_t *>(xchg + kXchgBytes);
+    uint64_t *empty = full + S;
+    uint64_t *q_full = empty + S;
+    uint64_t *d_full = q_full + 1;      // [2]
+    uint64_t *p_own = d_full + 2;       // [2]
+    uint64_t *p_rem = p_own + 2;        // [2]
+    uint64_t *o_full = p_rem + 2;
+    uint64_t *x_full = o_full + 1;      // [2]
+    uint64_t *x_empty = x_full + 2;     // [2]
+    uint64_t *c_done = x_empty + 2;     // [2] this CTA's conversion warps are done with the D buffer (its spare columns may be written)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(c_done + 2);
+    double *red = reinterpret_cast<double *>(c_done + 3);
+    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
+    float *projbuf = reinterpret_cast<float *>(flag + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank & 1u) == 0;                            // of its pair
+    const int grp = (int)(rank >> 1);                               // channel group = pair index inside the cluster
+    const uint32_t partner = rank ^ 2u;                             // same rows, other channel group
+    const int T = g.tiles, Th = T / 2;
+    const int pairidx = blockIdx.x >> 2, js = pairidx / Th;
+    const int itile = 2 * (pairidx - js * Th) + (int)(rank & 1u), b = blockIdx.z;
+    const int nt = T / g.jsplit, j0 = js * nt, nr = nt / 2;         // rounds: one own + one received column tile each
+    const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], vrows = gN / 2;
+    const uint32_t vbytes = (uint32_t)vrows * 128u;
+    const int row_q = b * g.Npad + itile * kTile;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_q);
+        prefetch_tmap(&tm_k);
+        prefetch_tmap(&tm_v);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&d_full[i], 1);
+            mbar_init(&p_own[i], 2 * kEpiWarps);
+            mbar_init(&p_rem[i], 2 * 4);            // the four expansion warps of both CTAs
+            mbar_init(&x_full[i], 1);               // armed per round with the 4 KB the partner's st.async stores deliver
+            mbar_init(&x_empty[i], 4);              // the partner's four expansion warps
+            mbar_init(&c_done[i], kEpiWarps);
+        }
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
+    fence_before_sync();
+    cluster_sync();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    int slot = 0;
+    uint32_t ph = 0;
+#define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
+
+    if (warp == 0) {
+        // ===================================== TMA producer (every CTA, for its own shared memory) =====================================
+        long long w_empty = 0;
+        const long long t_begin = clock64();
+        if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nkc * kBoxBytes);
+            for (int kc = 0; kc < nkc; ++kc) tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, kc * kElems, row_q);
+        }
+        __syncwarp();
+#define STAGE_FILL(bytes_per_cta, ...)                                                                   \
+        do {                                                                                             \
+            TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 21));                                         \
+            if (elect_one()) {                                                                           \
+                unsigned char *dst = ring + (size_t)slot * kStageBytes;                                  \
+                uint64_t *bar = &full[slot];                                                             \
+                if (leader) mbar_arrive_expect_tx(bar, 2u * (uint32_t)(bytes_per_cta));                  \
+                __VA_ARGS__                                                                              \
+            }                                                                                            \
+            __syncwarp();                                                                                \
+            RING_ADVANCE();                                                                              \
+        } while (0)
+        auto load_k = [&](int j) {
+            const int row_k = b * g.Npad + j * kTile + (int)(rank & 1u) * (kTile / 2);       // this CTA's 64 rows of K_j
+            for (int kc0 = 0; kc0 < nkc; kc0 += 2) {
+                const int nu = min(2, nkc - kc0);
+                STAGE_FILL(nu * kPairKBox, {
+                    for (int u = 0; u < nu; ++u) tma_load_2d_pair(dst + (size_t)u * kPairKBox, &tm_k, bar, (kc0 + u) * kElems, row_k);
+                });
+            }
+        };
+        auto load_v = [&](int j) {
+            const int row_v = b * g.Kc + gbeg + (int)(rank & 1u) * vrows;                    // this CTA's half of the group's channels
+            for (int jc = 0; jc < 2; ++jc) STAGE_FILL(vbytes, { tma_load_2d_pair(dst, &tm_v, bar, j * kTile + jc * kElems, row_v); });
+        };
+        load_k(j0 + grp);
+        for (int k = 0; k < nr; ++k) {
+            if (k + 1 < nr) load_k(j0 + 2 * (k + 1) + grp);
+            load_v(j0 + 2 * k + grp);
+            load_v(j0 + 2 * k + (grp ^ 1));
+        }
+#undef STAGE_FILL
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.z == 0 && lane == 0) {
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+            tm[0] = clock64() - t_begin; tm[1] = w_empty;
+        }
+#else
+        (void)t_begin; (void)w_empty;
+#endif
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (the leader of each pair) =====================================
+        if (leader) {
+            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4;
+            const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
+            const uint32_t id_pos = idesc_f16(2 * kTile, kTile, false), id_neg = idesc_f16(2 * kTile, kTile, true);
+            const uint32_t id_g = idesc_f16(2 * kTile, gN, false);
+            const uint16_t cmask = (uint16_t)(3u << (2 * grp));     // the two CTAs of this pair
+            const int q_neg = g.C1p / 16;                           // first K step (16 channels) of branch 2 (subtracted)
+            long long w_full = 0, w_own = 0, w_rem = 0;
+            const long long t_begin = clock64();
+            auto gemm_d = [&](int k) {
+                const int buf = k & 1;
+                const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
+                for (int kc0 = 0; kc0 < nkc; kc0 += 2) {
+                    TWAIT(w_full, mbar_wait(&full[slot], ph, 22));
+                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
+                    const int ss = slot;
+                    RING_ADVANCE();
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int kc = kc0 + u;
+                            if (kc < nkc) {
+                                const uint64_t ad = q_desc + (uint64_t)kc * kBoxDesc, bd = sd + (uint64_t)u * kKDesc;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_f16_ss_pair(dcol, ad + 2 * ks, bd + 2 * ks, 4 * kc + ks >= q_neg ? id_neg : id_pos, (kc | ks) != 0);
+                            }
+                        }
+                        umma_commit_pair(&empty[ss], cmask);
+                        if (kc0 + 2 >= nkc) umma_commit_pair(&d_full[buf], cmask);
+                    }
+                    __syncwarp();
+                }
+            };
+            // which = 0: the tile this pair converted itself (packed signs at columns [0,32) and [64,96) of the buffer),
+            // which = 1: the tile received from the other pair (columns [32,64) and [96,128))
+            auto gemm_g = [&](int k, int which, bool last) {
+                const int buf = k & 1;
+                const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile + (uint32_t)which * 32u;
+                if (which) TWAIT(w_rem, mbar_wait(&p_rem[buf], (k >> 1) & 1, 23)); else TWAIT(w_own, mbar_wait(&p_own[buf], (k >> 1) & 1, 23));
+                for (int jc = 0; jc < 2; ++jc) {
+                    TWAIT(w_full, mbar_wait(&full[slot], ph, 24));
+                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
+                    const int ss = slot;
+                    RING_ADVANCE();
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_f16_ts_pair(tmem, pcol + (uint32_t)(jc * 64 + ks * 8), sd + 2 * ks, id_g, (k | which | jc | ks) != 0);
+                        umma_commit_pair(&empty[ss], cmask);
+                        if (last && jc == 1) umma_commit_pair(o_full, cmask);
+                    }
+                    __syncwarp();
+                }
+            };
+            mbar_wait(q_full, 0, 25);
+            gemm_d(0);
+            for (int k = 0; k < nr; ++k) {
+                if (k + 1 < nr) gemm_d(k + 1);
+                gemm_g(k, 0, false);
+                gemm_g(k, 1, k == nr - 1);
+            }
+#ifdef DSRL_POS_TIMING
+            if (blockIdx.x == 0 && blockIdx.z == 0 && lane == 0) {
+                long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+                tm[2] = clock64() - t_begin; tm[3] = w_full; tm[4] = w_own; tm[5] = w_rem;
+            }
+#else
+            (void)t_begin; (void)w_full; (void)w_own; (void)w_rem;
+#endif
+        }
+    } else if (warp < 2 + kEpiWarps) {
+        // ===================================== conversion warps: the tiles this pair computed =====================================
+        // |D| sum, near-tie listing, packed FP16 signs -> own tensor memory, sign / zero bits -> the partner CTA
+        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t x_remote = map_to_cta(xchg, partner) + (uint32_t)((half * kTile + r) * 16);      // where this thread's bits go
+        const uint32_t xfull_remote = map_to_cta(x_full, partner);
+        const float tau = g.exact ? __ldg(a.tau + b) : 0.f;
+        const int nsub = g.fnsub;
+        const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * nsub + (size_t)((2 * js + half) * 2 + grp);
+        unsigned nlisted = 0;
+        double acc = 0.0;
+        float facc = 0.f;
+        long long w_d = 0, w_xe = 0, t_conv = 0, t_ship = 0;
+        const long long t_begin = clock64();
+        for (int k = 0; k < nr; ++k) {
+            const int buf = k & 1, j = j0 + 2 * k + grp;
+            const uint32_t php = (uint32_t)(k >> 1) & 1u;
+            TWAIT(w_d, mbar_wait(&d_full[buf], php, 26));
+            fence_after_sync();
+#ifdef DSRL_POS_TIMING
+            const long long t1 = clock64();
+#endif
+            const bool diag = j == itile;
+            float tsum = 0.f;
+            uint32_t negm[2], zerom[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int cg = 2 * half + s;
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32), v);
+                tmem_ld_wait();
+                if (diag && cg == q) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+                }
+                float zmin = 3.0e38f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = __uint_as_float(v[e]);
+                    tsum += fabsf(x);
+                    zmin = fminf(zmin, fabsf(x));
+                }
+                if (zmin < tau) {                            // near ties (exact signs), see epilogue_role
+                    uint32_t m = 0u, neg = 0u;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float ax = fabsf(__uint_as_float(v[e]));
+                        m |= (ax < tau && ax != 0.f) ? (1u << e) : 0u;
+                        neg |= (v[e] >> 31) << e;
+                    }
+                    while (m) {
+                        const int e = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (nlisted < (unsigned)g.fsub) a.fent[gsub * g.fsub + nlisted] = (uint32_t)(j * kTile + cg * 32 + e) | (((neg >> e) & 1u) << 31);
+                        ++nlisted;
+                    }
+                }
+                uint32_t pk[16], M = 0u, Z = 0u;
+                if (zmin != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t sg = __byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u;
+                        pk[e] = sg | 0x3c003c00u;
+                        M = (M >> 1) | sg;                   // after the last pair: bit e = sign of entry 2e, bit 16 + e = of entry 2e + 1
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
+                        const uint32_t zz = ((lo & 0x7fffffffu) ? 0u : 0x8000u) | ((hi & 0x7fffffffu) ? 0u : 0x80000000u);
+                        const uint32_t sg = __byte_perm(lo, hi, 0x7632) & 0x80008000u & ~zz;
+                        pk[e] = sg | (0x3c003c00u & ~((zz >> 2) | (zz >> 3) | (zz >> 4) | (zz >> 5)));      // no 1.0 where the entry is zero
+                        M = (M >> 1) | sg;
+                        Z = (Z >> 1) | zz;
+                    }
+                }
+                negm[s] = M; zerom[s] = Z;
+                tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + half * 64 + s * 16), pk);
+            }
+            tmem_st_wait();
+            fence_before_sync();
+#ifdef DSRL_POS_TIMING
+            const long long t2 = clock64();
+            t_conv += t2 - t1;
+#endif
+            if (k >= 2) TWAIT(w_xe, mbar_wait(&x_empty[buf], php ^ 1u, 27));       // the partner has expanded what this slot held two rounds ago
+            st_async_v4(x_remote + (uint32_t)buf * (kXchgBytes / 2), xfull_remote + (uint32_t)buf * 8u, negm[0], negm[1], zerom[0], zerom[1]);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_leader(&p_own[buf]);
+                mbar_arrive(&c_done[buf]);
+            }
+            facc += tsum;
+            if ((k & 7) == 7) { acc += (double)facc; facc = 0.f; }
+#ifdef DSRL_POS_TIMING
+            t_ship += clock64() - t2;
+#endif
+        }
+        acc += (double)facc;
+        if (g.exact) a.fcnt[gsub] = nlisted;
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+            tm[6] = clock64() - t_begin; tm[7] = w_d; tm[9] = w_xe; tm[10] = t_conv; tm[11] = t_ship;
+        }
+#else
+        (void)t_begin; (void)w_d; (void)w_xe; (void)t_conv; (void)t_ship;
+#endif
+        EpiCtx c;
+        c.d_full = d_full; c.p_full = p_own; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
+        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
+        c.part_index = (int)(blockIdx.z * gridDim.x + blockIdx.x);               // every CTA converted its own share of the D tiles
+        c.nparts = (int)(gridDim.x * gridDim.z);
+        c.sub = 0; c.nsub = nsub;
+        epilogue_finish<true, true>(g, a, c, acc);
+    } else {
+        // ===================================== expansion warps: the tiles the other pair computed =====================================
+        // sign / zero bits from this CTA's exchange slot -> packed FP16 signs in the spare columns of the same D buffer
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t xempty_remote = map_to_cta(x_empty, partner);
+        long long w_xf = 0;
+        for (int k = 0; k < nr; ++k) {
+            const int buf = k & 1;
+            const uint32_t php = (uint32_t)(k >> 1) & 1u;
+            if (warp == 2 + kEpiWarps && lane == 0) mbar_arrive_expect_tx(&x_full[buf], kXchgBytes / 2);     // this round's 4 KB
+            TWAIT(w_xf, mbar_wait(&x_full[buf], php, 28));
+            mbar_wait(&c_done[buf], php, 29);          // the spare columns still hold D until this CTA's conversion warps have read it
+            fence_after_sync();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 bits = *reinterpret_cast<const uint4 *>(xchg + (size_t)buf * (kXchgBytes / 2) + (size_t)((h * kTile + r) * 16));
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    uint32_t pk[16];
+                    expand_signs(s ? bits.y : bits.x, s ? bits.w : bits.z, pk);
+                    tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + h * 64 + 32 + s * 16), pk);
+                }
+            }
+            tmem_st_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_leader(&p_rem[buf]);
+                mbar_arrive_cluster_relaxed(xempty_remote + (uint32_t)buf * 8u);
+            }
+        }
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == kThreads) reinterpret_cast<long long *>(a.sum_out)[8 + 8] = w_xf;
+#else
+        (void)w_xf;
+#endif
+    }
+#undef RING_ADVANCE
+
+    fence_before_sync();
+    cluster_sync();                         // MMAs read peer shared / tensor memory, partners write each other's exchange slots
+    if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// exact signs: re-decide the listed near ties, correct the raw accumulator rows
+// ---------------------------------------------------------------------------------------------------------------
+// The tile kernel took sign(D_ij) from the tensor-core value and listed every entry with 0 < |D_ij| < tau.  Here one warp per
+// row i re-evaluates those entries from the raw pooled features,
+//     D_ij = <P1_i, P1_j> / (n1_i n1_j) - <P2_i, P2_j> / (n2_i n2_j),
+// first in FP32 FMA (a row of P_j is 2 KB: the pass is bound by those L2 gathers, ~1e-3 N^2 of them per sample): with unit
+// vectors the rounding error of that evaluation is below (16 + 5) 2^-24 per branch whatever the data, so |D| > kSafe32
+// settles the sign; the few per cent below it are redone in FP64, where products of two floats are exact.  Where the sign
+// differs from the one the tensor cores used, (s_exact - s_used) * Fh_j is added to the accumulator row -- the gradient is
+// linear in the sign tile, so this is the row the tensor cores would have produced with the exact signs.  Corrections are
+// summed in 2^-30 fixed point (integer adds: the order of a list does not matter), so results are bit-repeatable.  A row
+// with more near ties than its lists hold keeps the tensor-core signs for the overflow (counted).
+struct ResolveArgs {
+    const float *Ppm; const double *inv64; const float *tau; const unsigned *fcnt, *fent; unsigned long long *stats;
+    float *opart;            // raw accumulator rows of column share 0: (B, Npad, Kc)
+};
+constexpr float kSafe32 = 3.0e-6f;
+
+__global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
+    constexpr int kU = 4;                         // a lane holds channels 4*lane + 128*u .. +3, u < 4 (Kc <= 512)
+    constexpr int kR = 2;                         // entries per round: 8 independent 16-byte loads in flight per lane
+    constexpr float kFix = 1073741824.f;          // 2^30
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long grow_ll = (long long)blockIdx.x * 8 + warp;
+    if (grow_ll >= (long long)g.B * g.Npad) return;
+    const size_t grow = (size_t)grow_ll;
+    const int b = (int)(grow / g.Npad), irow = (int)(grow - (size_t)b * g.Npad);
+    const int nsub = g.fnsub;                     // <= 16
+    // this row's sub-lists (lane s holds the count of sub-list s) as one sequence of n entries
+    const unsigned cnt_s = lane < nsub ? ex.fcnt[grow * nsub + lane] : 0u;
+    const unsigned len_s = min(cnt_s, (unsigned)g.fsub);
+    unsigned end_s = len_s;                       // inclusive prefix sum over the sub-lists
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, end_s, o); if (lane >= o) end_s += t; }
+    const int n = (int)__shfl_sync(0xffffffffu, end_s, nsub - 1);
+    const unsigned listed = (unsigned)warp_sum((int)cnt_s);
+    if (listed == 0) return;
+    const float tau = ex.tau[b];
+    const double *inv1 = ex.inv64 + (size_t)b * 2 * g.Npad, *inv2 = inv1 + g.Npad;
+    float4 pi[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        const int c = 4 * lane + 128 * u;
+        pi[u] = c < g.Kc ? __ldg(reinterpret_cast<const float4 *>(ex.Ppm + grow * g.Kc + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const double i1 = inv1[irow], i2 = inv2[irow];
+    long long corr[4 * kU];
+#pragma unroll
+    for (int t = 0; t < 4 * kU; ++t) corr[t] = 0;
+    unsigned n_fix = 0;
+    float worst = 0.f;
+    const unsigned *ent = ex.fent + grow * g.fcap;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        // lane l owns entry e0 + l of the sequence: which sub-list holds it, the entry, and the two normalisation weights
+        const int e = e0 + lane;
+        int sub = 0;
+        unsigned start = 0;
+        for (int t = 0; t < nsub; ++t) {
+            const unsigned end_t = __shfl_sync(0xffffffffu, end_s, t);
+            if (end_t <= (unsigned)e) { sub = t + 1; start = end_t; }
+        }
+        const uint32_t en_l = e < n ? __ldg(ent + (size_t)sub * g.fsub + (e - start)) : 0xffffffffu;
+        const int j_l = (int)(en_l & 0x7fffffffu);
+        const double w1_l = e < n ? inv1[j_l] * i1 : 0.0, w2_l = e < n ? inv2[j_l] * i2 : 0.0;
+        const int m = min(32, n - e0);
+        for (int h0 = 0; h0 < m; h0 += kR) {
+            uint32_t en[kR];
+            float4 pj[kR][kU];
+#pragma unroll
+            for (int h = 0; h < kR; ++h) {
+                en[h] = __shfl_sync(0xffffffffu, en_l, (h0 + h) & 31);
+                if (h0 + h >= m) en[h] = 0xffffffffu;
+                const size_t jrow = (size_t)b * g.Npad + (en[h] & 0x7fffffffu);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int c = 4 * lane + 128 * u;
+                    pj[h][u] = (en[h] != 0xffffffffu && c < g.Kc) ? __ldg(reinterpret_cast<const float4 *>(ex.Ppm + jrow * g.Kc + c))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < kR; ++h) {
+                if (en[h] == 0xffffffffu) continue;                       // warp-uniform
+                const double w1 = __shfl_sync(0xffffffffu, w1_l, (h0 + h) & 31), w2 = __shfl_sync(0xffffffffu, w2_l, (h0 + h) & 31);
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    float t = pi[u].x * pj[h][u].x;
+                    t = fmaf(pi[u].y, pj[h][u].y, t); t = fmaf(pi[u].z, pj[h][u].z, t); t = fmaf(pi[u].w, pj[h][u].w, t);
+                    if (4 * lane + 128 * u < g.C1p) s1 += t; else s2 += t;
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                const float D32 = s1 * (float)w1 - s2 * (float)w2;
+                double D = (double)D32;
+                if (!(fabsf(D32) > kSafe32)) {
+                    // too close for FP32 (also NaN / overflow): exact products, FP64 sums
+                    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const double t = (double)pi[u].x * (double)pj[h][u].x + (double)pi[u].y * (double)pj[h][u].y +
+                                         (double)pi[u].z * (double)pj[h][u].z + (double)pi[u].w * (double)pj[h][u].w;
+                        if (4 * lane + 128 * u < g.C1p) d1 += t; else d2 += t;
+                    }
+                    d1 = warp_sum(d1);
+                    d2 = warp_sum(d2);
+                    D = d1 * w1 - d2 * w2;
+                }
+                const int s_exact = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0), s_used = (en[h] >> 31) ? -1 : 1;
+                if (s_exact != s_used) {
+                    ++n_fix;
+                    worst = fmaxf(worst, fabsf((float)D) / tau);
+                    const int j = (int)(en[h] & 0x7fffffffu);
+                    const float f1 = (float)inv1[j] * kFix, f2 = (float)inv2[j] * kFix;      // Fh_j = P_j / n_j, in 2^-30 units
+                    const long long dl = (long long)(s_exact - s_used);
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const float w = 4 * lane + 128 * u < g.C1p ? f1 : f2;
+                        corr[4 * u + 0] += dl * (long long)__float2int_rn(pj[h][u].x * w);
+                        corr[4 * u + 1] += dl * (long long)__float2int_rn(pj[h][u].y * w);
+                        corr[4 * u + 2] += dl * (long long)__float2int_rn(pj[h][u].z * w);
+                        corr[4 * u + 3] += dl * (long long)__float2int_rn(pj[h][u].w * w);
+                    }
+                }
+            }
+        }
+    }
+    if (n_fix) {
+        float *orow = ex.opart + grow * g.Kc;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int c = 4 * lane + 128 * u;
+            if (c < g.Kc) {
+                float4 o = *reinterpret_cast<float4 *>(orow + c);
+                o.x += (float)corr[4 * u + 0] * (1.f / kFix); o.y += (float)corr[4 * u + 1] * (1.f / kFix);
+                o.z += (float)corr[4 * u + 2] * (1.f / kFix); o.w += (float)corr[4 * u + 3] * (1.f / kFix);
+                *reinterpret_cast<float4 *>(orow + c) = o;
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(ex.stats + 0, (unsigned long long)listed);
+        if (n_fix) atomicAdd(ex.stats + 1, (unsigned long long)n_fix);
+        if (listed > (unsigned)n) atomicAdd(ex.stats + 2, (unsigned long long)(listed - (unsigned)n));
+        if (n_fix) atomicMax(reinterpret_cast<unsigned *>(ex.stats + 3), __float_as_uint(worst));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// finish: sum the partial accumulators (jsplit shares), apply the normalisation Jacobian, store dP channel-major (or dX
+// itself: fused forward + backward without pooling)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fa_pos_finish(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
+                                                    const __half *__restrict__ FcmH, const float *__restrict__ nrm, float grad_scale,
+                                                    float *__restrict__ dP, float *dx1, float *dx2, const float *go) {
     auto feat = [&](size_t o) { return Fcm ? Fcm[o] : __half2float(FcmH[o]); };      // FP16 form: only the FP16 copy exists
     extern __shared__ float T[];                     // [Kc][33] summed accumulator of a 32-position strip
     __shared__ float s_proj[2][32];
@@ -1171,31 +1852,42 @@ int opt_in_smem(K kern, size_t bytes) {
 int fa_pos_backward(int precision, const float *, const float *, const void *saved_v, size_t saved_bytes, const float *grad_out,
                     float *dx1, float *dx2, int B, int C1, int C2, int H, int W, int k, int, void *, size_t, cudaStream_t st);
 
-size_t fa_pos_saved_bytes(int B, int C1, int C2, int H, int W, int k) {
+// precision = DSRL_PREC_{FP32,TF32,F16}, optionally | DSRL_PREC_EXACT_SIGNS
+static bool geom_for(int precision, int B, int C1, int C2, int H, int W, int k, PosGeom &g) {
+    const int base = precision & ~DSRL_PREC_EXACT_SIGNS;
+    if (base != DSRL_PREC_TF32 && base != DSRL_PREC_FP32 && base != DSRL_PREC_F16) return false;
+    return make_geom(B, C1, C2, H, W, k, base == DSRL_PREC_FP32, g, base == DSRL_PREC_F16, (precision & DSRL_PREC_EXACT_SIGNS) != 0);
+}
+
+size_t fa_pos_saved_bytes(int precision, int B, int C1, int C2, int H, int W, int k) {
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, 0, g)) return 0;
+    if (!geom_for(precision, B, C1, C2, H, W, k, g)) return 0;
     return make_saved(g).total;
 }
 
-size_t fa_pos_workspace_bytes(int B, int C1, int C2, int H, int W, int k) {
+size_t fa_pos_workspace_bytes(int precision, int B, int C1, int C2, int H, int W, int k) {
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, 1, g)) return 0;     // the query has no precision: the larger of the 3xTF32 and FP16 layouts
-    const size_t split_total = make_ws(g).total;
-    if (!make_geom(B, C1, C2, H, W, k, 0, g, 1)) return 0;
-    const size_t half_total = make_ws(g).total;
-    return split_total > half_total ? split_total : half_total;
+    if (!geom_for(precision, B, C1, C2, H, W, k, g)) return 0;
+    return make_ws(g).total;
 }
+
+// operand-rounding model of the tie threshold (fa_pos_tau): relative rms error of one rounding to an 11-bit significand, and
+// the variance of the FP32 accumulation noise of a D tile
+static constexpr float kRound11 = 2.1e-4f;
+static constexpr float kAccNoise = 1.0e-6f;
 
 // go / dx1 / dx2 (all non-null, k == 1): fused forward + backward -- the gradient kernel writes dX directly (scaled by *go) and the
 // saved blob's dP is not produced; *fused_out tells the caller that no backward launch is needed.
 int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, int C1, int C2, int H, int W, int k, int reduction,
                         int need_grad, float *loss_out, void *saved_v, size_t saved_bytes, void *ws_v, size_t ws_bytes, cudaStream_t st,
                         const float *go, float *dx1, float *dx2, int *fused_out) {
-    if (precision != DSRL_PREC_TF32 && precision != DSRL_PREC_FP32 && precision != DSRL_PREC_F16)
-        DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass), F16 (kind::f16 operands) or FP32 (3xTF32 split)");
+    const int base = precision & ~DSRL_PREC_EXACT_SIGNS;
+    if (base != DSRL_PREC_TF32 && base != DSRL_PREC_FP32 && base != DSRL_PREC_F16)
+        DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(position): precision must be TF32 (one tcgen05 kind::tf32 pass), F16 (kind::f16 operands) or FP32 (3xTF32 split), optionally | EXACT_SIGNS");
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, precision == DSRL_PREC_FP32, g, precision == DSRL_PREC_F16))
+    if (!geom_for(need_grad ? precision : base, B, C1, C2, H, W, k, g))        // the loss alone has no sign decisions
         DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry B=%d C=(%d,%d) H=%d W=%d k=%d (channels per branch <= 256)", B, C1, C2, H, W, k);
+    precision = base;
     const PosWs wo = make_ws(g);
     const PosSaved so = make_saved(g);
     if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(position): saved blob too small (%zu < %zu)", saved_bytes, so.total);
@@ -1207,13 +1899,46 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     float *nrm = reinterpret_cast<float *>(ws + wo.nrm);
 
     const size_t pack_smem = (size_t)g.Kc * 33 * 4;
-    int rc = opt_in_smem(fa_pos_pack, pack_smem);
+    int rc = opt_in_smem(fa_pos_pack<false>, pack_smem);
     if (rc) return rc;
+    if ((rc = opt_in_smem(fa_pos_pack<true>, pack_smem))) return rc;
     __half *FpmH = g.half ? reinterpret_cast<__half *>(ws + wo.FpmH) : nullptr;
     __half *FcmH = g.half ? reinterpret_cast<__half *>(ws + wo.FcmH) : nullptr;
+    PackExact pex;
+    pex.Ppm = reinterpret_cast<float *>(ws + wo.Ppm);
+    pex.inv64 = reinterpret_cast<double *>(ws + wo.inv64);
+    pex.stats = reinterpret_cast<unsigned long long *>(saved + 8);
+    ResolveArgs rex;
+    rex.Ppm = pex.Ppm; rex.inv64 = pex.inv64; rex.stats = pex.stats;
+    rex.fcnt = reinterpret_cast<unsigned *>(ws + wo.fcnt);
+    rex.tau = reinterpret_cast<float *>(ws + wo.tau);
+    rex.fent = reinterpret_cast<unsigned *>(ws + wo.fent);
+    rex.opart = reinterpret_cast<float *>(ws + wo.opart);
     // FP16 form: the FP16 copies are the only ones written (and read back by the normalisation Jacobian)
-    fa_pos_pack<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH);
+    if (g.exact) {
+        fa_pos_pack<true><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
+        DSRL_LAUNCH_CHECK();
+        float ksigma = 3.5f;
+        if (const char *e = getenv("DSRL_POS_KSIGMA")) { const float v = (float)atof(e); if (v >= 0.f && v < 1e6f) ksigma = v; }   // tuning / test hook
+        const float r = g.split ? kRound11 * kRound11 : kRound11;      // 3xTF32: the products missing from the split are second order
+        fa_pos_tau<<<B, 1024, 0, st>>>(g, pex.Ppm, pex.inv64, r * r, kAccNoise * kAccNoise, ksigma, reinterpret_cast<float *>(ws + wo.tau));
+    } else {
+        fa_pos_pack<false><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
+    }
     DSRL_LAUNCH_CHECK();
+    // the tile kernel's raw accumulator rows -> dP / dX (all variants share it)
+    auto finish = [&](const PosArgs &a) -> int {
+        int rc2;
+        if (g.exact) {
+            const long long rows = (long long)B * g.Npad;
+            fa_pos_resolve<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g, rex);
+            DSRL_LAUNCH_CHECK();
+        }
+        if ((rc2 = opt_in_smem(fa_pos_finish, pack_smem))) return rc2;
+        fa_pos_finish<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
+        DSRL_LAUNCH_CHECK();
+        return DSRL_OK;
+    };
 
     CUtensorMap tm_pm, tm_cm;
     if ((rc = make_map(&tm_pm, Fpm, (uint64_t)(1 + g.split) * B * g.Npad, (uint64_t)g.Kc))) return rc;
@@ -1234,6 +1959,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     a.grad_scale = (float)(2.0 / Z);
     a.direct = need_grad && go && dx1 && dx2 && k == 1;
     a.dx[0] = dx1; a.dx[1] = dx2; a.go = go;
+    a.tau = rex.tau; a.fcnt = const_cast<unsigned *>(rex.fcnt); a.fent = const_cast<unsigned *>(rex.fent);
     if (fused_out) *fused_out = a.direct;
     const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
     if (need_grad && g.pair && (!g.half || g.half_pair)) {
@@ -1241,7 +1967,13 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
         const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];
         if (same) {
             CUtensorMap tm_k, tm_v;
-            if (g.half) {
+            if (g.quad) {
+                if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
+                if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
+                if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
+                if ((rc = opt_in_smem(fa_pos_tiles_quad, g.quad_smem_bytes))) return rc;
+                fa_pos_tiles_quad<<<dim3(2 * g.tiles * g.jsplit, 1, B), kQuadThreads, g.quad_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
+            } else if (g.half) {
                 if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
                 if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
                 if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
@@ -1260,11 +1992,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
 #undef LAUNCH_PAIR
             }
             DSRL_LAUNCH_CHECK();
-            if (g.jsplit > 1) {
-                if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-                fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
-                DSRL_LAUNCH_CHECK();
-            }
+            if (g.raw_o && (rc = finish(a))) return rc;
             return DSRL_OK;
         }
     }
@@ -1284,11 +2012,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
             fa_pos_tiles<false, false, true, true><<<grid, kThreads, g.half1_smem_bytes, st>>>(tm_pm, tm_cm, g, a);
         }
         DSRL_LAUNCH_CHECK();
-        if (need_grad && g.jsplit > 1) {
-            if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-            fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
-            DSRL_LAUNCH_CHECK();
-        }
+        if (need_grad && g.raw_o && (rc = finish(a))) return rc;
         return DSRL_OK;
     }
     const int variant = (need_grad ? 4 : 0) | (g.split ? 2 : 0) | (g.q_resident ? 1 : 0);
@@ -1304,11 +2028,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     }
 #undef LAUNCH_TILES
     DSRL_LAUNCH_CHECK();
-    if (need_grad && g.jsplit > 1) {
-        if ((rc = opt_in_smem(fa_pos_jacobian, pack_smem))) return rc;
-        fa_pos_jacobian<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
-    }
-    DSRL_LAUNCH_CHECK();
+    if (need_grad && g.raw_o && (rc = finish(a))) return rc;
     return DSRL_OK;
 }
 
@@ -1330,9 +2050,8 @@ int fa_pos_forward_backward(int precision, const float *x1, const float *x2, int
 
 int fa_pos_backward(int precision, const float *, const float *, const void *saved_v, size_t saved_bytes, const float *grad_out,
                     float *dx1, float *dx2, int B, int C1, int C2, int H, int W, int k, int, void *, size_t, cudaStream_t st) {
-    (void)precision;
     PosGeom g;
-    if (!make_geom(B, C1, C2, H, W, k, 0, g)) DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry");
+    if (!geom_for(precision, B, C1, C2, H, W, k, g)) DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(position): unsupported geometry");
     const PosSaved so = make_saved(g);
     if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(position): saved blob too small");
     const float *dP = reinterpret_cast<const float *>(static_cast<const unsigned char *>(saved_v) + so.dP);

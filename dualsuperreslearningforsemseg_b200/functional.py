@@ -19,22 +19,24 @@ _PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "
 
 class FAPlan:
     def __init__(self, shape1, shape2=None, subsample_factor=8, reduction="mean", affinity="reference", precision=None,
-                 device=None):
+                 device=None, exact_signs=False):
         shape2 = tuple(shape2 or shape1)
         self.B, self.C1, self.H, self.W = (int(v) for v in shape1)
         self.C2 = int(shape2[1])
         self.k = int(subsample_factor)
         self.mode, self.red, self.prec = _MODE[affinity], _RED[reduction], _PREC[precision]
+        if exact_signs and affinity == "position":
+            self.prec |= _lib.PREC_EXACT_SIGNS
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
         L = _lib.lib()
-        geom = (self.mode, self.B, self.C1, self.C2, self.H, self.W, self.k)
+        geom = (self.mode, self.prec, self.B, self.C1, self.C2, self.H, self.W, self.k)
         self.saved_bytes = int(L.dsrl_fa_saved_bytes(*geom))
         self.ws_bytes = int(L.dsrl_fa_workspace_bytes(*geom))
         if self.saved_bytes == 0:
             raise _lib.DsrlError(_lib.ERR_UNSUPPORTED, f"FAPlan: unsupported geometry {geom}")
         self.saved = torch.empty(self.saved_bytes, dtype=torch.uint8, device=dev)
-        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
         if self.red == _lib.REDUCE_NONE:
             n = (self.W // self.k) ** 2
             self.loss = torch.empty((self.B, self.C1, n * n), dtype=torch.float32, device=dev)
@@ -43,6 +45,13 @@ class FAPlan:
         self.dx1 = torch.empty((self.B, self.C1, self.H, self.W), dtype=torch.float32, device=dev)
         self.dx2 = torch.empty((self.B, self.C2, self.H, self.W), dtype=torch.float32, device=dev)
         self._p = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def sign_stats(self):
+        """exact_signs: {'listed', 'corrected', 'dropped', 'worst_ratio'} of the last forward that produced gradients (synchronises)."""
+        out = (ctypes.c_uint64 * 4)()
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(_lib.lib().dsrl_fa_sign_stats(self._p(self.saved), out, st))
+        return {"listed": int(out[0]), "corrected": int(out[1]), "dropped": int(out[2]), "worst_ratio": out[3] * 1e-6}
 
     def forward(self, x1, x2, need_grad=True):
         st = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -100,7 +109,7 @@ class FAHostPipeline:
     w.r.t. both inputs -- the same values ``FALoss`` + ``backward()`` give on the whole batch."""
 
     def __init__(self, shape1, shape2=None, subsample_factor=8, reduction="mean", affinity="reference", precision=None,
-                 chunk=2, ramp=True, device=None):
+                 chunk=2, ramp=True, device=None, exact_signs=False):
         if reduction not in ("mean", "sum"):
             raise ValueError("FAHostPipeline: reduction must be 'mean' or 'sum'")
         shape2 = tuple(shape2 or shape1)
@@ -114,7 +123,7 @@ class FAHostPipeline:
             n = hi - lo
             if n not in self.plans:
                 self.plans[n] = FAPlan((n,) + tuple(shape1[1:]), (n,) + tuple(shape2[1:]), subsample_factor, reduction,
-                                       affinity, precision, dev)
+                                       affinity, precision, dev, exact_signs)
         self.x1 = torch.empty(tuple(shape1), dtype=torch.float32, device=dev)
         self.x2 = torch.empty(tuple(shape2), dtype=torch.float32, device=dev)
         self.dx1 = torch.empty_like(self.x1)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DSRL_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define DSRL_B200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 typedef void *dsrl_stream_t; /* cudaStream_t */
 
@@ -51,8 +51,14 @@ enum dsrl_precision {
     DSRL_PREC_FP32 = 0,   /* reference mode: CUDA-core FP32 FMA (always); position mode: 3xTF32 split on tcgen05 */
     DSRL_PREC_TF32 = 1,   /* position mode default: one tcgen05 kind::tf32 pass, FP32 accumulate in TMEM */
     DSRL_PREC_BF16 = 2,   /* reserved: rejected with DSRL_ERR_UNSUPPORTED (a single BF16 pass misses the loss tolerance) */
-    DSRL_PREC_F16 = 3     /* position mode: FP16 operands (the 11-bit significand of TF32; unit-norm features need no more
+    DSRL_PREC_F16 = 3,    /* position mode: FP16 operands (the 11-bit significand of TF32; unit-norm features need no more
                              exponent range), tcgen05 kind::f16 at twice the TF32 rate, FP32 accumulate */
+    /* Flag, OR-ed onto one of the three position-mode precisions above.  The gradient of the position loss is a sum of
+     * sign(S1 - S2) terms; tensor-core operand rounding flips the sign of the ~1e-4 of the entries that lie within its error of
+     * zero (0.5-1 % relative-norm on the gradient for densely distributed inputs).  With this flag every entry whose
+     * tensor-core value is below ~3.5 sigma of that error is re-decided in FP64 from the unrounded features (a second,
+     * HBM/L2-bound kernel over ~1e-3 of the entries), and the gradient is the one the exact signs give. */
+    DSRL_PREC_EXACT_SIGNS = 16
 };
 
 enum dsrl_dtype { DSRL_U8 = 0, DSRL_I32 = 1, DSRL_I64 = 2 };
@@ -67,10 +73,18 @@ uint64_t dsrl_launch_count(void);
 /* ---- FA loss (replaces FALoss.forward, FALoss.py:18-34, and its autograd backward) --------------------- */
 
 /* Bytes of the opaque `saved` blob forward() fills and backward() consumes, and of the scratch workspace
- * both need.  C2 is only meaningful in position mode (reference mode requires C1 == C2, FALoss.py:20).
+ * forward needs (backward needs none except reference mode with DSRL_REDUCE_NONE).  `precision` as passed to the
+ * calls (it selects which operand copies the position-mode workspace holds; ignored in reference mode).  C2 is only
+ * meaningful in position mode (reference mode requires C1 == C2, FALoss.py:20).
  * Return 0 for an invalid / unsupported geometry. */
-size_t dsrl_fa_saved_bytes(int mode, int B, int C1, int C2, int H, int W, int k);
-size_t dsrl_fa_workspace_bytes(int mode, int B, int C1, int C2, int H, int W, int k);
+size_t dsrl_fa_saved_bytes(int mode, int precision, int B, int C1, int C2, int H, int W, int k);
+size_t dsrl_fa_workspace_bytes(int mode, int precision, int B, int C1, int C2, int H, int W, int k);
+
+/* Position mode with DSRL_PREC_EXACT_SIGNS: copies the statistics the last forward left in `saved` (device) to
+ * out[0..4) on the host: entries listed as near ties, signs corrected, ties dropped because a row's list was full (those
+ * keep the tensor-core sign), and 1e6 * the largest |D_exact| / threshold among the corrected entries (well below 1e6 when
+ * the threshold is wide enough).  Synchronises `stream`. */
+int dsrl_fa_sign_stats(const void *saved, uint64_t *out, dsrl_stream_t stream);
 
 /* Forward.  x1: (B, C1, H, W), x2: (B, C2, H, W) fp32.  k = subsample_factor (FALoss.py:14,23-24).
  * `workspace` and `saved` must be 16-byte aligned; position mode may launch a cluster kernel (CTA pairs).
@@ -83,7 +97,8 @@ int dsrl_fa_forward(int mode, int precision, const float *x1, const float *x2, i
                     size_t saved_bytes, void *workspace, size_t workspace_bytes, dsrl_stream_t stream);
 
 /* Backward.  grad_out: device pointer -- 1 float (mean/sum) or (B, C, n*n) floats (none).
- * dx1 / dx2: (B, C, H, W) fp32 outputs, either may be NULL (input does not require grad). */
+ * dx1 / dx2: (B, C, H, W) fp32 outputs, either may be NULL (input does not require grad).
+ * workspace may be NULL except in reference mode with DSRL_REDUCE_NONE; x1 / x2 are not read in position mode. */
 int dsrl_fa_backward(int mode, int precision, const float *x1, const float *x2, const void *saved,
                      size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C1, int C2,
                      int H, int W, int k, int reduction, void *workspace, size_t workspace_bytes,
@@ -99,6 +114,12 @@ int dsrl_fa_forward_backward(int mode, int precision, const float *x1, const flo
                              int W, int k, int reduction, const float *grad_out, float *loss_out, float *dx1,
                              float *dx2, void *saved, size_t saved_bytes, void *workspace, size_t workspace_bytes,
                              dsrl_stream_t stream);
+
+/* In-place `d1[i] *= *grad_out`, `d2[i] *= *grad_out` (either pointer may be NULL); returns at once on the device when
+ * *grad_out == 1.  Lets an autograd wrapper run dsrl_fa_forward_backward with a unit upstream gradient in its forward (one
+ * pass, no `saved` gradient round trip) and apply the real upstream gradient -- `w2` of `w2 * FALoss()(..)`,
+ * train_or_resume.py:437 -- when backward() delivers it.  grad_out: 1 device float. */
+int dsrl_scale_grads(const float *grad_out, float *d1, int64_t n1, float *d2, int64_t n2, dsrl_stream_t stream);
 
 /* ---- segmentation counts (replaces the three np.histogram passes of mIoU.update, mIoU.py:21-29, and the
  *      two reductions of Accuracy.update, Accuracy.py:19-20) ---------------------------------------------- */

@@ -33,12 +33,12 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_size_queries(lib):
-    assert lib.dsrl_version() == 100
+    assert lib.dsrl_version() == 200
     # size queries are pure host arithmetic: valid geometry > 0, invalid geometry 0
-    assert lib.dsrl_fa_saved_bytes(0, 6, 1, 1, 64, 128, 8) > 0
-    assert lib.dsrl_fa_workspace_bytes(0, 6, 1, 1, 64, 128, 8) > 0
-    assert lib.dsrl_fa_saved_bytes(0, 6, 1, 2, 64, 128, 8) == 0      # reference mode needs equal shapes
-    assert lib.dsrl_fa_saved_bytes(0, 1, 1, 1, 4, 4, 8) == 0         # smaller than the pooling window
+    assert lib.dsrl_fa_saved_bytes(0, 0, 6, 1, 1, 64, 128, 8) > 0
+    assert lib.dsrl_fa_workspace_bytes(0, 0, 6, 1, 1, 64, 128, 8) > 0
+    assert lib.dsrl_fa_saved_bytes(0, 0, 6, 1, 2, 64, 128, 8) == 0      # reference mode needs equal shapes
+    assert lib.dsrl_fa_saved_bytes(0, 0, 1, 1, 1, 4, 4, 8) == 0         # smaller than the pooling window
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
