@@ -53,33 +53,51 @@ int device_sm_count() {
 }
 
 
+// Ticket words: kTicketSlots recycled round robin by eager launches (a word is back to 0 when its kernel ends, and 4096
+// launches later that kernel has long finished), followed by kCaptureSlots handed out ONCE each to launches recorded into a
+// CUDA graph -- a graph replays with the word it captured, so that word must never be given to anyone else.
 static std::mutex g_ticket_mu;
-static unsigned *g_ticket_pool[64] = {};
+static std::atomic<unsigned *> g_ticket_pool[64];
 static std::atomic<unsigned> g_ticket_next{0};
-constexpr unsigned kTicketSlots = 4096;
+static std::atomic<unsigned> g_capture_next[64];
+constexpr unsigned kTicketSlots = 4096, kCaptureSlots = 16384;
 
-unsigned *next_ticket_slot() {
+unsigned *next_ticket_slot(cudaStream_t st) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         set_last_error("next_ticket_slot: cudaGetDevice failed");
         return nullptr;
     }
-    if (!g_ticket_pool[dev]) {
+    unsigned *pool = g_ticket_pool[dev].load(std::memory_order_acquire);
+    if (!pool) {
         std::lock_guard<std::mutex> lk(g_ticket_mu);
-        if (!g_ticket_pool[dev]) {
+        pool = g_ticket_pool[dev].load(std::memory_order_acquire);
+        if (!pool) {
             unsigned *p = nullptr;
-            cudaError_t e = cudaMalloc(&p, kTicketSlots * sizeof(unsigned));
-            if (e == cudaSuccess) e = cudaMemset(p, 0, kTicketSlots * sizeof(unsigned));
+            cudaError_t e = cudaMalloc(&p, (kTicketSlots + kCaptureSlots) * sizeof(unsigned));
+            if (e == cudaSuccess) e = cudaMemset(p, 0, (kTicketSlots + kCaptureSlots) * sizeof(unsigned));
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();      // the memset is ordered before a first launch on ANY stream
             if (e != cudaSuccess) {
                 set_last_error("ticket pool allocation failed (%s); if this happened inside a CUDA graph capture, run the "
                                "call once eagerly first", cudaGetErrorString(e));
                 (void)cudaGetLastError();
                 return nullptr;
             }
-            g_ticket_pool[dev] = p;
+            g_ticket_pool[dev].store(p, std::memory_order_release);
+            pool = p;
         }
     }
-    return g_ticket_pool[dev] + (g_ticket_next.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    if (cap == cudaStreamCaptureStatusActive) {
+        const unsigned i = g_capture_next[dev].fetch_add(1, std::memory_order_relaxed);
+        if (i >= kCaptureSlots) {
+            set_last_error("more than %u kernel launches with a ticket word have been captured into CUDA graphs on device %d", kCaptureSlots, dev);
+            return nullptr;
+        }
+        return pool + kTicketSlots + i;
+    }
+    return pool + (g_ticket_next.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
 }
 
 }  // namespace dsrl

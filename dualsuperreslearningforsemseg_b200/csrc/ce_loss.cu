@@ -18,6 +18,7 @@ constexpr int kCeThreads = 256;
 struct CeHeader {            // first bytes of the saved blob
     double sum;              // sum of the per-pixel losses over valid pixels
     long long valid;         // number of valid pixels
+    long long bad;           // targets that are neither ignore_index nor a class index: the loss is NaN when there is one
 };
 struct CePartial { double sum; long long valid; };
 
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
     // persistent CTAs: tile = (image, strip of kCeThreads * VEC pixels); one block-level reduction per CTA at the end
     const long long strips = (HW + (long long)kCeThreads * VEC - 1) / ((long long)kCeThreads * VEC), tiles = strips * nimg;
     float lsum = 0.f;
-    int lcnt = 0;
+    int lcnt = 0, lbad = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int b = (int)(tile / strips);
         const long long p0 = ((tile - (long long)b * strips) * kCeThreads + threadIdx.x) * VEC;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
             m[v] = -3.402823466e38f; s[v] = 0.f; xt[v] = 0.f;
             const long long tl = (p0 + v < HW) ? ce_load_target(target, (long long)b * HW + p0 + v) : ignore_index;
             t[v] = (tl != ignore_index && tl >= 0 && tl < C) ? (int)tl : -1;          // -1: ignored
+            lbad += (tl != ignore_index && (tl < 0 || tl >= C)) ? 1 : 0;              // a label-mapping bug: torch asserts here
         }
         // kCeChunk channels per round: all their loads are issued before any arithmetic, then one branch-free online-softmax
         // update per pixel (chunk sizes 4..20 measured within 10 % of each other at the training shape; 5 was the fastest)
@@ -123,7 +125,8 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
         }
     }
     const double bsum = block_sum<double>((double)lsum, s_sum);
-    const long long bcnt = block_sum<long long>((long long)lcnt, s_cnt);
+    // valid and bad counts travel in one word (pixel counts stay far below 2^40)
+    const long long bcnt = block_sum<long long>((long long)lcnt + ((long long)lbad << 40), s_cnt);
     CePartial *parts = reinterpret_cast<CePartial *>(saved + kCePartialsOff);
     const unsigned nblk = gridDim.x, blk = blockIdx.x;
     if (threadIdx.x == 0) {
@@ -142,9 +145,15 @@ __global__ void __launch_bounds__(kCeThreads) ce_forward_kernel(const float *__r
     tc = block_sum<long long>(tc, s_cnt);
     if (threadIdx.x == 0) {
         CeHeader *h = reinterpret_cast<CeHeader *>(saved);
+        const long long bad = tc >> 40;
+        tc &= (1ll << 40) - 1;
         h->sum = ts;
         h->valid = tc;
-        *loss_out = mean ? (float)(ts / (double)tc) : (float)ts;    // no valid pixel: 0/0 = NaN, like torch
+        h->bad = bad;
+        // no valid pixel: 0/0 = NaN, like torch.  A target outside [0, C) that is not ignore_index is a device assert in torch;
+        // here the loss is NaN (the backward kernel still treats those pixels as ignored), which the reference's own NaN checks
+        // (train_or_resume.py:406-411) turn into a stop
+        *loss_out = bad ? __int_as_float(0x7fc00000) : (mean ? (float)(ts / (double)tc) : (float)ts);
     }
 }
 
@@ -262,7 +271,7 @@ extern "C" int dsrl_ce_forward(const float *logits, const void *target, int targ
     const bool vec = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
     const int per_block = kCeThreads * (vec ? 4 : 1);
     const dim3 grid((unsigned)((HW + per_block - 1) / per_block), (unsigned)B);
-    unsigned *ticket = next_ticket_slot();
+    unsigned *ticket = next_ticket_slot(st);
     if (!ticket) return DSRL_ERR_CUDA;
     const size_t lse_off = ce_lse_off(B, HW);
     unsigned char *sv = static_cast<unsigned char *>(saved);

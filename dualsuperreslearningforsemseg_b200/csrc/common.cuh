@@ -38,10 +38,11 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     } while (0)
 
 int device_sm_count();          // cached
-// A zero-initialised device word from a per-device pool (round robin over 4096 slots) for kernels that elect their
-// last CTA with a self-resetting atomicInc.  Returns nullptr (and sets the error) on failure.  The pool is allocated on
+// A zero-initialised device word from a per-device pool for kernels that elect their last CTA with a self-resetting
+// atomicInc: round robin over 4096 words for eager launches, a word of its own (never handed out again) for a launch that
+// `st` is capturing into a CUDA graph.  Returns nullptr (and sets the error) on failure.  The pool is allocated on
 // first use, which must not happen inside a stream capture: run one eager call before capturing a CUDA graph.
-unsigned *next_ticket_slot();
+unsigned *next_ticket_slot(cudaStream_t st);
 int require_device();           // DSRL_OK or DSRL_ERR_CUDA (no device / wrong arch): there is no CPU fallback
 
 // ---- device helpers ---------------------------------------------------------------------------------------

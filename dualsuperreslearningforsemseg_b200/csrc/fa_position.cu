@@ -54,6 +54,9 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 256;     // first column of the two D / sign tiles
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kSmemAux = 1536;   // barriers, TMEM pointer, reduction scratch, projection halves
+// every tile kernel allocates all 512 tensor-memory columns, so two of its CTAs must never share an SM (the second would
+// spin in tcgen05.alloc; with CTA pairs that can deadlock): each requests more than half of an SM's shared memory
+constexpr size_t kOneCtaSmem = 116 * 1024;
 constexpr int kXchgBytes = 2 * 2 * 128 * 16;   // fa_pos_tiles_quad: two slots x (two column halves x 128 rows x 16 bytes of sign / zero bits)
 
 struct PosGeom {
@@ -105,6 +108,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     g.stages = (avail - (g.q_resident ? qboxes : 0)) / sb;
     if (g.stages > 6) g.stages = 6;
     g.smem_bytes = 1024 + (size_t)(g.q_resident ? qboxes : 0) * kBoxBytes + (size_t)g.stages * sb * kBoxBytes + kSmemAux;
+    if (g.smem_bytes < kOneCtaSmem) g.smem_bytes = kOneCtaSmem;
     // Wave quantisation: every CTA of the gradient variant does the same work (all column tiles of one row tile), and
     // only one CTA fits per SM, so a grid of e.g. 512 CTAs takes ceil(512/148) = 4 rounds instead of 3.46.  Splitting
     // the column range over `jsplit` CTAs (partial accumulators summed by fa_pos_jacobian) makes the rounds shorter.
@@ -126,6 +130,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         if (g.pair_stages > 6) g.pair_stages = 6;
         if (const char *e = getenv("DSRL_POS_STAGES")) { const int v = atoi(e); if (v >= 2 && v < g.pair_stages) g.pair_stages = v; }   // tuning hook
         g.pair_smem_bytes = 1024 + qbytes + (size_t)g.pair_stages * stage + kSmemAux;
+        if (g.pair_smem_bytes < kOneCtaSmem) g.pair_smem_bytes = kOneCtaSmem;
     }
     // FP16 operands: 64 channels per 128-byte row, so the CTA's own rows (<= 8 boxes) are always resident
     g.nkh = (g.Kc + 63) / 64;
@@ -135,6 +140,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         g.half1_stages = (avail - g.nkh) / 2;
         if (g.half1_stages > 6) g.half1_stages = 6;
         g.half1_smem_bytes = 1024 + (size_t)g.nkh * kBoxBytes + (size_t)g.half1_stages * 2 * kBoxBytes + kSmemAux;
+        if (g.half1_smem_bytes < kOneCtaSmem) g.half1_smem_bytes = kOneCtaSmem;
     }
     {
         const size_t qbytes = (size_t)g.nkh * kBoxBytes;
@@ -142,6 +148,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         if (g.half_stages > 6) g.half_stages = 6;
         if (const char *e = getenv("DSRL_POS_STAGES")) { const int v = atoi(e); if (v >= 2 && v < g.half_stages) g.half_stages = v; }
         g.half_smem_bytes = 1024 + qbytes + (size_t)g.half_stages * 2 * kBoxBytes + kSmemAux;
+        if (g.half_smem_bytes < kOneCtaSmem) g.half_smem_bytes = kOneCtaSmem;
         if (g.half_stages < 2) g.half_pair = 0;
     }
     if (const char *force = getenv("DSRL_POS_JSPLIT")) {          // test hook: force 1, 2 or 4 (when it divides the tile count)
@@ -157,6 +164,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         g.quad_stages = room > 0 ? (int)(room / kBoxBytes) : 0;
         if (g.quad_stages > 8) g.quad_stages = 8;
         g.quad_smem_bytes = 1024 + qbytes + (size_t)g.quad_stages * kBoxBytes + kXchgBytes + kSmemAux;
+        if (g.quad_smem_bytes < kOneCtaSmem) g.quad_smem_bytes = kOneCtaSmem;
         g.quad = g.half_pair && g.G == 2 && g.gcnt[0] == g.gcnt[1] && (g.tiles / g.jsplit) % 2 == 0 && g.quad_stages >= 3;
         if (const char *e = getenv("DSRL_POS_QUAD")) { if (atoi(e) == 0) g.quad = 0; }
     }
@@ -1580,8 +1588,10 @@ constexpr float kSafe32 = 3.0e-6f;
 
 __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
     constexpr int kU = 4;                         // a lane holds channels 4*lane + 128*u .. +3, u < 4 (Kc <= 512)
-    constexpr int kR = 2;                         // entries per round: 8 independent 16-byte loads in flight per lane
+    constexpr int kR = 4;                         // entries per round: 16 independent 16-byte loads in flight per lane (the pass
+                                                  // is latency x bandwidth bound: 16 warps x 4 rows x 2 KB in flight per SM)
     constexpr float kFix = 1073741824.f;          // 2^30
+    __shared__ long long s_corr[8][4 * kU][32];   // per warp: fixed-point correction of the lane's 16 channels (few entries flip)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long grow_ll = (long long)blockIdx.x * 8 + warp;
     if (grow_ll >= (long long)g.B * g.Npad) return;
@@ -1606,9 +1616,8 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
         pi[u] = c < g.Kc ? __ldg(reinterpret_cast<const float4 *>(ex.Ppm + grow * g.Kc + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const double i1 = inv1[irow], i2 = inv2[irow];
-    long long corr[4 * kU];
 #pragma unroll
-    for (int t = 0; t < 4 * kU; ++t) corr[t] = 0;
+    for (int t = 0; t < 4 * kU; ++t) s_corr[warp][t][lane] = 0;
     unsigned n_fix = 0;
     float worst = 0.f;
     const unsigned *ent = ex.fent + grow * g.fcap;
@@ -1678,10 +1687,10 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
                         const float w = 4 * lane + 128 * u < g.C1p ? f1 : f2;
-                        corr[4 * u + 0] += dl * (long long)__float2int_rn(pj[h][u].x * w);
-                        corr[4 * u + 1] += dl * (long long)__float2int_rn(pj[h][u].y * w);
-                        corr[4 * u + 2] += dl * (long long)__float2int_rn(pj[h][u].z * w);
-                        corr[4 * u + 3] += dl * (long long)__float2int_rn(pj[h][u].w * w);
+                        s_corr[warp][4 * u + 0][lane] += dl * (long long)__float2int_rn(pj[h][u].x * w);
+                        s_corr[warp][4 * u + 1][lane] += dl * (long long)__float2int_rn(pj[h][u].y * w);
+                        s_corr[warp][4 * u + 2][lane] += dl * (long long)__float2int_rn(pj[h][u].z * w);
+                        s_corr[warp][4 * u + 3][lane] += dl * (long long)__float2int_rn(pj[h][u].w * w);
                     }
                 }
             }
@@ -1694,8 +1703,8 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
             const int c = 4 * lane + 128 * u;
             if (c < g.Kc) {
                 float4 o = *reinterpret_cast<float4 *>(orow + c);
-                o.x += (float)corr[4 * u + 0] * (1.f / kFix); o.y += (float)corr[4 * u + 1] * (1.f / kFix);
-                o.z += (float)corr[4 * u + 2] * (1.f / kFix); o.w += (float)corr[4 * u + 3] * (1.f / kFix);
+                o.x += (float)s_corr[warp][4 * u + 0][lane] * (1.f / kFix); o.y += (float)s_corr[warp][4 * u + 1][lane] * (1.f / kFix);
+                o.z += (float)s_corr[warp][4 * u + 2][lane] * (1.f / kFix); o.w += (float)s_corr[warp][4 * u + 3][lane] * (1.f / kFix);
                 *reinterpret_cast<float4 *>(orow + c) = o;
             }
         }
@@ -1712,40 +1721,91 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
 // finish: sum the partial accumulators (jsplit shares), apply the normalisation Jacobian, store dP channel-major (or dX
 // itself: fused forward + backward without pooling)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fa_pos_finish(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
+__global__ void __launch_bounds__(256, 2) fa_pos_finish(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
                                                     const __half *__restrict__ FcmH, const float *__restrict__ nrm, float grad_scale,
                                                     float *__restrict__ dP, float *dx1, float *dx2, const float *go) {
-    auto feat = [&](size_t o) { return Fcm ? Fcm[o] : __half2float(FcmH[o]); };      // FP16 form: only the FP16 copy exists
     extern __shared__ float T[];                     // [Kc][33] summed accumulator of a 32-position strip
-    __shared__ float s_proj[2][32];
+    __shared__ float s_part[2][8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, p0 = blockIdx.x * 32;
-    for (int q = warp; q < 32; q += 8) {              // position-major rows in, fixed summation order over the shares
-        for (int c = lane; c < g.Kc; c += 32) {
-            float s = 0.f;
-            for (int js = 0; js < g.jsplit; ++js) s += opart[(((size_t)js * g.B + b) * g.Npad + p0 + q) * g.Kc + c];
-            T[c * 33 + q] = s;
+    // position-major rows in: a warp takes four rows, two at a time, 16-byte loads, all eight of a column share in flight at
+    // once (a loop of dependent 4-byte loads ran this kernel at 0.6 TB/s); fixed summation order over the shares
+#pragma unroll 1
+    for (int i0 = 0; i0 < 4; i0 += 2) {
+        float4 acc4[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc4[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int js = 0; js < g.jsplit; ++js) {
+            float4 v[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float *row = opart + (((size_t)js * g.B + b) * g.Npad + p0 + warp + 8 * (i0 + i)) * g.Kc;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = 4 * lane + 128 * u;
+                    v[i][u] = c < g.Kc ? __ldcs(reinterpret_cast<const float4 *>(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc4[i][u].x += v[i][u].x; acc4[i][u].y += v[i][u].y; acc4[i][u].z += v[i][u].z; acc4[i][u].w += v[i][u].w;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = 4 * lane + 128 * u, q = warp + 8 * (i0 + i);
+                if (c < g.Kc) {
+                    T[(c + 0) * 33 + q] = acc4[i][u].x; T[(c + 1) * 33 + q] = acc4[i][u].y;
+                    T[(c + 2) * 33 + q] = acc4[i][u].z; T[(c + 3) * 33 + q] = acc4[i][u].w;
+                }
+            }
+    }
+    __syncthreads();
+    // thread (warp, lane) owns position p0 + lane of the channels warp, warp + 8, ...: its normalised features stay in
+    // registers between the projection <Fh_i, O_i> (partial sums per warp, combined in a fixed order) and the output
+    constexpr int kMaxPer = 2 * kMaxGroupCh / 8;      // 64 channels per thread at most
+    float fr[kMaxPer];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPer; ++k) {
+        const int c = warp + 8 * k;
+        fr[k] = 0.f;
+        if (c < g.Kc) {
+            const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
+            fr[k] = Fcm ? Fcm[o] : __half2float(FcmH[o]);      // FP16 form: only the FP16 copy exists
+            if (c < g.C1p) p1 = fmaf(fr[k], T[c * 33 + lane], p1); else p2 = fmaf(fr[k], T[c * 33 + lane], p2);
         }
     }
+    s_part[0][warp][lane] = p1;
+    s_part[1][warp][lane] = p2;
     __syncthreads();
-    if (warp < 2) {                                   // proj = <Fh_i, O_i> over the channels of branch `warp`
-        const int c0 = warp ? g.C1p : 0, c1 = warp ? g.Kc : g.C1p;
-        float s = 0.f;
-        for (int c = c0; c < c1; ++c) s = fmaf(feat(((size_t)b * g.Kc + c) * g.Npad + p0 + lane), T[c * 33 + lane], s);
-        const float n = nrm[((size_t)b * 2 + warp) * g.Npad + p0 + lane];
-        s_proj[warp][lane] = n > 1e-12f ? s : 0.f;    // F/eps branch of the clamp: no projection
-    }
-    __syncthreads();
-    for (int c = warp; c < g.Kc; c += 8) {
-        const int br = c >= g.C1p;
+    float proj[2], scale[2];
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+        float sp = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sp += s_part[br][w][lane];
         const float n = nrm[((size_t)b * 2 + br) * g.Npad + p0 + lane];
-        const float scale = (br ? -grad_scale : grad_scale) / fmaxf(n, 1e-12f);
-        const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
-        const float val = (T[c * 33 + lane] - feat(o) * s_proj[br][lane]) * scale;
-        if (!go) { dP[o] = val; continue; }
+        proj[br] = n > 1e-12f ? sp : 0.f;             // F/eps branch of the clamp: no projection
+        scale[br] = (br ? -grad_scale : grad_scale) / fmaxf(n, 1e-12f);
+    }
+    const float gmul = go ? __ldg(go) : 1.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPer; ++k) {
+        const int c = warp + 8 * k;
+        if (c >= g.Kc) continue;
+        const int br = c >= g.C1p;
+        const float val = (T[c * 33 + lane] - fr[k] * proj[br]) * scale[br];
+        if (!go) { dP[((size_t)b * g.Kc + c) * g.Npad + p0 + lane] = val; continue; }
         // fused forward + backward without pooling: dX itself, real channels and positions only
         const int cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
-        if (cc < Cr && p0 + lane < g.N) (br ? dx2 : dx1)[((size_t)b * Cr + cc) * g.N + p0 + lane] = val * __ldg(go);
+        if (cc < Cr && p0 + lane < g.N) __stcs((br ? dx2 : dx1) + ((size_t)b * Cr + cc) * g.N + p0 + lane, val * gmul);
     }
 }
 
@@ -1944,7 +2004,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     if ((rc = make_map(&tm_pm, Fpm, (uint64_t)(1 + g.split) * B * g.Npad, (uint64_t)g.Kc))) return rc;
     if ((rc = make_map(&tm_cm, Fcm, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad))) return rc;
 
-    unsigned *ticket = next_ticket_slot();
+    unsigned *ticket = next_ticket_slot(st);
     if (!ticket) return DSRL_ERR_CUDA;
     PosArgs a;
     a.Fpm = Fpm; a.FpmH = FpmH; a.nrm = nrm;

@@ -1197,7 +1197,7 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
     unsigned char *saved = static_cast<unsigned char *>(saved_v);
 
     if (reduction != DSRL_REDUCE_NONE && fused_ok(g)) {
-        unsigned *ticket = next_ticket_slot();
+        unsigned *ticket = next_ticket_slot(st);
         if (!ticket) return DSRL_ERR_CUDA;
         const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
         fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
@@ -1255,7 +1255,7 @@ int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int 
     RefSaved so = make_saved(g);
     if (saved_bytes < so.total) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(reference): saved blob too small (%zu < %zu)", saved_bytes, so.total);
     if (ws_bytes < fa_ref_workspace_bytes(B, C, H, W, k)) DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA(reference): workspace too small");
-    unsigned *ticket = next_ticket_slot();
+    unsigned *ticket = next_ticket_slot(st);
     if (!ticket) return DSRL_ERR_CUDA;
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
     fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket,

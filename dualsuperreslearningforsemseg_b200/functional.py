@@ -19,7 +19,7 @@ _PREC = {None: _lib.PREC_TF32, "fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "
 
 class FAPlan:
     def __init__(self, shape1, shape2=None, subsample_factor=8, reduction="mean", affinity="reference", precision=None,
-                 device=None, exact_signs=False):
+                 device=None, exact_signs=True):
         shape2 = tuple(shape2 or shape1)
         self.B, self.C1, self.H, self.W = (int(v) for v in shape1)
         self.C2 = int(shape2[1])
@@ -109,7 +109,7 @@ class FAHostPipeline:
     w.r.t. both inputs -- the same values ``FALoss`` + ``backward()`` give on the whole batch."""
 
     def __init__(self, shape1, shape2=None, subsample_factor=8, reduction="mean", affinity="reference", precision=None,
-                 chunk=2, ramp=True, device=None, exact_signs=False):
+                 chunk=2, ramp=True, device=None, exact_signs=True):
         if reduction not in ("mean", "sum"):
             raise ValueError("FAHostPipeline: reduction must be 'mean' or 'sum'")
         shape2 = tuple(shape2 or shape1)

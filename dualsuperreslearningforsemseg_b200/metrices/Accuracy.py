@@ -2,7 +2,8 @@
 
 Same API (``update(pred, target, valid_labels_mask)``, ``()`` -> percent, ``reset()``, ``accuracies``).  The two
 reductions of Accuracy.py:19-20 come out of the same K4 pass that serves ``mIoU`` (when both meters are fed the
-same arrays back to back, as at train_or_resume.py:480-481, the second one re-uses the first one's counts);
+same arrays back to back, as at train_or_resume.py:480-481 and benchmark.py:76-77, the second one re-uses the first
+one's pass whichever runs first: correct / valid do not depend on the number of classes, see _counts._SharedPass);
 the division and the mean are the reference's own float64 NumPy expressions (Accuracy.py:24,29).
 """
 import numpy as np
@@ -11,7 +12,9 @@ from . import _counts
 
 
 class Accuracy:
-    def __init__(self):
+    def __init__(self, num_classes: int = _counts.NC_DEFAULT):
+        # the reference's Accuracy() takes no argument; the class count only sets the row width of a pass this meter starts
+        self.num_classes = num_classes
         self.reset()
 
     def reset(self):
@@ -19,20 +22,19 @@ class Accuracy:
         self.mean_accuracy = 0.0
         self._accuracies = []
         self._pending = _counts.PendingRows()
-        self._nc = []
 
     def update(self, pred, target, valid_labels_mask):
         self.dirty = True
-        nc = _counts._last_nc
-        self._pending.add(_counts.counts_for_update(pred, target, valid_labels_mask, nc)[:, 3 * nc:3 * nc + 2])
+        rows, nc = _counts.counts_for_update(pred, target, valid_labels_mask, self.num_classes, any_nc=True)
+        self._pending.add(rows[:, 3 * nc:3 * nc + 2])
 
     def update_many(self, pred, target, valid_labels_mask):
         self.dirty = True
-        nc = _counts._last_nc
-        self._pending.add(_counts.counts_for_update(pred, target, valid_labels_mask, nc, updates_leading=True)[:, 3 * nc:3 * nc + 2])
+        rows, nc = _counts.counts_for_update(pred, target, valid_labels_mask, self.num_classes, updates_leading=True, any_nc=True)
+        self._pending.add(rows[:, 3 * nc:3 * nc + 2])
 
-    def sync(self, group=None, mode="sum"):
-        _counts.sync_rows(self._pending, group, mode)
+    def sync(self, group=None, mode="sum", offset=0, total=0):
+        _counts.sync_rows(self._pending, group, mode, offset, total)
 
     def _finish(self):
         if len(self._pending) == 0:

@@ -30,14 +30,13 @@ class mIoU:
 
     # -- updates ------------------------------------------------------------------------------------------
     def update(self, pred, target, valid_labels_mask):
-        _counts._last_nc = self.num_classes
         self.dirty = True
-        self._pending.add(_counts.counts_for_update(pred, target, valid_labels_mask, self.num_classes))
+        self._pending.add(_counts.counts_for_update(pred, target, valid_labels_mask, self.num_classes)[0])
 
     def update_many(self, pred, target, valid_labels_mask):
         """U updates in one launch: arrays shaped (U, B, H, W); equivalent to U consecutive ``update`` calls."""
         self.dirty = True
-        self._pending.add(_counts.counts_for_update(pred, target, valid_labels_mask, self.num_classes, updates_leading=True))
+        self._pending.add(_counts.counts_for_update(pred, target, valid_labels_mask, self.num_classes, updates_leading=True)[0])
 
     def update_from_logits(self, logits, target, valid_labels_mask=None, return_pred=False):
         """Fused ``argmax(logits, dim=1)`` + update (replaces benchmark.py:61-77's D2H + host argmax)."""
@@ -46,9 +45,10 @@ class mIoU:
         self._pending.add(rows)
         return pred
 
-    def sync(self, group=None, mode="sum"):
-        """All-reduce / all-gather the pending per-update rows across the process group (see _counts.sync_rows)."""
-        _counts.sync_rows(self._pending, group, mode)
+    def sync(self, group=None, mode="sum", offset=0, total=0):
+        """All-reduce / all-gather the pending per-update rows across the process group, once per validation pass (see
+        _counts.sync_rows: 'sum', 'place' -- this rank's updates start at global index ``offset`` of ``total`` -- or 'gather')."""
+        _counts.sync_rows(self._pending, group, mode, offset, total)
 
     # -- results ------------------------------------------------------------------------------------------
     def _finish(self):

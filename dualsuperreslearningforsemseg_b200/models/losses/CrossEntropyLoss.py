@@ -6,6 +6,7 @@ One pass over the (B,C,H,W) logits in forward and one in backward (``csrc/ce_los
 log_softmax + nll_loss pair and their two backward kernels.  ``target`` may stay the uint8 map the dataset delivers
 (the ``.long()`` copy is not needed) or be int32 / int64.  Only what the reference uses is supported: no class
 weights, no label smoothing, class-index targets, reduction 'mean' or 'sum'; anything else raises.  No CPU fallback.
+A target that is neither ``ignore_index`` nor a class index (torch: device assert) makes the loss NaN.
 """
 from __future__ import annotations
 
@@ -43,6 +44,7 @@ class _CEFunction(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         x, tg, saved = ctx.saved_tensors
         B, C, HW, ignore_index, reduction, saved_bytes = ctx.geom

@@ -150,8 +150,9 @@ int dsrl_seg_counts_from_logits(const float *logits, const void *target, int tar
  *      log_softmax + nll_loss forward and their two backward kernels, by one pass each) ----------------------- */
 
 /* logits: (B, C, HW) fp32 NCHW; target: (B, HW) of `target_dtype` (uint8 as the dataset delivers it, or the
- * int64 of `target.long()`).  Pixels whose target equals ignore_index -- or lies outside [0, C): torch raises a
- * device assert there, this library treats them as ignored -- contribute neither loss nor gradient.
+ * int64 of `target.long()`).  Pixels whose target equals ignore_index contribute neither loss nor gradient.  A target
+ * outside [0, C) that is not ignore_index (torch raises a device assert there) makes the loss NaN; its pixel gets no
+ * gradient.
  * reduction: DSRL_REDUCE_MEAN (sum / number of valid pixels; NaN when there is none, like torch) or DSRL_REDUCE_SUM.
  * saved: dsrl_ce_saved_bytes(B, HW) bytes, 16-byte aligned; holds the per-pixel log-sum-exp and the valid count
  * for dsrl_ce_backward, which writes dlogits = grad_out * dloss/dlogits (grad_out: 1 device float). */

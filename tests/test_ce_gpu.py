@@ -64,7 +64,7 @@ def test_ce_training_shape_vs_torch_cuda(tdt):
     assert float(l3) == float(l1) and torch.equal(a2.grad, a.grad)
 
 
-def test_ce_out_of_range_target_is_ignored_and_inf_logits():
+def test_ce_out_of_range_target_is_loud_and_inf_logits():
     from dualsuperreslearningforsemseg_b200.models.losses import CrossEntropyLoss
     x = torch.randn((1, 5, 4, 8), device="cuda")
     t = torch.randint(0, 5, (1, 4, 8), device="cuda")
@@ -72,7 +72,11 @@ def test_ce_out_of_range_target_is_ignored_and_inf_logits():
     t2 = t.clone(); t2[0, 0, 0] = 77                               # torch would raise a device assert here
     t3 = t.clone(); t3[0, 0, 0] = 255
     f = CrossEntropyLoss(ignore_index=255)
-    assert float(f(x, t2)) == float(f(x, t3))
+    bad = x.clone().requires_grad_(True)
+    lb = f(bad, t2)
+    lb.backward()
+    assert bool(torch.isnan(lb)) and bool(torch.isfinite(f(x, t3)))       # a label-mapping bug cannot train silently
+    assert float(bad.grad[0, :, 0, 0].abs().sum()) == 0.0                  # ... and that pixel gets no gradient
     x[0, 2, 1, 1] = float("-inf")                                  # a -inf logit is a zero-probability class
     a = x.clone().requires_grad_(True)
     l = f(a, t3); l.backward()

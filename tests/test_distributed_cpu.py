@@ -1,6 +1,6 @@
 """N>1 path on CPU: world_size-2 gloo.  The per-update integer rows of two ranks (each holding half of every
 update's batch) all-reduce to exactly the rows of the unsharded run, so mIoU/accuracy are bit-identical; the
-'gather' mode concatenates rank-major."""
+'gather' mode concatenates rank-major, the 'place' mode (one all-reduce per pass) returns the rows in global update order."""
 import os
 import socket
 import warnings
@@ -44,11 +44,20 @@ def _worker(rank, world, port, q):
     for seed in (21, 22, 23, 24, 25):     # 'gather' mode: whole updates live on different ranks (3 on one, 2 on the other)
         if seed % world == rank:
             mg._pending.add(_row(*seg_case("plain", seed, (4, 33, 47), nc), nc)); mg.dirty = True
+    # 'place' mode: the ranks know where their updates sit in the pass (rank 0: updates 0-2, rank 1: updates 3-4) -> one
+    # all-reduce of the [5, row] table, rows in global order on both ranks; run twice (the table is kept between passes)
+    mp_ = mIoU(nc)
+    for _ in range(2):
+        mp_.reset()
+        seeds = (21, 22, 23) if rank == 0 else (24, 25)
+        for seed in seeds:
+            mp_._pending.add(_row(*seg_case("plain", seed, (4, 33, 47), nc), nc)); mp_.dirty = True
+        mp_.sync(mode="place", offset=0 if rank == 0 else 3, total=5)
     m.sync(mode="sum"); a.sync(mode="sum"); mg.sync(mode="gather")
     loss = D.all_reduce_mean_loss(torch.tensor(float(rank + 1)))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
-        q.put((rank, m(), a(), list(m.ious), sorted(mg.ious), float(loss)))
+        q.put((rank, m(), a(), list(m.ious), sorted(mg.ious), float(loss), list(mp_.ious)))
     dist.destroy_process_group()
 
 
@@ -73,7 +82,8 @@ def test_two_rank_metric_sync_is_bit_exact():
     mg = seg_oracle.MIoUOracle(nc)
     for seed in (21, 22, 23, 24, 25):
         mg.update(*seg_case("plain", seed, (4, 33, 47), nc))
-    for rank, miou, acc, ious, gious, loss in res:
+    for rank, miou, acc, ious, gious, loss, pious in res:
         assert miou == m() and acc == a() and ious == m.ious
         assert gious == sorted(mg.ious)
+        assert pious == mg.ious                       # global update order, not rank-major
         assert loss == 1.5

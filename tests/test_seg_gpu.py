@@ -53,8 +53,8 @@ def test_sequences_bit_exact_vs_reference_golden(name, nc, seq, as_cuda):
 
 def raw_counts(pred, target, mask, nc, **kw):
     from dualsuperreslearningforsemseg_b200.metrices import _counts
-    _counts._cache.update(key=None)
-    rows = _counts.counts_for_update(pred, target, mask, nc, **kw)
+    _counts.clear_shared_pass()
+    rows, _ = _counts.counts_for_update(pred, target, mask, nc, **kw)
     return rows.cpu().numpy()
 
 
@@ -161,3 +161,127 @@ def test_logits_many_updates_one_launch():
         pred = seg_oracle.argmax_first(logits[u])
         ap, ai, at, c, v = seg_oracle.seg_counts(pred, target[u], target[u] != 255, nc)
         assert np.array_equal(rows[u], np.concatenate([ap, ai, at, [c, v]]))
+
+
+@pytest.mark.parametrize("as_cuda", [False, True], ids=["numpy_in", "cuda_in"])
+def test_the_meter_pair_shares_one_pass(as_cuda):
+    """The reference feeds the same arrays to both meters back to back, in either order (train_or_resume.py:480-481,
+    benchmark.py:76-77): the second meter re-uses the first one's kernel pass -- one launch per batch, also for NumPy inputs
+    (one host -> device copy) and whatever the number of classes, without any state shared between threads or instances."""
+    from dualsuperreslearningforsemseg_b200 import _lib
+    from dualsuperreslearningforsemseg_b200.metrices import _counts
+    mIoU, Accuracy = metrics()
+    probe = seg_case("plain", 20, (1, 8, 8), 19)
+    n0 = _lib.launch_count()
+    mIoU(19).update(*probe)
+    one_pass = _lib.launch_count() - n0              # launches (kernel + memset node) of ONE counting pass
+    assert one_pass >= 1
+    for nc, acc_first in ((19, True), (19, False), (6, False)):
+        pred, target, mask = seg_case("plain", 21, (2, 37, 53), nc)
+        if as_cuda:
+            pred_in, target_in, mask_in = (torch.from_numpy(v).cuda() for v in (pred, target, mask))
+        else:
+            pred_in, target_in, mask_in = pred, target, mask
+        _counts.clear_shared_pass()
+        m, a = mIoU(nc), Accuracy()
+        n0 = _lib.launch_count()
+        for meter in ((a, m) if acc_first else (m, a)):
+            meter.update(pred_in, target_in, mask_in)
+        assert _lib.launch_count() - n0 == one_pass, (nc, acc_first)
+        mo, ao = seg_oracle.MIoUOracle(nc), seg_oracle.AccuracyOracle()
+        mo.update(pred, target, mask); ao.update(pred, target, mask)
+        assert bits(m()) == bits(mo()) and bits(a()) == bits(ao())
+    # Accuracy first with another class count than the mIoU that follows: two passes, both right
+    pred, target, mask = seg_case("plain", 22, (2, 37, 53), 6)
+    _counts.clear_shared_pass()
+    m, a = mIoU(6), Accuracy()
+    n0 = _lib.launch_count()
+    a.update(pred, target, mask); m.update(pred, target, mask)
+    assert _lib.launch_count() - n0 == 2 * one_pass
+    mo, ao = seg_oracle.MIoUOracle(6), seg_oracle.AccuracyOracle()
+    mo.update(pred, target, mask); ao.update(pred, target, mask)
+    assert bits(m()) == bits(mo()) and bits(a()) == bits(ao())
+    # a modified tensor (new version) or a different array never matches the kept pass
+    if as_cuda:
+        p, t, k = (torch.from_numpy(v).cuda() for v in (pred, target, mask))
+        m2 = mIoU(6)
+        m2.update(p, t, k)
+        p[0, 0, 0] = (p[0, 0, 0] + 1) % 6
+        m2.update(p, t, k)
+        mo2 = seg_oracle.MIoUOracle(6)
+        mo2.update(pred, target, mask); mo2.update(p.cpu().numpy(), target, mask)
+        assert np.array_equal(bits(m2.ious), bits(mo2.ious))
+
+
+def test_dataset_level_iou_from_kernel_rows():
+    """the README's dataset-level definitions (README.md:10-16; intersections and unions summed over ALL updates
+    first) from the rows the counts kernel produced, against plain NumPy on the same maps -- including an all-ignored update,
+    a class that never occurs and out-of-range labels."""
+    mIoU, _ = metrics()
+    nc = 19
+    m = mIoU(nc)
+    tot_i = np.zeros(nc, dtype=np.int64); tot_u = np.zeros(nc, dtype=np.int64)
+    for kind, seed, shape in (("plain", 31, (2, 64, 96)), ("all_ignored", 32, (1, 40, 40)), ("oor_target", 33, (2, 37, 53)),
+                              ("plain", 34, (3, 33, 31)), ("oor_pred", 35, (2, 21, 35))):
+        pred, target, mask = seg_case(kind, seed, shape, nc)
+        pred[pred == 7] = 8; target[target == 7] = 8                      # class 7 never occurs: its IoU is 0/0
+        mask = mask & (target != 255)
+        m.update(torch.from_numpy(pred).cuda(), torch.from_numpy(target).cuda(), torch.from_numpy(mask).cuda())
+        for c in range(nc):
+            p_c = mask & (pred == c); t_c = target == c
+            inter = (p_c & (pred == target)).sum()
+            tot_i[c] += inter
+            tot_u[c] += p_c.sum() + t_c.sum() - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pooled = np.float64(tot_i.sum()) / np.float64(tot_u.sum()) * 100.
+        per_class = np.nanmean(tot_i / tot_u) * 100.
+    got = m.dataset_level()
+    assert bits(got[0]) == bits(pooled) and bits(got[1]) == bits(per_class), (got, pooled, per_class)
+    assert tot_u[7] == 0 and 0. < got[0] < 100.
+
+
+@pytest.mark.timeout(900)
+def test_config3_all_500_updates_at_full_size():
+    """BASELINE configs[2] at its stated size: 500 updates of one 1024 x 2048 map each (int64 pred, uint8 target, bool mask,
+    10 % ignored, 70 % correct), fed as ten launches of 50 updates; every integer row, every per-update IoU / accuracy and
+    the two final percentages bit for bit against the C restatement of the reference (oracle/seg_counts_ref.c) on the same
+    maps; plus the reference's batch-4 grouping (125 updates) on the first 100 maps."""
+    import os
+    mIoU, Accuracy = metrics()
+    nc, H, W = 19, 1024, 2048
+    m, a = mIoU(nc), Accuracy()
+    m4, a4 = mIoU(nc), Accuracy()
+    mo, ao, mo4, ao4 = [], [], [], []
+    threads = os.cpu_count()
+    g = torch.Generator(device="cuda")
+    for chunk in range(10):
+        g.manual_seed(54321 + chunk)
+        shape = (50, 1, H, W)
+        target = torch.randint(0, nc, shape, device="cuda", generator=g, dtype=torch.uint8)
+        ign = torch.rand(shape, device="cuda", generator=g) < 0.1
+        target.masked_fill_(ign, 255)
+        rnd = torch.randint(0, nc, shape, device="cuda", generator=g, dtype=torch.uint8)
+        keep = torch.rand(shape, device="cuda", generator=g) < 0.7
+        pred = torch.where(keep, torch.where(ign, torch.zeros_like(target), target), rnd).to(torch.int64)
+        mask = target != 255
+        del rnd, keep, ign
+        m.update_many(pred, target, mask)
+        a.update_many(pred, target, mask)
+        hp, ht, hm = pred.cpu().numpy(), target.cpu().numpy(), mask.cpu().numpy()
+        rows = raw_counts(pred, target, mask, nc, updates_leading=True)
+        for u in range(50):
+            ap, ai, at, c, v = seg_oracle.seg_counts_c(hp[u], ht[u], hm[u], nc, threads=threads)
+            assert np.array_equal(rows[u], np.concatenate([ap, ai, at, [c, v]])), (chunk, u)
+            mo.append(seg_oracle.iou_from_counts(ap, ai, at)); ao.append(seg_oracle.accuracy_from_counts(c, v))
+        if chunk < 2:                                       # batch-4 grouping: (B, H, W) = (4, 1024, 2048) per update
+            p4, t4, k4 = (v.view(-1, 4, H, W) for v in (pred[:48], target[:48], mask[:48]))
+            m4.update_many(p4, t4, k4); a4.update_many(p4, t4, k4)
+            for u in range(12):
+                sl = slice(4 * u, 4 * u + 4)
+                ap, ai, at, c, v = seg_oracle.seg_counts_c(hp[sl, 0], ht[sl, 0], hm[sl, 0], nc, threads=threads)
+                mo4.append(seg_oracle.iou_from_counts(ap, ai, at)); ao4.append(seg_oracle.accuracy_from_counts(c, v))
+        del pred, target, mask
+    assert len(m.ious) == 500 and np.array_equal(bits(m.ious), bits(mo)) and np.array_equal(bits(a.accuracies), bits(ao))
+    assert bits(m()) == bits(np.nanmean(mo) * 100.) and bits(a()) == bits(np.mean(ao) * 100.)
+    assert np.array_equal(bits(m4.ious), bits(mo4)) and np.array_equal(bits(a4.accuracies), bits(ao4))
+    assert bits(m4()) == bits(np.nanmean(mo4) * 100.) and bits(a4()) == bits(np.mean(ao4) * 100.)
