@@ -1586,12 +1586,14 @@ struct ResolveArgs {
 };
 constexpr float kSafe32 = 3.0e-6f;
 
+// kNU = ceil(Kc / 128): a lane holds channels 4*lane + 128*u .. +3 for u < kNU (Kc <= 512).  The kernel issues about one
+// warp instruction per 10 bytes it gathers, so the instruction count matters as much as the bytes: addresses are one
+// 64-bit multiply-add per row, the loads carry immediate offsets, both branches share one warp reduction.
+template <int kNU>
 __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
-    constexpr int kU = 4;                         // a lane holds channels 4*lane + 128*u .. +3, u < 4 (Kc <= 512)
-    constexpr int kR = 4;                         // entries per round: 16 independent 16-byte loads in flight per lane (the pass
-                                                  // is latency x bandwidth bound: 16 warps x 4 rows x 2 KB in flight per SM)
+    constexpr int kR = 4;                         // entries per round: up to 16 independent 16-byte loads in flight per lane
     constexpr float kFix = 1073741824.f;          // 2^30
-    __shared__ long long s_corr[8][4 * kU][32];   // per warp: fixed-point correction of the lane's 16 channels (few entries flip)
+    __shared__ long long s_corr[8][4 * kNU][32];  // per warp: fixed-point correction of the lane's channels (few entries flip)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long grow_ll = (long long)blockIdx.x * 8 + warp;
     if (grow_ll >= (long long)g.B * g.Npad) return;
@@ -1609,15 +1611,26 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
     if (listed == 0) return;
     const float tau = ex.tau[b];
     const double *inv1 = ex.inv64 + (size_t)b * 2 * g.Npad, *inv2 = inv1 + g.Npad;
-    float4 pi[kU];
+    // the lane's slice of the raw rows of this sample: row j is at lane_base + j * Kc, chunk u 128 floats further; a lane whose
+    // last chunk lies past Kc reads chunk 0 again and masks the product (Kc is a multiple of 32, so chunks are whole or absent)
+    const float *lane_base = ex.Ppm + (size_t)b * g.Npad * g.Kc + 4 * lane;
+    const bool last_ok = 4 * lane + 128 * (kNU - 1) < g.Kc;
+    const int last_off = last_ok ? 128 * (kNU - 1) : 0;
+    float4 pi[kNU];
+    float bsel[kNU];                              // +1: the chunk belongs to branch 1, -1: branch 2, 0: absent
+    {
+        const float *ri = lane_base + (size_t)irow * g.Kc;
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-        const int c = 4 * lane + 128 * u;
-        pi[u] = c < g.Kc ? __ldg(reinterpret_cast<const float4 *>(ex.Ppm + grow * g.Kc + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < kNU; ++u) {
+            const int off = u == kNU - 1 ? last_off : 128 * u;
+            pi[u] = __ldg(reinterpret_cast<const float4 *>(ri + off));
+            bsel[u] = (u == kNU - 1 && !last_ok) ? 0.f : (4 * lane + 128 * u < g.C1p ? 1.f : -1.f);
+            if (bsel[u] == 0.f) pi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     const double i1 = inv1[irow], i2 = inv2[irow];
 #pragma unroll
-    for (int t = 0; t < 4 * kU; ++t) s_corr[warp][t][lane] = 0;
+    for (int t = 0; t < 4 * kNU; ++t) s_corr[warp][t][lane] = 0;
     unsigned n_fix = 0;
     float worst = 0.f;
     const unsigned *ent = ex.fent + grow * g.fcap;
@@ -1630,63 +1643,61 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
             const unsigned end_t = __shfl_sync(0xffffffffu, end_s, t);
             if (end_t <= (unsigned)e) { sub = t + 1; start = end_t; }
         }
-        const uint32_t en_l = e < n ? __ldg(ent + (size_t)sub * g.fsub + (e - start)) : 0xffffffffu;
+        const uint32_t en_l = e < n ? __ldg(ent + (size_t)sub * g.fsub + (e - start)) : 0u;
         const int j_l = (int)(en_l & 0x7fffffffu);
-        const double w1_l = e < n ? inv1[j_l] * i1 : 0.0, w2_l = e < n ? inv2[j_l] * i2 : 0.0;
+        // weights of the two branches for this (i, j): +1 / (n1_i n1_j) and -1 / (n2_i n2_j), so that D is ONE weighted sum
+        const float w1_l = e < n ? (float)(inv1[j_l] * i1) : 0.f, w2_l = e < n ? -(float)(inv2[j_l] * i2) : 0.f;
         const int m = min(32, n - e0);
         for (int h0 = 0; h0 < m; h0 += kR) {
             uint32_t en[kR];
-            float4 pj[kR][kU];
+            float4 pj[kR][kNU];
 #pragma unroll
             for (int h = 0; h < kR; ++h) {
                 en[h] = __shfl_sync(0xffffffffu, en_l, (h0 + h) & 31);
-                if (h0 + h >= m) en[h] = 0xffffffffu;
-                const size_t jrow = (size_t)b * g.Npad + (en[h] & 0x7fffffffu);
+                const float *rj = lane_base + (size_t)(en[h] & 0x7fffffffu) * g.Kc;      // past the list: entry 0 = row 0, result unused
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int c = 4 * lane + 128 * u;
-                    pj[h][u] = (en[h] != 0xffffffffu && c < g.Kc) ? __ldg(reinterpret_cast<const float4 *>(ex.Ppm + jrow * g.Kc + c))
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int u = 0; u < kNU; ++u) pj[h][u] = __ldg(reinterpret_cast<const float4 *>(rj + (u == kNU - 1 ? last_off : 128 * u)));
             }
 #pragma unroll
             for (int h = 0; h < kR; ++h) {
-                if (en[h] == 0xffffffffu) continue;                       // warp-uniform
-                const double w1 = __shfl_sync(0xffffffffu, w1_l, (h0 + h) & 31), w2 = __shfl_sync(0xffffffffu, w2_l, (h0 + h) & 31);
-                float s1 = 0.f, s2 = 0.f;
+                if (h0 + h >= m) break;                                   // warp-uniform
+                const float w1 = __shfl_sync(0xffffffffu, w1_l, (h0 + h) & 31), w2 = __shfl_sync(0xffffffffu, w2_l, (h0 + h) & 31);
+                float d = 0.f;
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
+                for (int u = 0; u < kNU; ++u) {
                     float t = pi[u].x * pj[h][u].x;
                     t = fmaf(pi[u].y, pj[h][u].y, t); t = fmaf(pi[u].z, pj[h][u].z, t); t = fmaf(pi[u].w, pj[h][u].w, t);
-                    if (4 * lane + 128 * u < g.C1p) s1 += t; else s2 += t;
+                    d = fmaf(t, bsel[u] > 0.f ? w1 : w2, d);              // pi is zero where the chunk is absent
                 }
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                const float D32 = s1 * (float)w1 - s2 * (float)w2;
-                double D = (double)D32;
-                if (!(fabsf(D32) > kSafe32)) {
-                    // too close for FP32 (also NaN / overflow): exact products, FP64 sums
+                d = warp_sum(d);
+                int s_exact = d > 0.f ? 1 : -1;
+                float dabs = fabsf(d);
+                if (!(dabs > kSafe32)) {
+                    // too close for FP32 (also NaN / overflow): exact products, FP64 sums, FP64 weights
+                    const int j = (int)(en[h] & 0x7fffffffu);
                     double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
+                    for (int u = 0; u < kNU; ++u) {
                         const double t = (double)pi[u].x * (double)pj[h][u].x + (double)pi[u].y * (double)pj[h][u].y +
                                          (double)pi[u].z * (double)pj[h][u].z + (double)pi[u].w * (double)pj[h][u].w;
-                        if (4 * lane + 128 * u < g.C1p) d1 += t; else d2 += t;
+                        if (bsel[u] > 0.f) d1 += t; else d2 += t;
                     }
                     d1 = warp_sum(d1);
                     d2 = warp_sum(d2);
-                    D = d1 * w1 - d2 * w2;
+                    const double D = d1 * (i1 * inv1[j]) - d2 * (i2 * inv2[j]);
+                    s_exact = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0);
+                    dabs = (float)fabs(D);
                 }
-                const int s_exact = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0), s_used = (en[h] >> 31) ? -1 : 1;
+                const int s_used = (en[h] >> 31) ? -1 : 1;
                 if (s_exact != s_used) {
                     ++n_fix;
-                    worst = fmaxf(worst, fabsf((float)D) / tau);
+                    worst = fmaxf(worst, dabs / tau);
                     const int j = (int)(en[h] & 0x7fffffffu);
                     const float f1 = (float)inv1[j] * kFix, f2 = (float)inv2[j] * kFix;      // Fh_j = P_j / n_j, in 2^-30 units
                     const long long dl = (long long)(s_exact - s_used);
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const float w = 4 * lane + 128 * u < g.C1p ? f1 : f2;
+                    for (int u = 0; u < kNU; ++u) {
+                        const float w = bsel[u] > 0.f ? f1 : (bsel[u] < 0.f ? f2 : 0.f);
                         s_corr[warp][4 * u + 0][lane] += dl * (long long)__float2int_rn(pj[h][u].x * w);
                         s_corr[warp][4 * u + 1][lane] += dl * (long long)__float2int_rn(pj[h][u].y * w);
                         s_corr[warp][4 * u + 2][lane] += dl * (long long)__float2int_rn(pj[h][u].z * w);
@@ -1697,16 +1708,14 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
         }
     }
     if (n_fix) {
-        float *orow = ex.opart + grow * g.Kc;
+        float *orow = ex.opart + grow * g.Kc + 4 * lane;
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int c = 4 * lane + 128 * u;
-            if (c < g.Kc) {
-                float4 o = *reinterpret_cast<float4 *>(orow + c);
-                o.x += (float)s_corr[warp][4 * u + 0][lane] * (1.f / kFix); o.y += (float)s_corr[warp][4 * u + 1][lane] * (1.f / kFix);
-                o.z += (float)s_corr[warp][4 * u + 2][lane] * (1.f / kFix); o.w += (float)s_corr[warp][4 * u + 3][lane] * (1.f / kFix);
-                *reinterpret_cast<float4 *>(orow + c) = o;
-            }
+        for (int u = 0; u < kNU; ++u) {
+            if (u == kNU - 1 && !last_ok) break;
+            float4 o = *reinterpret_cast<float4 *>(orow + 128 * u);
+            o.x += (float)s_corr[warp][4 * u + 0][lane] * (1.f / kFix); o.y += (float)s_corr[warp][4 * u + 1][lane] * (1.f / kFix);
+            o.z += (float)s_corr[warp][4 * u + 2][lane] * (1.f / kFix); o.w += (float)s_corr[warp][4 * u + 3][lane] * (1.f / kFix);
+            *reinterpret_cast<float4 *>(orow + 128 * u) = o;
         }
     }
     if (lane == 0) {
@@ -1721,7 +1730,7 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
 // finish: sum the partial accumulators (jsplit shares), apply the normalisation Jacobian, store dP channel-major (or dX
 // itself: fused forward + backward without pooling)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) fa_pos_finish(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
+__global__ void __launch_bounds__(256, 3) fa_pos_finish(PosGeom g, const float *__restrict__ opart, const float *__restrict__ Fcm,
                                                     const __half *__restrict__ FcmH, const float *__restrict__ nrm, float grad_scale,
                                                     float *__restrict__ dP, float *dx1, float *dx2, const float *go) {
     extern __shared__ float T[];                     // [Kc][33] summed accumulator of a 32-position strip
@@ -1767,20 +1776,18 @@ __global__ void __launch_bounds__(256, 2) fa_pos_finish(PosGeom g, const float *
             }
     }
     __syncthreads();
-    // thread (warp, lane) owns position p0 + lane of the channels warp, warp + 8, ...: its normalised features stay in
-    // registers between the projection <Fh_i, O_i> (partial sums per warp, combined in a fixed order) and the output
-    constexpr int kMaxPer = 2 * kMaxGroupCh / 8;      // 64 channels per thread at most
-    float fr[kMaxPer];
+    // thread (warp, lane) owns position p0 + lane of the channels warp, warp + 8, ...: projection <Fh_i, O_i> as partial sums per
+    // warp, combined in a fixed order; the features are read again for the output (they sit in L1 / L2 by then), which keeps the
+    // kernel at three CTAs per SM
+    auto feat = [&](int c) {
+        const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
+        return Fcm ? Fcm[o] : __half2float(FcmH[o]);      // FP16 form: only the FP16 copy exists
+    };
     float p1 = 0.f, p2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < kMaxPer; ++k) {
-        const int c = warp + 8 * k;
-        fr[k] = 0.f;
-        if (c < g.Kc) {
-            const size_t o = ((size_t)b * g.Kc + c) * g.Npad + p0 + lane;
-            fr[k] = Fcm ? Fcm[o] : __half2float(FcmH[o]);      // FP16 form: only the FP16 copy exists
-            if (c < g.C1p) p1 = fmaf(fr[k], T[c * 33 + lane], p1); else p2 = fmaf(fr[k], T[c * 33 + lane], p2);
-        }
+#pragma unroll 8
+    for (int c = warp; c < g.Kc; c += 8) {
+        const float f = feat(c);
+        if (c < g.C1p) p1 = fmaf(f, T[c * 33 + lane], p1); else p2 = fmaf(f, T[c * 33 + lane], p2);
     }
     s_part[0][warp][lane] = p1;
     s_part[1][warp][lane] = p2;
@@ -1796,12 +1803,10 @@ __global__ void __launch_bounds__(256, 2) fa_pos_finish(PosGeom g, const float *
         scale[br] = (br ? -grad_scale : grad_scale) / fmaxf(n, 1e-12f);
     }
     const float gmul = go ? __ldg(go) : 1.f;
-#pragma unroll
-    for (int k = 0; k < kMaxPer; ++k) {
-        const int c = warp + 8 * k;
-        if (c >= g.Kc) continue;
+#pragma unroll 8
+    for (int c = warp; c < g.Kc; c += 8) {
         const int br = c >= g.C1p;
-        const float val = (T[c * 33 + lane] - fr[k] * proj[br]) * scale[br];
+        const float val = (T[c * 33 + lane] - feat(c) * proj[br]) * scale[br];
         if (!go) { dP[((size_t)b * g.Kc + c) * g.Npad + p0 + lane] = val; continue; }
         // fused forward + backward without pooling: dX itself, real channels and positions only
         const int cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
@@ -1991,7 +1996,13 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
         int rc2;
         if (g.exact) {
             const long long rows = (long long)B * g.Npad;
-            fa_pos_resolve<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g, rex);
+            const unsigned blocks = (unsigned)((rows + 7) / 8);
+            switch ((g.Kc + 127) / 128) {
+                case 1: fa_pos_resolve<1><<<blocks, 256, 0, st>>>(g, rex); break;
+                case 2: fa_pos_resolve<2><<<blocks, 256, 0, st>>>(g, rex); break;
+                case 3: fa_pos_resolve<3><<<blocks, 256, 0, st>>>(g, rex); break;
+                default: fa_pos_resolve<4><<<blocks, 256, 0, st>>>(g, rex); break;
+            }
             DSRL_LAUNCH_CHECK();
         }
         if ((rc2 = opt_in_smem(fa_pos_finish, pack_smem))) return rc2;
