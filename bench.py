@@ -915,9 +915,10 @@ def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6)
     from dualsuperreslearningforsemseg_b200 import _lib
     img, org, target = synthetic_batch(batch, dev, SEED + rank)
     out = {}
-    for name, fa, ce in (("dsrl_b200", FALoss(), None), ("pytorch_eager_fa", _TorchFALoss(), None),
-                         ("dsrl_b200_fa_and_ce", FALoss(), CrossEntropyLoss(ignore_index=255))):
-        step = Stage3Step(fa, dev, ddp=world > 1, ce_loss=ce)
+    for name, fa, ce, fused in (("dsrl_b200", FALoss(), None, False), ("pytorch_eager_fa", _TorchFALoss(), None, False),
+                                ("dsrl_b200_fa_and_ce", FALoss(), CrossEntropyLoss(ignore_index=255), False),
+                                ("dsrl_b200_stage3_loss", FALoss(), None, True)):
+        step = Stage3Step(fa, dev, ddp=world > 1, ce_loss=ce, fused_losses=fused)
         n0 = _lib.launch_count()
         for _ in range(max(3, warmup)):
             losses = step(img, org, target)
@@ -931,7 +932,7 @@ def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6)
         ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
         # the FA term alone (forward + backward on the step's own feature-transformer outputs)
         with torch.no_grad():
-            o = step.model(img)
+            o = step.core(img)
         a, b = o[2].detach().requires_grad_(True), o[3].detach().requires_grad_(True)
         for _ in range(3):
             fa(a, b).backward()
@@ -955,6 +956,8 @@ def bench_train_step(args, rank, world, dev, peaks, steps=10, warmup=3, batch=6)
                                    f"{'torch DDP over NCCL' if world > 1 else 'single GPU'}; model = harness/dsrl_model.py (cuDNN fp32)",
                        "fa_inputs": [batch, 1, 64, 128]},
             "with_dsrl_b200_fa": ours, "with_pytorch_eager_fa": ref, "with_dsrl_b200_fa_and_ce": out["dsrl_b200_fa_and_ce"],
+            "with_dsrl_b200_stage3_loss": dict(out["dsrl_b200_stage3_loss"],
+                                               note="CE + MSE + both feature transformers + FA through Stage3Loss: 4 launches forward, 3 backward (SURVEY 8f-2b / 8f-3)"),
             "fa_speedup_in_step": ref["fa_fwd_bwd_ms"] / ours["fa_fwd_bwd_ms"],
             "step_speedup": ref["ms_per_step"] / ours["ms_per_step"]}
 
@@ -1126,6 +1129,8 @@ def summarise_secondary(extra):
         "fa_train_us_per_step": (get("fa_train", "ms_per_step") or 0) * 1e3 or None, "fa_train_gpairs_per_s": get("fa_train", "value"),
         "fa_train_e2e_gpairs_per_s": get("fa_train", "e2e", "value"),
         "train_step_ms": get("train_step", "ms_per_step"), "train_step_images_per_s": get("train_step", "value"),
+        "train_step_ms_with_stage3_loss": get("train_step", "with_dsrl_b200_stage3_loss", "ms_per_step"),
+        "train_step_ms_with_pytorch_eager_fa": get("train_step", "with_pytorch_eager_fa", "ms_per_step"),
         "ce_loss_ms": get("ce_loss", "ms_per_step"),
     }
     for name, v in extra.items():

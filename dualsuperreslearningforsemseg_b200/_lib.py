@@ -26,6 +26,9 @@ EXPORTS = (
     "dsrl_fa_sign_stats", "dsrl_scale_grads",
     "dsrl_seg_counts", "dsrl_seg_counts_from_logits",
     "dsrl_ce_saved_bytes", "dsrl_ce_forward", "dsrl_ce_backward",
+    "dsrl_ce_forward_tap", "dsrl_tap_dw_blocks", "dsrl_ce_backward_tap",
+    "dsrl_mse_workspace_bytes", "dsrl_mse_forward", "dsrl_mse_backward",
+    "dsrl_ft_bn_forward", "dsrl_ft_bn_backward", "dsrl_fa_forward_backward_transformed",
 )
 
 
@@ -72,6 +75,25 @@ def _declare(lib):
     lib.dsrl_ce_forward.argtypes = [vp, vp, i, i, i, i64, i64, i, vp, vp, sz, vp]
     lib.dsrl_ce_backward.restype = i
     lib.dsrl_ce_backward.argtypes = [vp, vp, i, i, i, i64, i64, i, vp, sz, vp, vp, vp]
+    f = c.c_float
+    lib.dsrl_ce_forward_tap.restype = i
+    lib.dsrl_ce_forward_tap.argtypes = [vp, vp, i, i, i, i, i, i64, i, vp, vp, sz, vp, vp, i, vp]
+    lib.dsrl_tap_dw_blocks.restype = i64
+    lib.dsrl_tap_dw_blocks.argtypes = [i, i, i, i]
+    lib.dsrl_ce_backward_tap.restype = i
+    lib.dsrl_ce_backward_tap.argtypes = [vp, vp, i, i, i, i, i, i64, i, vp, sz, vp, vp, vp, vp, vp, i, c.POINTER(c.c_int64), vp]
+    lib.dsrl_mse_workspace_bytes.restype = sz
+    lib.dsrl_mse_workspace_bytes.argtypes = [i, i, i, i]
+    lib.dsrl_mse_forward.restype = i
+    lib.dsrl_mse_forward.argtypes = [vp, vp, i, i, i, i, vp, vp, sz, vp, vp, i, vp]
+    lib.dsrl_mse_backward.restype = i
+    lib.dsrl_mse_backward.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp]
+    lib.dsrl_ft_bn_forward.restype = i
+    lib.dsrl_ft_bn_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, f, f, i, vp, vp]
+    lib.dsrl_ft_bn_backward.restype = i
+    lib.dsrl_ft_bn_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i, vp]
+    lib.dsrl_fa_forward_backward_transformed.restype = i
+    lib.dsrl_fa_forward_backward_transformed.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, sz, vp, sz, vp]
 
 
 def lib():

@@ -13,7 +13,7 @@ int fa_ref_backward(const void *saved, size_t saved_bytes, const float *grad_out
 
 int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int H, int W, int k, int reduction,
                             const float *grad_out, float *loss_out, float *dx1, float *dx2, void *saved, size_t saved_bytes,
-                            void *ws, size_t ws_bytes, cudaStream_t st);
+                            void *ws, size_t ws_bytes, cudaStream_t st, const float *bn);
 
 size_t fa_pos_saved_bytes(int precision, int B, int C1, int C2, int H, int W, int k);
 size_t fa_pos_workspace_bytes(int precision, int B, int C1, int C2, int H, int W, int k);
@@ -144,7 +144,7 @@ extern "C" int dsrl_fa_forward_backward(int mode, int precision, const float *x1
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mode == DSRL_FA_REFERENCE) {
         rc = fa_ref_forward_backward(x1, x2, B, C1, H, W, k, reduction, grad_out, loss_out, dx1, dx2, saved, saved_bytes, workspace,
-                                     workspace_bytes, st);
+                                     workspace_bytes, st, nullptr);
         if (rc != DSRL_ERR_UNSUPPORTED) return rc;       // DSRL_OK or a real error; otherwise fall through to the two-call path
     }
     if (mode == DSRL_FA_POSITION)
@@ -155,4 +155,20 @@ extern "C" int dsrl_fa_forward_backward(int mode, int precision, const float *x1
     if (rc) return rc;
     return dsrl_fa_backward(mode, precision, x1, x2, saved, saved_bytes, grad_out, dx1, dx2, B, C1, C2, H, W, k, reduction, workspace,
                             workspace_bytes, stream);
+}
+
+extern "C" int dsrl_fa_forward_backward_transformed(const float *z1, const float *z2, const float *bn, int B, int H, int W, int k,
+                                                    int reduction, const float *grad_out, float *loss_out, float *df1, float *df2,
+                                                    void *saved, size_t saved_bytes, void *workspace, size_t workspace_bytes,
+                                                    dsrl_stream_t stream) {
+    if (!z1 || !z2 || !bn || !grad_out || !loss_out || !df1 || !df2 || !saved || !workspace)
+        DSRL_FAIL(DSRL_ERR_BAD_ARG, "FA (transformed): null pointer");
+    if (reduction != DSRL_REDUCE_MEAN && reduction != DSRL_REDUCE_SUM) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA (transformed): reduction must be mean or sum");
+    int rc = require_device();
+    if (rc) return rc;
+    rc = fa_ref_forward_backward(z1, z2, B, 1, H, W, k, reduction, grad_out, loss_out, df1, df2, saved, saved_bytes, workspace, workspace_bytes,
+                                 static_cast<cudaStream_t>(stream), bn);
+    if (rc == DSRL_ERR_UNSUPPORTED)
+        set_last_error("FA (transformed): only the single-launch geometries (pooled map at most 32 x 16, H and W divisible by k, k divisible by 4)");
+    return rc;
 }

@@ -875,8 +875,11 @@ struct FusedBranch {
 };
 inline bool fused_ok(const RefGeom &g) { return g.w <= kFusedMaxW && g.h <= kFusedMaxH; }
 
-__device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, int W, int k, bool vec4) {
+// act: the map is a feature transformer's convolution output and the cell averages relu(a * z + b) -- BatchNorm2d(1) + ReLU
+// (models/DSRL.py:86-95) folded into the pooling read
+__device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, int W, int k, bool vec4, bool act, float a, float b) {
     float s = 0.f;
+    auto f = [&](float v) { return act ? fmaxf(fmaf(a, v, b), 0.f) : v; };
     if (vec4 && k == 8) {
         // the model's subsample factor: all 16 vector loads of the 8 x 8 window in flight at once (the inputs are cold in
         // HBM; issued one row at a time the pooling phase was eight dependent memory latencies long)
@@ -888,19 +891,19 @@ __device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, i
             v[2 * dy + 1] = __ldg(r + 1);
         }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { s += v[q].x; s += v[q].y; s += v[q].z; s += v[q].w; }
+        for (int q = 0; q < 16; ++q) { s += f(v[q].x); s += f(v[q].y); s += f(v[q].z); s += f(v[q].w); }
     } else if (vec4) {
 #pragma unroll 1
         for (int dy = 0; dy < k; ++dy) {
             const float4 *r = reinterpret_cast<const float4 *>(base + (size_t)dy * W);
 #pragma unroll 2
-            for (int q = 0; q < (k >> 2); ++q) { const float4 v = __ldg(r + q); s += v.x; s += v.y; s += v.z; s += v.w; }
+            for (int q = 0; q < (k >> 2); ++q) { const float4 v = __ldg(r + q); s += f(v.x); s += f(v.y); s += f(v.z); s += f(v.w); }
         }
     } else {
 #pragma unroll 1
         for (int dy = 0; dy < k; ++dy)
 #pragma unroll 1
-            for (int dx = 0; dx < k; ++dx) s += __ldg(base + (size_t)dy * W + dx);
+            for (int dx = 0; dx < k; ++dx) s += f(__ldg(base + (size_t)dy * W + dx));
     }
     return s / (float)(k * k);
 }
@@ -910,7 +913,8 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
                                                           double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                           float g_scale, double loss_div, float *__restrict__ loss_out,
                                                           int need_grad, const float *__restrict__ grad_out,
-                                                          float *__restrict__ dx1, float *__restrict__ dx2) {
+                                                          float *__restrict__ dx1, float *__restrict__ dx2,
+                                                          const float *__restrict__ bn) {
     __shared__ FusedBranch sb[2];
     __shared__ double red[34];
     __shared__ int is_last;
@@ -934,8 +938,10 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
     // 1. pool (FALoss.py:23-24)
     const float *x = (br ? x2 : x1) + (size_t)bc * g.H * g.W;
     const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    if (c0) fb.P[a0] = pool_cell_rolled(x + (size_t)qw * g.k * g.W + (size_t)rw * g.k, g.W, g.k, vec4);
-    if (c1) fb.P[a1] = pool_cell_rolled(x + (size_t)qw2 * g.k * g.W + (size_t)rw2 * g.k, g.W, g.k, vec4);
+    const bool act = bn != nullptr;                          // {a, b, mean, invstd} per branch from ft_bn_forward_kernel
+    const float bn_a = act ? __ldg(bn + 4 * br) : 1.f, bn_b = act ? __ldg(bn + 4 * br + 1) : 0.f;
+    if (c0) fb.P[a0] = pool_cell_rolled(x + (size_t)qw * g.k * g.W + (size_t)rw * g.k, g.W, g.k, vec4, act, bn_a, bn_b);
+    if (c1) fb.P[a1] = pool_cell_rolled(x + (size_t)qw2 * g.k * g.W + (size_t)rw2 * g.k, g.W, g.k, vec4, act, bn_a, bn_b);
     grp.sync();
 
     TSTAMP(1);
@@ -1201,7 +1207,7 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
         if (!ticket) return DSRL_ERR_CUDA;
         const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
         fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
-                                                  loss_out, need_grad, nullptr, nullptr, nullptr);
+                                                  loss_out, need_grad, nullptr, nullptr, nullptr, nullptr);
         DSRL_LAUNCH_CHECK();
         return DSRL_OK;
     }
@@ -1245,9 +1251,12 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
 
 // Forward + backward in ONE launch when the geometry allows it (training shapes, windows tile the map exactly);
 // returns DSRL_ERR_UNSUPPORTED otherwise and the caller falls back to forward + backward.
+// bn (optional): x1, x2 are the convolution outputs of the two feature transformers and the loss is taken on
+// relu(a * x + b) with {a, b} = bn[4 * branch + {0, 1}] (device memory, written by dsrl_ft_bn_forward); dx then is the
+// gradient w.r.t. the transformer OUTPUT (the BatchNorm / ReLU backward is dsrl_ft_bn_backward)
 int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int H, int W, int k, int reduction,
                             const float *grad_out, float *loss_out, float *dx1, float *dx2, void *saved_v, size_t saved_bytes,
-                            void *ws, size_t ws_bytes, cudaStream_t st) {
+                            void *ws, size_t ws_bytes, cudaStream_t st, const float *bn) {
     RefGeom g;
     if (!make_geom(B, C, H, W, k, g)) DSRL_FAIL(DSRL_ERR_BAD_SHAPE, "FA(reference): bad geometry B=%d C=%d H=%d W=%d k=%d", B, C, H, W, k);
     const bool aligned = (!dx1 || (reinterpret_cast<uintptr_t>(dx1) & 15) == 0) && (!dx2 || (reinterpret_cast<uintptr_t>(dx2) & 15) == 0);
@@ -1259,7 +1268,7 @@ int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int 
     if (!ticket) return DSRL_ERR_CUDA;
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
     fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket,
-                                              (float)(1.0 / Z), Z, loss_out, 1, grad_out, dx1, dx2);
+                                              (float)(1.0 / Z), Z, loss_out, 1, grad_out, dx1, dx2, bn);
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;
 }

@@ -90,7 +90,9 @@ class DSRL(nn.Module):
             self.SISR_feature_transformer = _cbr(NUM_RGB, 1, 1, stride=8)
             _kaiming(self.SSSR_feature_transformer, self.SISR_feature_transformer)
 
-    def forward(self, x):
+    def forward(self, x, apply_transformers=True):
+        """apply_transformers=False: the two stage-3 feature transformers are left to the loss (dsrl-b200 Stage3Loss evaluates
+        them inside the CE / MSE / FA passes); the last two outputs are then None."""
         fe = self.feature_extractor
         deep, low = fe["backbone"](x)
         deep = F.interpolate(fe["aspp"](deep), scale_factor=4.0, mode="bilinear", align_corners=True)
@@ -100,6 +102,8 @@ class DSRL(nn.Module):
         if self.stage > 1:
             sisr = self.SISR_decoder(cat)
         if self.stage > 2:
+            if not apply_transformers:
+                return sssr, sisr, None, None
             sssr_t = self.SSSR_feature_transformer(sssr)
             sisr_t = self.SISR_feature_transformer(sisr)
         return sssr, sisr, sssr_t, sisr_t

@@ -24,7 +24,7 @@ def synthetic_batch(batch, device, seed, in_hw=(256, 512), num_classes=19):
 
 
 class Stage3Step:
-    def __init__(self, fa_loss, device, seed=54321, num_classes=19, ddp=False, ce_loss=None):
+    def __init__(self, fa_loss, device, seed=54321, num_classes=19, ddp=False, ce_loss=None, fused_losses=False):
         torch.manual_seed(seed)                                   # all ranks build the same weights (train_or_resume.py:31)
         self.model = DSRL(3, num_classes).to(device).train()
         self.core = self.model
@@ -36,9 +36,18 @@ class Stage3Step:
         self.ce_takes_uint8 = ce_loss is not None
         self.mse = nn.MSELoss()
         self.fa = fa_loss
+        # fused_losses: CE, MSE, both feature transformers and FA through dsrl-b200's Stage3Loss (shared passes)
+        self.stage3 = None
+        if fused_losses:
+            from dualsuperreslearningforsemseg_b200.models.losses import Stage3Loss
+            self.stage3 = Stage3Loss(self.core.SSSR_feature_transformer, self.core.SISR_feature_transformer, ignore_index=IGNORE)
         self.opt = torch.optim.SGD(self.model.parameters(), lr=LR, momentum=MOMENTUM, weight_decay=WEIGHT_DECAY)
 
     def losses(self, img, org, target):
+        if self.stage3 is not None:
+            sssr, sisr, _, _ = self.model(img, apply_transformers=False)
+            ce, mse, fa = self.stage3(sssr, sisr, target, org)
+            return ce, W1 * mse, W2 * fa, (sssr, sisr, None, None)
         sssr, sisr, sssr_t, sisr_t = self.model(img)
         ce = self.ce(sssr, target if self.ce_takes_uint8 else target.long())
         mse = W1 * self.mse(sisr, org)

@@ -164,6 +164,55 @@ int dsrl_ce_backward(const float *logits, const void *target, int target_dtype, 
                      int64_t ignore_index, int reduction, const void *saved, size_t saved_bytes,
                      const float *grad_out, float *dlogits, dsrl_stream_t stream);
 
+/* ---- the stage-3 losses in shared passes ----------------------------------------------------
+ * The reference's stage-3 step evaluates   CE(SSSR, target) + w1 * MSE(SISR, image) + w2 * FA(T1(SSSR), T2(SISR))
+ * (train_or_resume.py:435-438) where T1 / T2 are the "feature transformers" Conv2d(C -> 1, kernel 1, stride 8, no bias) +
+ * BatchNorm2d(1) + ReLU (models/DSRL.py:86-95,181,184).  The strided 1x1 convolution reads 1/64 of the pixels the CE / MSE
+ * passes stream anyway, so those passes emit it ("tap"); BatchNorm + ReLU are folded into the FA kernel's pooling read; and
+ * the backward passes of CE / MSE add the transformer path's input gradient dz * w[c] at the strided pixels in place and
+ * collect dw.  Forward: 4 launches for the three losses, backward: 3.
+ *
+ * tap_w: [C] convolution weight; tap_z: (B, Hf, Wf) convolution output, Hf = (H-1)/stride + 1; tap_dz: gradient w.r.t. it;
+ * tap_dw_part: [dsrl_tap_dw_blocks(B, H, W, stride)][C] per-block partial sums of dw (every row written; the rows actually
+ * used by a call are returned in *dw_blocks_used; sum them over axis 0).  The vector path needs W % 4 == 0, stride % 4 == 0. */
+int dsrl_ce_forward_tap(const float *logits, const void *target, int target_dtype, int B, int C, int H, int W,
+                        int64_t ignore_index, int reduction, float *loss_out, void *saved, size_t saved_bytes,
+                        const float *tap_w, float *tap_z, int tap_stride, dsrl_stream_t stream);
+int64_t dsrl_tap_dw_blocks(int B, int H, int W, int tap_stride);
+int dsrl_ce_backward_tap(const float *logits, const void *target, int target_dtype, int B, int C, int H, int W,
+                         int64_t ignore_index, int reduction, const void *saved, size_t saved_bytes, const float *grad_out,
+                         float *dlogits, const float *tap_w, const float *tap_dz, float *tap_dw_part, int tap_stride,
+                         int64_t *dw_blocks_used, dsrl_stream_t stream);
+
+/* Mean squared error over (B, C, H, W) fp32 tensors (`t.nn.MSELoss()`, train_or_resume.py:117,436) in one pass forward
+ * (deterministic two-level sum) and one pass backward (dx = grad_out * 2 (x - y) / count), with the same optional taps
+ * (tap_w == NULL: none).  H * W divisible by 4, 16-byte aligned tensors. */
+size_t dsrl_mse_workspace_bytes(int B, int C, int H, int W);
+int dsrl_mse_forward(const float *x, const float *y, int B, int C, int H, int W, float *loss_out, void *workspace,
+                     size_t workspace_bytes, const float *tap_w, float *tap_z, int tap_stride, dsrl_stream_t stream);
+int dsrl_mse_backward(const float *x, const float *y, int B, int C, int H, int W, const float *grad_out, float *dx,
+                      const float *tap_w, const float *tap_dz, float *tap_dw_part, int tap_stride, dsrl_stream_t stream);
+
+/* BatchNorm2d(1) + ReLU of the two transformers (models/DSRL.py:93-95).  Forward: batch statistics (training) or the running
+ * ones (eval) -> bn_out[t] = {a, b, mean, invstd}, the transformer output being relu(a z + b); in training mode the running
+ * statistics are updated as torch does (momentum, unbiased variance).  Backward: from dF (gradient w.r.t. the transformer
+ * output for a unit upstream gradient) and grad_out (1 device float) -> dz (gradient w.r.t. the convolution output) and
+ * dgb = {dgamma, dbeta}.  count = B * Hf * Wf.  One launch each for both transformers. */
+int dsrl_ft_bn_forward(const float *z1, const float *z2, int64_t count, const float *gamma1, const float *beta1,
+                       float *run_mean1, float *run_var1, const float *gamma2, const float *beta2, float *run_mean2,
+                       float *run_var2, float eps, float momentum, int training, float *bn_out, dsrl_stream_t stream);
+int dsrl_ft_bn_backward(const float *z1, const float *dF1, float *dz1, float *dgb1, const float *z2, const float *dF2,
+                        float *dz2, float *dgb2, int64_t count, const float *bn, const float *grad_out, int training,
+                        dsrl_stream_t stream);
+
+/* FA loss (reference semantics, C = 1) of the two transformer outputs relu(a z + b), read straight from the convolution outputs
+ * z1, z2 (B, 1, H, W) with bn = dsrl_ft_bn_forward's bn_out; forward + backward in ONE launch: loss and df1 / df2 = gradient
+ * w.r.t. the transformer outputs, scaled by *grad_out.  saved / workspace as dsrl_fa_forward_backward (reference mode). */
+int dsrl_fa_forward_backward_transformed(const float *z1, const float *z2, const float *bn, int B, int H, int W, int k,
+                                         int reduction, const float *grad_out, float *loss_out, float *df1, float *df2,
+                                         void *saved, size_t saved_bytes, void *workspace, size_t workspace_bytes,
+                                         dsrl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
