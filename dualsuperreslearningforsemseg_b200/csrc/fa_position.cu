@@ -57,6 +57,8 @@ constexpr size_t kSmemAux = 1536;   // barriers, TMEM pointer, reduction scratch
 // every tile kernel allocates all 512 tensor-memory columns, so two of its CTAs must never share an SM (the second would
 // spin in tcgen05.alloc; with CTA pairs that can deadlock): each requests more than half of an SM's shared memory
 constexpr size_t kOneCtaSmem = 116 * 1024;
+constexpr size_t kSignBlockBytes = 2 * 128 * 16;              // two-pass form: sign planes, bytes per (row tile, column tile)
+constexpr size_t kSignPlaneCapBytes = (size_t)6 << 30;        // largest sign-plane footprint the two-pass form may use
 constexpr int kXchgBytes = 2 * 2 * 128 * 16;   // fa_pos_tiles_quad: two slots x (two column halves x 128 rows x 16 bytes of sign / zero bits)
 
 struct PosGeom {
@@ -74,10 +76,14 @@ struct PosGeom {
     int exact, fnsub, fsub, fcap; // exact signs: near-tie entries of D are listed per row -- 2 * jsplit private sub-lists (one per
                                   // epilogue thread that converts part of the row) of fsub entries, fcap in all -- and re-decided in FP64
     int raw_o;                    // the tile kernel stores raw accumulator rows, fa_pos_finish completes them (jsplit > 1 or exact)
+    int ab;                       // FP16 form as two symmetric passes (fa_position_ab.cuh): D tiles j >= i -> sign planes -> gradient
+    int a_chunk, a_units;         // pass A: column tiles per work unit (tiles: no split), work units per sample
+    int b_stages;                 // pass B: depth of the V ring
+    size_t b_smem_bytes, sb_bytes;   // pass B shared memory; sign planes of all samples
     size_t smem_bytes, pair_smem_bytes, half_smem_bytes, half1_smem_bytes;
 };
 
-struct PosWs { size_t Fpm, Fcm, FpmH, FcmH, nrm, partials, opart, Ppm, inv64, tau, fcnt, fent, total; };
+struct PosWs { size_t Fpm, Fcm, FpmH, FcmH, nrm, partials, opart, Ppm, inv64, tau, fcnt, fent, sb, total; };
 struct PosSaved { size_t dP, total; };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -168,18 +174,42 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         g.quad = g.half_pair && g.G == 2 && g.gcnt[0] == g.gcnt[1] && (g.tiles / g.jsplit) % 2 == 0 && g.quad_stages >= 3;
         if (const char *e = getenv("DSRL_POS_QUAD")) { if (atoi(e) == 0) g.quad = 0; }
     }
+    // FP16 form as two symmetric passes over CTA pairs (fa_position_ab.cuh): whenever the pair form applies and the sign
+    // planes (N^2 / 4 bytes per sample) stay below the cap
+    {
+        g.sb_bytes = (size_t)B * g.tiles * g.tiles * kSignBlockBytes;
+        g.ab = g.half_pair && g.sb_bytes <= kSignPlaneCapBytes;
+        if (const char *e = getenv("DSRL_POS_AB")) { if (atoi(e) == 0) g.ab = 0; }
+        if (!g.ab) g.sb_bytes = 0;
+        // pass A: a pair of row tiles against its column tiles j >= 2p is one work unit when there are plenty of them; small
+        // grids cut the column range into chunks (no accumulator: a chunk only re-loads the pair's own rows) so that the
+        // triangle balances over the SMs.  Near-tie sub-lists are per (chunk, column half): at most 8 chunks.
+        g.a_chunk = g.tiles;
+        if ((long long)B * (g.tiles / 2) < 8LL * (sms / 2)) g.a_chunk = (g.tiles + 7) / 8 < 8 ? (g.tiles < 8 ? g.tiles : 8) : (g.tiles + 7) / 8;
+        if (const char *e = getenv("DSRL_POS_ACHUNK")) {          // test hook
+            const int v = atoi(e);
+            if (v >= 1 && (g.tiles + v - 1) / v <= 8) g.a_chunk = v < g.tiles ? v : g.tiles;
+        }
+        g.a_units = 0;
+        for (int p = 0; p < g.tiles / 2; ++p) g.a_units += (g.tiles - 2 * p + g.a_chunk - 1) / g.a_chunk;
+        g.b_stages = (int)((kSmemBudget - 1024 - kSmemAux) / kBoxBytes);
+        if (g.b_stages > 12) g.b_stages = 12;
+        g.b_smem_bytes = 1024 + (size_t)g.b_stages * kBoxBytes + kSmemAux;
+        if (g.ab) g.quad = 0;
+    }
     // exact signs: about 1e-3 of a row's entries are near ties (|D| below ~3.5 sigma of the operand-rounding error, whatever
     // C is: threshold and spread of D both scale like 1/sqrt(C)); the per-row list holds 4x that, at least 32 entries
     g.exact = exact ? 1 : 0;
     {
         // sub-lists per row: column half x column share (x 2 when the two channel groups split the column tiles between them);
-        // expected N * 1.1e-3 / nsub entries each, room for 4x that + 16
-        const int nsub = g.fnsub = 2 * g.jsplit * (g.quad ? 2 : 1);
+        // expected N * 1.1e-3 / nsub entries each, room for 4x that + 16.  Two-pass form: column half x column chunk of pass A
+        // (upper triangle only, so a row holds at most what a full row would).
+        const int nsub = g.fnsub = g.ab ? 2 * ((g.tiles + g.a_chunk - 1) / g.a_chunk) : 2 * g.jsplit * (g.quad ? 2 : 1);
         g.fsub = (int)align_up((size_t)(N / (200 * nsub)) + 16, 8);
         if (g.fsub > 2048) g.fsub = 2048;
         g.fcap = g.fsub * nsub;
     }
-    g.raw_o = g.jsplit > 1 || g.exact;
+    g.raw_o = g.jsplit > 1 || (g.exact && !g.ab);      // two-pass form: the resolve pass fixes the sign planes, not the accumulators
     return true;
 }
 
@@ -193,7 +223,11 @@ inline PosWs make_ws(const PosGeom &g) {
     w.FpmH = off;     off = align_up(off + (g.half ? (size_t)g.B * g.Npad * g.Kc * 2 : 0), 1024);           // FP16 copies of both layouts
     w.FcmH = off;     off = align_up(off + (g.half ? ((size_t)g.B * g.Kc + kTile) * g.Npad * 2 : 0), 1024);
     w.nrm = off;      off = align_up(off + (size_t)g.B * 2 * g.Npad * 4, 256);
-    w.partials = off; off = align_up(off + (size_t)g.B * g.tiles * g.jsplit * g.G * 8 + 16384, 256);   // + debug timing area
+    {
+        size_t np = (size_t)g.B * g.tiles * g.jsplit * g.G;
+        if (g.ab && (size_t)g.B * 2 * g.a_units > np) np = (size_t)g.B * 2 * g.a_units;       // pass A: one loss partial per CTA
+        w.partials = off; off = align_up(off + np * 8 + 16384, 256);   // + debug timing area
+    }
     w.opart = off;    off = align_up(off + (g.raw_o ? (size_t)g.jsplit * g.B * g.Npad * g.Kc * 4 : 0), 256);
     // exact signs: raw pooled features (position-major fp32), FP64 inverse norms, per-sample tie threshold, per-row tie lists
     w.Ppm = off;      off = align_up(off + (g.exact ? (size_t)g.B * g.Npad * g.Kc * 4 : 0), 256);
@@ -201,6 +235,7 @@ inline PosWs make_ws(const PosGeom &g) {
     w.tau = off;      off = align_up(off + (g.exact ? (size_t)g.B * 4 : 0), 256);
     w.fcnt = off;     off = align_up(off + (g.exact ? (size_t)g.B * g.Npad * g.fnsub * 4 : 0), 256);
     w.fent = off;     off = align_up(off + (g.exact ? (size_t)g.B * g.Npad * g.fcap * 4 : 0), 256);
+    w.sb = off;       off = align_up(off + g.sb_bytes, 256);
     w.total = off;
     return w;
 }
@@ -391,6 +426,7 @@ struct PosArgs {
     // exact signs: per-sample tie threshold, per-row tie counters and lists (column | sign bit of the tensor-core value)
     const float *tau;
     unsigned *fcnt, *fent;
+    uint4 *sb;          // two-pass form: the sign planes
 };
 
 #ifdef DSRL_POS_TIMING
@@ -1567,8 +1603,10 @@ fa_pos_tiles_quad(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
 }
 
+#include "fa_position_ab.cuh"      // the symmetric two-pass form (fa_pos_dsign, fa_pos_grad, sign planes)
+
 // ---------------------------------------------------------------------------------------------------------------
-// exact signs: re-decide the listed near ties, correct the raw accumulator rows
+// exact signs: re-decide the listed near ties, correct the raw accumulator rows (or, two-pass form, the sign planes)
 // ---------------------------------------------------------------------------------------------------------------
 // The tile kernel took sign(D_ij) from the tensor-core value and listed every entry with 0 < |D_ij| < tau.  Here one warp per
 // row i re-evaluates those entries from the raw pooled features,
@@ -1583,25 +1621,31 @@ fa_pos_tiles_quad(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 struct ResolveArgs {
     const float *Ppm; const double *inv64; const float *tau; const unsigned *fcnt, *fent; unsigned long long *stats;
     float *opart;            // raw accumulator rows of column share 0: (B, Npad, Kc)
+    uint4 *sb;               // two-pass form (kBits): the sign planes; the lists hold upper-triangle entries only
 };
 constexpr float kSafe32 = 3.0e-6f;
 
 // kNU = ceil(Kc / 128): a lane holds channels 4*lane + 128*u .. +3 for u < kNU (Kc <= 512).  The kernel issues about one
 // warp instruction per 10 bytes it gathers, so the instruction count matters as much as the bytes: addresses are one
 // 64-bit multiply-add per row, the loads carry immediate offsets, both branches share one warp reduction.
-template <int kNU>
+// kBits (two-pass form): nothing is accumulated -- the exact sign of a listed entry (i, j), j > i, is written into the sign
+// planes at (i, j) and at (j, i) wherever it differs from the tensor-core sign (inside a diagonal tile always: its lower half
+// was converted from its own tensor-core values).
+template <int kNU, bool kBits = false>
 __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
     constexpr int kR = 4;                         // entries per round: up to 16 independent 16-byte loads in flight per lane
     constexpr float kFix = 1073741824.f;          // 2^30
-    __shared__ long long s_corr[8][4 * kNU][32];  // per warp: fixed-point correction of the lane's channels (few entries flip)
+    __shared__ long long s_corr[kBits ? 1 : 8][kBits ? 1 : 4 * kNU][32];  // per warp: fixed-point correction of the lane's channels (few entries flip)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long grow_ll = (long long)blockIdx.x * 8 + warp;
     if (grow_ll >= (long long)g.B * g.Npad) return;
     const size_t grow = (size_t)grow_ll;
     const int b = (int)(grow / g.Npad), irow = (int)(grow - (size_t)b * g.Npad);
     const int nsub = g.fnsub;                     // <= 16
-    // this row's sub-lists (lane s holds the count of sub-list s) as one sequence of n entries
-    const unsigned cnt_s = lane < nsub ? ex.fcnt[grow * nsub + lane] : 0u;
+    // this row's sub-lists (lane s holds the count of sub-list s) as one sequence of n entries; two-pass form: only the column
+    // chunks that exist for the row's pair of tiles were written
+    const int nsub_row = kBits ? 2 * dsign_chunks(g.tiles, g.a_chunk, irow / (2 * kTile)) : nsub;
+    const unsigned cnt_s = lane < nsub_row ? ex.fcnt[grow * nsub + lane] : 0u;
     const unsigned len_s = min(cnt_s, (unsigned)g.fsub);
     unsigned end_s = len_s;                       // inclusive prefix sum over the sub-lists
 #pragma unroll
@@ -1629,8 +1673,11 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
         }
     }
     const double i1 = inv1[irow], i2 = inv2[irow];
+    if (!kBits) {
 #pragma unroll
-    for (int t = 0; t < 4 * kNU; ++t) s_corr[warp][t][lane] = 0;
+        for (int t = 0; t < 4 * kNU; ++t) s_corr[warp][t][lane] = 0;
+    }
+    uint32_t *sbw = kBits ? reinterpret_cast<uint32_t *>(ex.sb + (size_t)b * g.tiles * g.tiles * (kSignBlockBytes / 16)) : nullptr;
     unsigned n_fix = 0;
     float worst = 0.f;
     const unsigned *ent = ex.fent + grow * g.fcap;
@@ -1689,6 +1736,16 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
                     dabs = (float)fabs(D);
                 }
                 const int s_used = (en[h] >> 31) ? -1 : 1;
+                if (kBits) {
+                    const int j = (int)(en[h] & 0x7fffffffu);
+                    const bool fix = s_exact != s_used;
+                    if (fix) { ++n_fix; worst = fmaxf(worst, dabs / tau); }
+                    if ((fix || (j >> 7) == (irow >> 7)) && lane == 0) {
+                        if (fix) sign_plane_set(sbw, g.tiles, irow, j, s_exact);
+                        sign_plane_set(sbw, g.tiles, j, irow, s_exact);
+                    }
+                    continue;
+                }
                 if (s_exact != s_used) {
                     ++n_fix;
                     worst = fmaxf(worst, dabs / tau);
@@ -1707,7 +1764,7 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
             }
         }
     }
-    if (n_fix) {
+    if (!kBits && n_fix) {
         float *orow = ex.opart + grow * g.Kc + 4 * lane;
 #pragma unroll
         for (int u = 0; u < kNU; ++u) {
@@ -1979,6 +2036,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     rex.tau = reinterpret_cast<float *>(ws + wo.tau);
     rex.fent = reinterpret_cast<unsigned *>(ws + wo.fent);
     rex.opart = reinterpret_cast<float *>(ws + wo.opart);
+    rex.sb = reinterpret_cast<uint4 *>(ws + wo.sb);
     // FP16 form: the FP16 copies are the only ones written (and read back by the normalisation Jacobian)
     if (g.exact) {
         fa_pos_pack<true><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
@@ -1992,19 +2050,30 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     }
     DSRL_LAUNCH_CHECK();
     // the tile kernel's raw accumulator rows -> dP / dX (all variants share it)
-    auto finish = [&](const PosArgs &a) -> int {
-        int rc2;
-        if (g.exact) {
-            const long long rows = (long long)B * g.Npad;
-            const unsigned blocks = (unsigned)((rows + 7) / 8);
+    auto resolve = [&]() -> int {
+        const long long rows = (long long)B * g.Npad;
+        const unsigned blocks = (unsigned)((rows + 7) / 8);
+        if (g.ab) {
+            switch ((g.Kc + 127) / 128) {
+                case 1: fa_pos_resolve<1, true><<<blocks, 256, 0, st>>>(g, rex); break;
+                case 2: fa_pos_resolve<2, true><<<blocks, 256, 0, st>>>(g, rex); break;
+                case 3: fa_pos_resolve<3, true><<<blocks, 256, 0, st>>>(g, rex); break;
+                default: fa_pos_resolve<4, true><<<blocks, 256, 0, st>>>(g, rex); break;
+            }
+        } else {
             switch ((g.Kc + 127) / 128) {
                 case 1: fa_pos_resolve<1><<<blocks, 256, 0, st>>>(g, rex); break;
                 case 2: fa_pos_resolve<2><<<blocks, 256, 0, st>>>(g, rex); break;
                 case 3: fa_pos_resolve<3><<<blocks, 256, 0, st>>>(g, rex); break;
                 default: fa_pos_resolve<4><<<blocks, 256, 0, st>>>(g, rex); break;
             }
-            DSRL_LAUNCH_CHECK();
         }
+        DSRL_LAUNCH_CHECK();
+        return DSRL_OK;
+    };
+    auto finish = [&](const PosArgs &a) -> int {
+        int rc2;
+        if (g.exact && !g.ab && (rc2 = resolve())) return rc2;
         if ((rc2 = opt_in_smem(fa_pos_finish, pack_smem))) return rc2;
         fa_pos_finish<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
         DSRL_LAUNCH_CHECK();
@@ -2033,6 +2102,24 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     a.tau = rex.tau; a.fcnt = const_cast<unsigned *>(rex.fcnt); a.fent = const_cast<unsigned *>(rex.fent);
     if (fused_out) *fused_out = a.direct;
     const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
+    a.sb = rex.sb;
+    if (need_grad && g.ab) {
+        // symmetric two-pass form (fa_position_ab.cuh): D tiles j >= i -> loss, near-tie lists, sign planes; [exact signs: the
+        // resolve pass sets the bits of the near ties]; sign planes -> gradient contraction -> dX / dP
+        CUtensorMap tm_k, tm_v;
+        if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
+        if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
+        if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
+        if ((rc = opt_in_smem(fa_pos_dsign, g.half_smem_bytes))) return rc;
+        fa_pos_dsign<<<dim3(2 * g.a_units, 1, B), kThreads, g.half_smem_bytes, st>>>(tm_pm, tm_k, g, a);
+        DSRL_LAUNCH_CHECK();
+        if (g.exact && (rc = resolve())) return rc;
+        if ((rc = opt_in_smem(fa_pos_grad, g.b_smem_bytes))) return rc;
+        fa_pos_grad<<<grid, kThreads, g.b_smem_bytes, st>>>(tm_v, g, a);
+        DSRL_LAUNCH_CHECK();
+        if (g.raw_o && (rc = finish(a))) return rc;
+        return DSRL_OK;
+    }
     if (need_grad && g.pair && (!g.half || g.half_pair)) {
         // both channel groups have the same width when there are two (C1p == C2p) or the V box height would differ per group
         const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];

@@ -1,0 +1,419 @@
+// FA loss, position semantics: the SYMMETRIC TWO-PASS form of the FP16 tile engine (included by fa_position.cu inside
+// namespace dsrl { namespace { ... } }; it uses that file's geometry, argument structs, epilogue_finish and expand_signs).
+//
+// D = S1 - S2 is symmetric, and the gradient needs nothing of D but the SIGN of every entry.  So instead of one fused kernel
+// that computes every D tile next to the gradient accumulator it feeds (8 C N^2 executed FLOP per sample, and a cluster of
+// four CTAs at C = 256 because accumulator + D tiles do not fit one SM's tensor memory -- only 132 of the 148 SMs can hold
+// clusters of four), the work is split into two tensor-bound passes over CTA pairs (clusters of two, every SM busy):
+//
+//   pass A  fa_pos_dsign   D(i, j) for the tiles j >= i only (2 C N^2): |D| sums (the loss, off-diagonal tiles counted twice),
+//                          near-tie lists (exact signs), and the sign / is-zero BITS of the tile written twice into the
+//                          "sign planes": as computed for block (i, j) and bit-transposed (32 x 32 warp butterflies) for
+//                          block (j, i).  Four D buffers in tensor memory (all 512 columns) decouple the MMA issuer from
+//                          the conversion warps.
+//   resolve fa_pos_resolve (exact signs) re-decides the listed near ties from the unrounded features and SETS THE BITS --
+//                          both (i, j) and (j, i) -- so no accumulator is ever corrected and no raw rows are kept.
+//   pass B  fa_pos_grad    O_i = sum_j sign(D_ij) Fh_j (4 C N^2): per column tile the conversion warps expand 4 KB of bits
+//                          into the packed FP16 sign tile in tensor memory (A-from-TMEM operand), the issuer runs the
+//                          gradient MMAs against the V_j boxes; normalisation Jacobian and dX / dP in the epilogue.
+//
+// Executed tensor work: 6 C N^2 per sample (4 for the gradient, 2 for the upper triangle of D) instead of 8.
+// Sign planes: per sample T x T blocks of 4 KB, block (I, J) = [column half h][row r] x 16 bytes {neg s0, zero s0, neg s1,
+// zero s1}: the sign and is-zero bits of row r of tile I against the two 32-column strips s of half h of tile J, bit e of a
+// word = entry 2e, bit 16 + e = entry 2e + 1 of the strip (the order expand_signs() wants).  N^2 / 4 bytes per sample
+// (268 MB at N = 32768), written once and read once per channel group; geometries whose planes would exceed the cap
+// fall back to the fused kernels (kSignPlaneCapBytes).
+
+constexpr size_t kSignBlock = kSignBlockBytes;       // bytes per (row tile, column tile)
+constexpr int kDBufs = 4;                            // pass A: D tiles in flight (4 x 128 tensor-memory columns)
+constexpr int kSBufs = 4;                            // pass B: packed sign tiles in flight (4 x 64 columns at kColS)
+constexpr uint32_t kColS = 256;
+
+// 32 x 32 bit transpose across a warp: lane l enters with row l, leaves with column l (bit b = row b's bit l)
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int k = 16 >> s;
+        const uint32_t m = s == 0 ? 0x0000ffffu : s == 1 ? 0x00ff00ffu : s == 2 ? 0x0f0f0f0fu : s == 3 ? 0x33333333u : 0x55555555u;   // bits b with (b & k) == 0
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+        x = (lane & k) ? ((x & ~m) | ((y >> k) & m)) : ((x & m) | ((y << k) & ~m));
+    }
+    return x;
+}
+// natural bit order (bit e = entry e) -> the paired order of the sign planes (bit e = entry 2e, bit 16 + e = entry 2e + 1)
+__device__ __forceinline__ uint32_t pair_order(uint32_t x) {
+    uint32_t ev = x & 0x55555555u, od = (x >> 1) & 0x55555555u;
+    ev = (ev | (ev >> 1)) & 0x33333333u; od = (od | (od >> 1)) & 0x33333333u;
+    ev = (ev | (ev >> 2)) & 0x0f0f0f0fu; od = (od | (od >> 2)) & 0x0f0f0f0fu;
+    ev = (ev | (ev >> 4)) & 0x00ff00ffu; od = (od | (od >> 4)) & 0x00ff00ffu;
+    ev = (ev | (ev >> 8)) & 0x0000ffffu; od = (od | (od >> 8)) & 0x0000ffffu;
+    return ev | (od << 16);
+}
+
+// work unit of pass A: (pair of row tiles p, column chunk) -- column tiles [2p + chunk * Lc, ... + Lc) of the rows [256 p, 256 p + 256)
+__host__ __device__ inline int dsign_chunks(int T, int Lc, int p) { return (T - 2 * p + Lc - 1) / Lc; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass A: upper-triangle D tiles -> loss, near-tie lists, sign planes
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const PosGeom g, const PosArgs a) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t raw = smem_u32(smraw);
+    unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
+    constexpr int kElems = 64;                                      // FP16 operand elements per 128-byte row
+    constexpr int kUnitBytes = kPairKBox;                           // this CTA's 64 rows of one 64-channel chunk of K_j
+    constexpr int kStageBytes = 4 * kPairKBox;
+    constexpr int kUPS = 4;
+    const int S = g.half_stages, nkc = g.nkh;
+    unsigned char *qreg = sm;
+    unsigned char *ring = sm + (size_t)nkc * kBoxBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
+    uint64_t *empty = full + S;
+    uint64_t *q_full = empty + S;
+    uint64_t *d_full = q_full + 1;          // [kDBufs]
+    uint64_t *d_empty = d_full + kDBufs;    // [kDBufs] (in the leader: the conversion warps of both CTAs have read the buffer)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_empty + kDBufs);
+    double *red = reinterpret_cast<double *>(d_empty + kDBufs + 1);
+    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int T = g.tiles, Lc = g.a_chunk, b = blockIdx.z;
+    int p = (int)(blockIdx.x >> 1), chunk = 0;
+    if (Lc < T) {                                                    // units are numbered pair by pair, chunk by chunk
+        int rem = p;
+        for (p = 0;; ++p) {
+            const int nch = dsign_chunks(T, Lc, p);
+            if (rem < nch) break;
+            rem -= nch;
+        }
+        chunk = rem;
+    }
+    const int itile = 2 * p + (int)rank;
+    const int jbeg = 2 * p + chunk * Lc, nt = min(Lc, T - jbeg);
+    const int row_q = b * g.Npad + itile * kTile;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_q);
+        prefetch_tmap(&tm_k);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < kDBufs; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 2 * kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
+    fence_before_sync();
+    cluster_sync();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    int slot = 0;
+    uint32_t ph = 0;
+#define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs, each for its own shared memory) =====================================
+        if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nkc * kBoxBytes);
+            for (int kc = 0; kc < nkc; ++kc) tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, kc * kElems, row_q);
+        }
+        __syncwarp();
+        for (int jj = 0; jj < nt; ++jj) {
+            const int row_k = b * g.Npad + (jbeg + jj) * kTile + (int)rank * (kTile / 2);     // this CTA's 64 rows of K_j
+            for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
+                const int nu = min(kUPS, nkc - kc0);
+                mbar_wait(&empty[slot], ph ^ 1, 31);
+                if (elect_one()) {
+                    unsigned char *dst = ring + (size_t)slot * kStageBytes;
+                    if (leader) mbar_arrive_expect_tx(&full[slot], 2u * (uint32_t)(nu * kUnitBytes));
+                    for (int u = 0; u < nu; ++u) tma_load_2d_pair(dst + (size_t)u * kUnitBytes, &tm_k, &full[slot], (kc0 + u) * kElems, row_k);
+                }
+                __syncwarp();
+                RING_ADVANCE();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================================
+        if (leader) {
+            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kStageDesc = kStageBytes >> 4, kUnitDesc = kUnitBytes >> 4;
+            const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
+            const uint32_t id_pos = idesc_f16(2 * kTile, kTile, false), id_neg = idesc_f16(2 * kTile, kTile, true);
+            const int q_neg = g.C1p / 16;                           // first K step (16 channels) of branch 2 (subtracted)
+            mbar_wait(q_full, 0, 32);
+            for (int jj = 0; jj < nt; ++jj) {
+                const int buf = jj & (kDBufs - 1);
+                const uint32_t dcol = tmem + (uint32_t)buf * kTile;
+                mbar_wait(&d_empty[buf], ((uint32_t)(jj / kDBufs) & 1u) ^ 1u, 33);      // the tile that used this buffer has been read
+                fence_after_sync();
+                for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
+                    mbar_wait(&full[slot], ph, 34);
+                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
+                    const int ss = slot;
+                    RING_ADVANCE();
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int u = 0; u < kUPS; ++u) {
+                            const int kc = kc0 + u;
+                            if (kc < nkc) {
+                                const uint64_t ad = q_desc + (uint64_t)kc * kBoxDesc, bd = sd + (uint64_t)u * kUnitDesc;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_f16_ss_pair(dcol, ad + 2 * ks, bd + 2 * ks, 4 * kc + ks >= q_neg ? id_neg : id_pos, (kc | ks) != 0);
+                            }
+                        }
+                        umma_commit_pair(&empty[ss]);
+                        if (kc0 + kUPS >= nkc) umma_commit_pair(&d_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===================================== conversion warps =====================================
+        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const bool listing = g.exact != 0;
+        const float tau = listing ? __ldg(a.tau + b) : 0.f;
+        const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * g.fnsub + (size_t)(2 * chunk + half);
+        uint4 *sb = a.sb + (size_t)b * T * T * (kSignBlock / 16);
+        const int tcol = lane < 16 ? 2 * lane : 2 * (lane - 16) + 1;      // the strip column whose transposed word this lane holds
+        unsigned nlisted = 0;
+        double acc = 0.0;
+        float facc = 0.f;
+        for (int jj = 0; jj < nt; ++jj) {
+            const int buf = jj & (kDBufs - 1), j = jbeg + jj;
+            mbar_wait(&d_full[buf], (uint32_t)(jj / kDBufs) & 1u, 35);
+            fence_after_sync();
+            const bool diag = j == itile, lower = j < itile;       // lower: tile (2p + 1, 2p), supplied by the transpose of (2p, 2p + 1)
+            float tsum = 0.f;
+            uint32_t w[4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int cg = 2 * half + s;
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + (uint32_t)(buf * kTile + cg * 32), v);
+                tmem_ld_wait();
+                if (s == 1) {                                      // both strips are in registers: the buffer may be overwritten
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&d_empty[buf]);
+                }
+                if (diag && cg == q) {                             // S_ii = 1 in both branches: a structural tie
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+                }
+                float zmin = 3.0e38f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = __uint_as_float(v[e]);
+                    tsum += fabsf(x);
+                    zmin = fminf(zmin, fabsf(x));
+                }
+                if (listing && !lower && zmin < tau) {
+                    // near ties of this strip, upper triangle only (the resolve pass sets both mirror bits); exact zeros keep sign 0
+                    uint32_t m = 0u, neg = 0u;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float ax = fabsf(__uint_as_float(v[e]));
+                        m |= (ax < tau && ax != 0.f) ? (1u << e) : 0u;
+                        neg |= (v[e] >> 31) << e;
+                    }
+                    if (diag) m = cg > q ? m : (cg == q ? (m & ~((2u << lane) - 1u)) : 0u);       // columns right of the diagonal
+                    while (m) {
+                        const int e = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (nlisted < (unsigned)g.fsub) a.fent[gsub * g.fsub + nlisted] = (uint32_t)(j * kTile + cg * 32 + e) | (((neg >> e) & 1u) << 31);
+                        ++nlisted;
+                    }
+                }
+                uint32_t M = 0u, Z = 0u;
+                if (zmin != 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) M = (M >> 1) | (__byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
+                        const uint32_t zz = ((lo & 0x7fffffffu) ? 0u : 0x8000u) | ((hi & 0x7fffffffu) ? 0u : 0x80000000u);
+                        M = (M >> 1) | (__byte_perm(lo, hi, 0x7632) & 0x80008000u & ~zz);
+                        Z = (Z >> 1) | zz;
+                    }
+                }
+                w[2 * s] = M; w[2 * s + 1] = Z;
+                if (!diag && !lower) {
+                    // block (j, itile): this warp's 32 rows are 32 columns there (quarter q -> half q / 2, strip q % 2)
+                    const uint32_t tn = pair_order(transpose32(M, lane));
+                    uint32_t tz = 0u;
+                    if (__any_sync(0xffffffffu, Z != 0u)) tz = pair_order(transpose32(Z, lane));
+                    uint2 *dst = reinterpret_cast<uint2 *>(sb + ((size_t)(j * T + itile) * 2 + (q >> 1)) * kTile + cg * 32 + tcol) + (q & 1);
+                    *dst = make_uint2(tn, tz);
+                }
+            }
+            if (!lower) sb[((size_t)(itile * T + j) * 2 + half) * kTile + r] = make_uint4(w[0], w[1], w[2], w[3]);
+            // tile sums gathered in FP32 over eight tiles before they enter the FP64 total (see epilogue_role)
+            facc += lower ? 0.f : (diag ? tsum : 2.f * tsum);
+            if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
+        }
+        acc += (double)facc;
+        if (listing) a.fcnt[gsub] = nlisted;
+        EpiCtx c;
+        c.d_full = d_full; c.p_full = nullptr; c.o_full = nullptr; c.red = red; c.flag = flag; c.proj = nullptr; c.tmem = tmem;
+        c.itile = itile; c.js = 0; c.grp = 0; c.b = b; c.j0 = jbeg; c.nt = nt; c.gN = 0; c.gbeg = 0; c.T = T;
+        c.part_index = (int)(blockIdx.z * gridDim.x + blockIdx.x);
+        c.nparts = (int)(gridDim.x * gridDim.z);
+        c.sub = 0; c.nsub = g.fnsub;
+        epilogue_finish<false, true>(g, a, c, acc);
+    }
+#undef RING_ADVANCE
+
+    fence_before_sync();
+    cluster_sync();                         // the leader's MMAs read the peer's shared / tensor memory until the very end
+    if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass B: sign planes -> gradient contraction -> normalisation Jacobian -> dX / dP (or raw partial rows, jsplit > 1)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t raw = smem_u32(smraw);
+    unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
+    constexpr int kElems = 64;
+    constexpr int kStageBytes = kBoxBytes;                          // one V box: this CTA's half of the group's channels x 64 positions
+    const int S = g.b_stages;
+    unsigned char *ring = sm;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
+    uint64_t *empty = full + S;
+    uint64_t *p_full = empty + S;           // [kSBufs] (in the leader: both CTAs' conversion warps have written the sign tile)
+    uint64_t *p_empty = p_full + kSBufs;    // [kSBufs] the gradient MMAs of the tile that used this buffer have completed
+    uint64_t *o_full = p_empty + kSBufs;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
+    double *red = reinterpret_cast<double *>(o_full + 2);
+    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
+    float *projbuf = reinterpret_cast<float *>(flag + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int T = g.tiles, js = blockIdx.x / T;
+    const int itile = blockIdx.x - js * T, grp = blockIdx.y, b = blockIdx.z;          // T is even: the pair shares js
+    const int nt = T / g.jsplit, j0 = js * nt;
+    const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], vrows = gN / 2;
+    const uint32_t vbytes = (uint32_t)vrows * 128u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_v);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < kSBufs; ++i) { mbar_init(&p_full[i], 2 * kEpiWarps); mbar_init(&p_empty[i], 1); }
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
+    fence_before_sync();
+    cluster_sync();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    int slot = 0;
+    uint32_t ph = 0;
+#define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
+
+    if (warp == 0) {
+        // ===================================== TMA producer: the V_j boxes =====================================
+        const int row_v = b * g.Kc + gbeg + (int)rank * vrows;                        // this CTA's half of the group's channels
+        for (int jj = 0; jj < nt; ++jj) {
+            for (int jc = 0; jc < 2; ++jc) {
+                mbar_wait(&empty[slot], ph ^ 1, 41);
+                if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(&full[slot], 2u * vbytes);
+                    tma_load_2d_pair(ring + (size_t)slot * kStageBytes, &tm_v, &full[slot], (j0 + jj) * kTile + jc * kElems, row_v);
+                }
+                __syncwarp();
+                RING_ADVANCE();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================================
+        if (leader) {
+            constexpr uint64_t kStageDesc = kStageBytes >> 4;
+            const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring));
+            const uint32_t id_g = idesc_f16(2 * kTile, gN, false);
+            for (int jj = 0; jj < nt; ++jj) {
+                const int buf = jj & (kSBufs - 1);
+                const uint32_t pcol = tmem + kColS + (uint32_t)buf * 64u;
+                mbar_wait(&p_full[buf], (uint32_t)(jj / kSBufs) & 1u, 42);
+                fence_after_sync();
+                for (int jc = 0; jc < 2; ++jc) {
+                    mbar_wait(&full[slot], ph, 43);
+                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
+                    const int ss = slot;
+                    RING_ADVANCE();
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_f16_ts_pair(tmem, pcol + (uint32_t)(jc * 32 + ks * 8), sd + 2 * ks, id_g, (jj | jc | ks) != 0);
+                        umma_commit_pair(&empty[ss]);
+                        if (jc == 1) umma_commit_pair(&p_empty[buf]);
+                        if (jc == 1 && jj == nt - 1) umma_commit_pair(o_full);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===================================== conversion warps: bits -> packed FP16 sign tiles =====================================
+        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        // this thread's 16 bytes of block (itile, j): consecutive column tiles are one block (4 KB) apart
+        const uint4 *src = a.sb + ((size_t)b * T * T + (size_t)itile * T + j0) * (kSignBlock / 16) + (size_t)half * kTile + r;
+        constexpr int kAhead = 3;                                      // loads in flight: ~3 tiles of MMA time cover an L2 / HBM round trip
+        uint4 pre[kAhead];
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) pre[i] = i < nt ? ldg_stream_u4(src + (size_t)i * (kSignBlock / 16)) : make_uint4(0u, 0u, 0u, 0u);
+        for (int jj = 0; jj < nt; ++jj) {
+            const int buf = jj & (kSBufs - 1);
+            const uint4 cur = pre[0];
+#pragma unroll
+            for (int i = 0; i + 1 < kAhead; ++i) pre[i] = pre[i + 1];
+            if (jj + kAhead < nt) pre[kAhead - 1] = ldg_stream_u4(src + (size_t)(jj + kAhead) * (kSignBlock / 16));
+            mbar_wait(&p_empty[buf], ((uint32_t)(jj / kSBufs) & 1u) ^ 1u, 44);
+            fence_after_sync();
+            uint32_t pk[16];
+            expand_signs(cur.x, cur.y, pk);
+            tmem_st16(tmem + lane_addr + kColS + (uint32_t)(buf * 64 + half * 32), pk);
+            expand_signs(cur.z, cur.w, pk);
+            tmem_st16(tmem + lane_addr + kColS + (uint32_t)(buf * 64 + half * 32 + 16), pk);
+            tmem_st_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&p_full[buf]);
+        }
+        EpiCtx c;
+        c.d_full = nullptr; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
+        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
+        c.part_index = -1;                   // the loss was finished by pass A
+        c.nparts = 0;
+        c.sub = 0; c.nsub = g.fnsub;
+        epilogue_finish<true, true>(g, a, c, 0.0);
+    }
+#undef RING_ADVANCE
+
+    fence_before_sync();
+    cluster_sync();
+    if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
+}
+
+// One entry of the sign planes set to an exactly known sign (resolve pass, one lane): entry (i, j) of a sample whose planes
+// start at `sbw`.  Integer atomics on different bits commute, so the planes are bit-repeatable.
+__device__ __forceinline__ void sign_plane_set(uint32_t *sbw, int T, int i, int j, int s) {
+    const size_t unit = ((size_t)((i >> 7) * T + (j >> 7)) * 2 + ((j >> 6) & 1)) * kTile + (i & 127);
+    uint32_t *w = sbw + unit * 4 + 2 * ((j >> 5) & 1);
+    const uint32_t bit = 1u << (((j & 31) >> 1) + 16 * (j & 1));
+    if (s < 0) atomicOr(w, bit); else atomicAnd(w, ~bit);
+    if (s == 0) atomicOr(w + 1, bit);
+}

@@ -46,9 +46,14 @@ _MODE = {"reference": _lib.FA_REFERENCE, "position": _lib.FA_POSITION}
 _size_cache = {}
 
 
+def _layout_hooks():
+    """Test / tuning hooks of the library that change the workspace layout (part of every size-cache key)."""
+    return tuple(os.environ.get(k) for k in ("DSRL_POS_JSPLIT", "DSRL_POS_AB", "DSRL_POS_ACHUNK", "DSRL_POS_QUAD", "DSRL_POS_PAIR"))
+
+
 def _sizes(mode, precision, B, C1, C2, H, W, k):
     geom = (mode, precision, B, C1, C2, H, W, k)
-    key = geom + (os.environ.get("DSRL_POS_JSPLIT"),)        # test hook that changes the workspace layout
+    key = geom + _layout_hooks()
     v = _size_cache.get(key)
     if v is None:
         L = _lib.lib()
@@ -196,7 +201,7 @@ class FALoss(torch.nn.modules.loss._Loss):
         return f"subsample_factor={self.subsample_factor}, reduction={self.reduction!r}, affinity={self.affinity!r}"
 
     def _scratch_of(self, dev, geom, saved_bytes, ws_bytes):
-        key = (dev, geom, os.environ.get("DSRL_POS_JSPLIT"))
+        key = (dev, geom) + _layout_hooks()
         sc = self._scratch.get(key)
         if sc is None or sc.saved_bytes != saved_bytes or sc.ws_bytes != ws_bytes:
             if len(self._scratch) >= 4:                       # a loss module sees one or two geometries; do not hoard

@@ -198,11 +198,47 @@ def test_column_split_variants_agree(jsplit, monkeypatch):
             assert st["dropped"] == 0, st
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 32, 64), (1, 64, 32, 32), (1, 200, 24, 40), (2, 19, 32, 32)])
+@pytest.mark.parametrize("exact", [True, False])
+def test_two_pass_form_matches_the_fused_kernels(shape, exact, monkeypatch):
+    """FP16 operands: the symmetric two-pass form (D tiles j >= i -> sign planes, transposed for the lower triangle -> gradient
+    pass; DSRL_POS_AB=1, the default) against the fused kernels that compute every D tile next to its accumulator
+    (DSRL_POS_AB=0).  Same loss to FP32 summation order; the sign tiles are the same bits (the tensor-core D is symmetric
+    bit for bit), so the gradients agree to accumulation order; the two-pass near-tie lists hold each unordered pair once."""
+    x1, x2 = pos_inputs(shape, shape, 11)
+    res = {}
+    for ab in ("1", "0"):
+        monkeypatch.setenv("DSRL_POS_AB", ab)
+        res[ab] = run(x1, x2, 1, "mean", precision="f16", exact=exact, stats=True)
+    (la, a1, a2, sa), (lb, b1, b2, sb) = res["1"], res["0"]
+    assert abs(la - lb) <= 1e-6 * abs(lb), (la, lb)
+    assert relnorm(a1, b1) <= 2e-6 and relnorm(a2, b2) <= 2e-6, (relnorm(a1, b1), relnorm(a2, b2))
+    if exact:
+        assert 2 * sa["listed"] == sb["listed"] and 2 * sa["corrected"] == sb["corrected"], (sa, sb)
+        assert sa["dropped"] == 0 and sb["dropped"] == 0
+
+
+@pytest.mark.parametrize("chunk", ["1", "3", "8"])
+def test_two_pass_column_chunks_agree(chunk, monkeypatch):
+    """Pass A may cut the column range of a pair of row tiles into chunks (small grids; DSRL_POS_ACHUNK forces the chunk
+    length in tiles): same loss, same gradients, no near tie lost between the per-chunk sub-lists."""
+    x1, x2 = pos_inputs((1, 200, 32, 32), (1, 200, 32, 32), 5)
+    ol, o1, o2 = fa_oracle.fa_position(x1, x2, 1, "mean")
+    base = run(x1, x2, 1, "mean", precision="f16", stats=True)
+    monkeypatch.setenv("DSRL_POS_ACHUNK", chunk)
+    loss, d1, d2, st = run(x1, x2, 1, "mean", precision="f16", stats=True)
+    assert abs(loss - ol) <= LOSS_RTOL * abs(ol), (loss, ol)
+    assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
+    assert st["dropped"] == 0 and st["listed"] == base[3]["listed"] and st["corrected"] == base[3]["corrected"], (st, base[3])
+    assert relnorm(d1, base[1]) <= 1e-6 and relnorm(d2, base[2]) <= 1e-6
+
+
 def test_cluster_of_four_matches_the_pair_kernel(monkeypatch):
-    """Two equal channel groups at FP16: the cluster-of-four kernel (each D tile computed once, signs shipped through
-    distributed shared memory) against the CTA-pair kernel that computes every D tile in both groups -- same loss to FP32
-    summation order, same gradients (the sign tiles are bit-identical), same near-tie lists."""
+    """Two equal channel groups at FP16, fused kernels (DSRL_POS_AB=0): the cluster-of-four kernel (each D tile computed
+    once, signs shipped through distributed shared memory) against the CTA-pair kernel that computes every D tile in both
+    groups -- same loss to FP32 summation order, same gradients (the sign tiles are bit-identical), same near-tie lists."""
     x1, x2 = pos_inputs((2, 256, 32, 64), (2, 256, 32, 64), 11)
+    monkeypatch.setenv("DSRL_POS_AB", "0")
     res = {}
     for quad in ("1", "0"):
         monkeypatch.setenv("DSRL_POS_QUAD", quad)
