@@ -203,8 +203,8 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     {
         // sub-lists per row: column half x column share (x 2 when the two channel groups split the column tiles between them);
         // expected N * 1.1e-3 / nsub entries each, room for 4x that + 16.  Two-pass form: column half x column chunk of pass A
-        // (upper triangle only, so a row holds at most what a full row would).
-        const int nsub = g.fnsub = g.ab ? 2 * ((g.tiles + g.a_chunk - 1) / g.a_chunk) : 2 * g.jsplit * (g.quad ? 2 : 1);
+        // (upper triangle only, so a row holds at most what a full row would): one sub-list per 32-column strip of a tile and chunk.
+        const int nsub = g.fnsub = g.ab ? 4 * ((g.tiles + g.a_chunk - 1) / g.a_chunk) : 2 * g.jsplit * (g.quad ? 2 : 1);
         g.fsub = (int)align_up((size_t)(N / (200 * nsub)) + 16, 8);
         if (g.fsub > 2048) g.fsub = 2048;
         g.fcap = g.fsub * nsub;
@@ -1641,15 +1641,15 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
     if (grow_ll >= (long long)g.B * g.Npad) return;
     const size_t grow = (size_t)grow_ll;
     const int b = (int)(grow / g.Npad), irow = (int)(grow - (size_t)b * g.Npad);
-    const int nsub = g.fnsub;                     // <= 16
+    const int nsub = g.fnsub;                     // <= 32
     // this row's sub-lists (lane s holds the count of sub-list s) as one sequence of n entries; two-pass form: only the column
     // chunks that exist for the row's pair of tiles were written
-    const int nsub_row = kBits ? 2 * dsign_chunks(g.tiles, g.a_chunk, irow / (2 * kTile)) : nsub;
+    const int nsub_row = kBits ? 4 * dsign_chunks(g.tiles, g.a_chunk, irow / (2 * kTile)) : nsub;
     const unsigned cnt_s = lane < nsub_row ? ex.fcnt[grow * nsub + lane] : 0u;
     const unsigned len_s = min(cnt_s, (unsigned)g.fsub);
     unsigned end_s = len_s;                       // inclusive prefix sum over the sub-lists
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, end_s, o); if (lane >= o) end_s += t; }
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, end_s, o); if (lane >= o) end_s += t; }
     const int n = (int)__shfl_sync(0xffffffffu, end_s, nsub - 1);
     const unsigned listed = (unsigned)warp_sum((int)cnt_s);
     if (listed == 0) return;
@@ -2111,7 +2111,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
         if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
         if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
         if ((rc = opt_in_smem(fa_pos_dsign, g.half_smem_bytes))) return rc;
-        fa_pos_dsign<<<dim3(2 * g.a_units, 1, B), kThreads, g.half_smem_bytes, st>>>(tm_pm, tm_k, g, a);
+        fa_pos_dsign<<<dim3(2 * g.a_units, 1, B), kDsignThreads, g.half_smem_bytes, st>>>(tm_pm, tm_k, g, a);
         DSRL_LAUNCH_CHECK();
         if (g.exact && (rc = resolve())) return rc;
         if ((rc = opt_in_smem(fa_pos_grad, g.b_smem_bytes))) return rc;

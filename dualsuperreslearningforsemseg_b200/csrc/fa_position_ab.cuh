@@ -28,6 +28,9 @@ constexpr size_t kSignBlock = kSignBlockBytes;       // bytes per (row tile, col
 constexpr int kDBufs = 4;                            // pass A: D tiles in flight (4 x 128 tensor-memory columns)
 constexpr int kSBufs = 4;                            // pass B: packed sign tiles in flight (4 x 64 columns at kColS)
 constexpr uint32_t kColS = 256;
+constexpr int kDsignEpiWarps = 16;                   // pass A: one conversion warp per (lane quarter, 32-column strip)
+constexpr int kDsignEpiThreads = kDsignEpiWarps * 32;
+constexpr int kDsignThreads = 64 + kDsignEpiThreads;
 
 // 32 x 32 bit transpose across a warp: lane l enters with row l, leaves with column l (bit b = row b's bit l)
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
@@ -56,7 +59,7 @@ __host__ __device__ inline int dsign_chunks(int T, int Lc, int p) { return (T - 
 // ---------------------------------------------------------------------------------------------------------------
 // pass A: upper-triangle D tiles -> loss, near-tie lists, sign planes
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDsignThreads, 1)
 fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const PosGeom g, const PosArgs a) {
     extern __shared__ unsigned char smraw[];
     const uint32_t raw = smem_u32(smraw);
@@ -75,7 +78,7 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     uint64_t *d_empty = d_full + kDBufs;    // [kDBufs] (in the leader: the conversion warps of both CTAs have read the buffer)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_empty + kDBufs);
     double *red = reinterpret_cast<double *>(d_empty + kDBufs + 1);
-    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
+    int *flag = reinterpret_cast<int *>(red + 2 * kDsignEpiWarps);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -100,7 +103,7 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         prefetch_tmap(&tm_k);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(q_full, 1);
-        for (int i = 0; i < kDBufs; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 2 * kEpiWarps); }
+        for (int i = 0; i < kDBufs; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 2 * kDsignEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
@@ -173,11 +176,14 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         }
     } else {
         // ===================================== conversion warps =====================================
-        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+        // Sixteen warps, one per (TMEM lane quarter q, 32-column strip cg) of a tile: the conversion is a chain of dependent
+        // short instructions, so what bounds it is the latency of one warp's chain per tile, not the issue slots -- eight warps
+        // converting two strips each ran pass A at 49 % of the tensor peak (ncu r02c), about 960 instructions per warp and tile.
+        const int q = warp & 3, r = q * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const bool listing = g.exact != 0;
         const float tau = listing ? __ldg(a.tau + b) : 0.f;
-        const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * g.fnsub + (size_t)(2 * chunk + half);
+        const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * g.fnsub + (size_t)(4 * chunk + cg);
         uint4 *sb = a.sb + (size_t)b * T * T * (kSignBlock / 16);
         const int tcol = lane < 16 ? 2 * lane : 2 * (lane - 16) + 1;      // the strip column whose transposed word this lane holds
         unsigned nlisted = 0;
@@ -188,84 +194,108 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             mbar_wait(&d_full[buf], (uint32_t)(jj / kDBufs) & 1u, 35);
             fence_after_sync();
             const bool diag = j == itile, lower = j < itile;       // lower: tile (2p + 1, 2p), supplied by the transpose of (2p, 2p + 1)
-            float tsum = 0.f;
-            uint32_t w[4];
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_addr + (uint32_t)(buf * kTile + cg * 32), v);
+            tmem_ld_wait();
+            fence_before_sync();                                   // the strip is in registers: the buffer may be overwritten
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&d_empty[buf]);
+            if (lower) continue;                                   // warp-uniform
+            if (diag && cg == q) {                                 // S_ii = 1 in both branches: a structural tie
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int cg = 2 * half + s;
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + (uint32_t)(buf * kTile + cg * 32), v);
-                tmem_ld_wait();
-                if (s == 1) {                                      // both strips are in registers: the buffer may be overwritten
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&d_empty[buf]);
+                for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+            }
+            float tsum = 0.f, zmin = 3.0e38f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float x = __uint_as_float(v[e]);
+                tsum += fabsf(x);
+                zmin = fminf(zmin, fabsf(x));
+            }
+            // sign / is-zero words in the paired order (bit e = entry 2e, bit 16 + e = entry 2e + 1): one funnel shift per entry
+            // pushes its sign bit into the word of its parity
+            uint32_t M, Z = 0u;
+            {
+                uint32_t ev = 0u, od = 0u;
+#pragma unroll
+                for (int e = 15; e >= 0; --e) { ev = __funnelshift_l(v[2 * e], ev, 1); od = __funnelshift_l(v[2 * e + 1], od, 1); }
+                M = ev | (od << 16);
+            }
+            if (zmin == 0.f) {                                     // exact zeros (the forced diagonal, padding, identical branches): sign 0
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    Z |= ((v[2 * e] & 0x7fffffffu) ? 0u : (1u << e)) | ((v[2 * e + 1] & 0x7fffffffu) ? 0u : (1u << (16 + e)));
+                M &= ~Z;
+            }
+            if (listing && zmin < tau) {
+                // near ties of this strip, upper triangle only (the resolve pass sets both mirror bits); exact zeros keep sign 0.
+                // A warp takes this path when ANY of its rows has a near tie in the strip (about 70 % of the strips at 3.5 sigma),
+                // so the scan is two instructions per entry: a compare that yields all ones, funnel-shifted into the mask.
+                uint32_t m = 0u;
+#pragma unroll
+                for (int e = 31; e >= 0; --e) {
+                    uint32_t c;
+                    asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(c) : "f"(fabsf(__uint_as_float(v[e]))), "f"(tau));
+                    m = __funnelshift_l(c, m, 1);                  // entry e ends at bit e
                 }
-                if (diag && cg == q) {                             // S_ii = 1 in both branches: a structural tie
+                if (zmin == 0.f) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
+                    for (int e = 0; e < 32; ++e) m &= (v[e] & 0x7fffffffu) ? 0xffffffffu : ~(1u << e);
                 }
-                float zmin = 3.0e38f;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float x = __uint_as_float(v[e]);
-                    tsum += fabsf(x);
-                    zmin = fminf(zmin, fabsf(x));
-                }
-                if (listing && !lower && zmin < tau) {
-                    // near ties of this strip, upper triangle only (the resolve pass sets both mirror bits); exact zeros keep sign 0
-                    uint32_t m = 0u, neg = 0u;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float ax = fabsf(__uint_as_float(v[e]));
-                        m |= (ax < tau && ax != 0.f) ? (1u << e) : 0u;
-                        neg |= (v[e] >> 31) << e;
-                    }
-                    if (diag) m = cg > q ? m : (cg == q ? (m & ~((2u << lane) - 1u)) : 0u);       // columns right of the diagonal
-                    while (m) {
-                        const int e = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (nlisted < (unsigned)g.fsub) a.fent[gsub * g.fsub + nlisted] = (uint32_t)(j * kTile + cg * 32 + e) | (((neg >> e) & 1u) << 31);
-                        ++nlisted;
-                    }
-                }
-                uint32_t M = 0u, Z = 0u;
-                if (zmin != 0.f) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) M = (M >> 1) | (__byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
-                        const uint32_t zz = ((lo & 0x7fffffffu) ? 0u : 0x8000u) | ((hi & 0x7fffffffu) ? 0u : 0x80000000u);
-                        M = (M >> 1) | (__byte_perm(lo, hi, 0x7632) & 0x80008000u & ~zz);
-                        Z = (Z >> 1) | zz;
-                    }
-                }
-                w[2 * s] = M; w[2 * s + 1] = Z;
-                if (!diag && !lower) {
-                    // block (j, itile): this warp's 32 rows are 32 columns there (quarter q -> half q / 2, strip q % 2)
-                    const uint32_t tn = pair_order(transpose32(M, lane));
-                    uint32_t tz = 0u;
-                    if (__any_sync(0xffffffffu, Z != 0u)) tz = pair_order(transpose32(Z, lane));
-                    uint2 *dst = reinterpret_cast<uint2 *>(sb + ((size_t)(j * T + itile) * 2 + (q >> 1)) * kTile + cg * 32 + tcol) + (q & 1);
-                    *dst = make_uint2(tn, tz);
+                if (diag) m = cg > q ? m : (cg == q ? (m & ~((2u << lane) - 1u)) : 0u);       // columns right of the diagonal
+                while (m) {
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t ng = (M >> ((e >> 1) + ((e & 1) << 4))) & 1u;
+                    if (nlisted < (unsigned)g.fsub) a.fent[gsub * g.fsub + nlisted] = (uint32_t)(j * kTile + cg * 32 + e) | (ng << 31);
+                    ++nlisted;
                 }
             }
-            if (!lower) sb[((size_t)(itile * T + j) * 2 + half) * kTile + r] = make_uint4(w[0], w[1], w[2], w[3]);
+            // block (itile, j): this thread's row, its strip's two words
+            *(reinterpret_cast<uint2 *>(sb + ((size_t)(itile * T + j) * 2 + (cg >> 1)) * kTile + r) + (cg & 1)) = make_uint2(M, Z);
+            if (!diag) {
+                // block (j, itile): this warp's 32 rows are 32 columns there (quarter q -> half q / 2, strip q % 2)
+                const uint32_t tn = pair_order(transpose32(M, lane));
+                uint32_t tz = 0u;
+                if (__any_sync(0xffffffffu, Z != 0u)) tz = pair_order(transpose32(Z, lane));
+                *(reinterpret_cast<uint2 *>(sb + ((size_t)(j * T + itile) * 2 + (q >> 1)) * kTile + cg * 32 + tcol) + (q & 1)) = make_uint2(tn, tz);
+            }
             // tile sums gathered in FP32 over eight tiles before they enter the FP64 total (see epilogue_role)
-            facc += lower ? 0.f : (diag ? tsum : 2.f * tsum);
+            facc += diag ? tsum : 2.f * tsum;
             if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
         }
         acc += (double)facc;
         if (listing) a.fcnt[gsub] = nlisted;
-        EpiCtx c;
-        c.d_full = d_full; c.p_full = nullptr; c.o_full = nullptr; c.red = red; c.flag = flag; c.proj = nullptr; c.tmem = tmem;
-        c.itile = itile; c.js = 0; c.grp = 0; c.b = b; c.j0 = jbeg; c.nt = nt; c.gN = 0; c.gbeg = 0; c.T = T;
-        c.part_index = (int)(blockIdx.z * gridDim.x + blockIdx.x);
-        c.nparts = (int)(gridDim.x * gridDim.z);
-        c.sub = 0; c.nsub = g.fnsub;
-        epilogue_finish<false, true>(g, a, c, acc);
+        // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
+        {
+            const int et = threadIdx.x - 64;
+            const int part_index = (int)(blockIdx.z * gridDim.x + blockIdx.x), nparts = (int)(gridDim.x * gridDim.z);
+            const double tot = warp_sum(acc);
+            if (lane == 0) red[et >> 5] = tot;
+            asm volatile("bar.sync 1, %0;" ::"n"(kDsignEpiThreads) : "memory");
+            if (et == 0) {
+                double sum = 0.0;
+                for (int i = 0; i < kDsignEpiWarps; ++i) sum += red[i];
+                a.partials[part_index] = sum;
+                __threadfence();
+                *flag = atomicInc(a.ticket, (unsigned)nparts - 1u) == (unsigned)nparts - 1u;      // self-resetting
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDsignEpiThreads) : "memory");
+            if (*flag) {
+                __threadfence();
+                double sum = 0.0;
+                for (int i = et; i < nparts; i += kDsignEpiThreads) sum += __ldcg(a.partials + i);
+                sum = warp_sum(sum);
+                if (lane == 0) red[kDsignEpiWarps + (et >> 5)] = sum;
+                asm volatile("bar.sync 1, %0;" ::"n"(kDsignEpiThreads) : "memory");
+                if (et == 0) {
+                    double all = 0.0;
+                    for (int i = 0; i < kDsignEpiWarps; ++i) all += red[kDsignEpiWarps + i];
+                    *a.sum_out = all;
+                    *a.loss_out = (float)(all / a.loss_div);
+                }
+            }
+        }
     }
 #undef RING_ADVANCE
 
