@@ -708,8 +708,8 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     n0 = _lib.launch_count()
     step()
     launches_per_step = _lib.launch_count() - n0
-    # L2: one step streams 2 x 268 MB of features per 128-row tile pass (>> 126 MB L2) and ends by writing 0.5 GB of
-    # gradients, so no step starts with a warm L2; no explicit flush.
+    # L2: one step writes and re-reads 2.1 GB of sign planes, streams 2 x 268 MB of features per pass (>> 126 MB L2) and ends by
+    # writing 0.5 GB of gradients, so no step starts with a warm L2; no explicit flush.
     with ClockSampler(dev.index) as clk:
         ms = timed_steps(step, steps, warmup, world, flush=None)
     ms = max_over_ranks(ms, world, dev)
@@ -718,16 +718,24 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     stats = plan.sign_stats() if exact else None
     pairs_total = STRESS_B * N * N
     alg_flops_rank = 12.0 * b_local * C * N * N                   # fwd 4CN^2 + recompute 4CN^2 + two gradient GEMMs 4CN^2
-    min_flops_rank = 8.0 * b_local * C * N * N                    # one fused pass: D once (4CN^2) + the gradient contraction (4CN^2)
     kc = 2 * ((C + 31) // 32 * 32)
-    # executed: D is computed once per row tile except by the TF32 kernels with two channel groups (Kc > 256), which
-    # compute it in both; the FP16 form splits the D tiles between the two groups' CTA pairs (fa_pos_tiles_quad)
-    d_passes = 2 if (kc > 256 and precision != "f16") else 1
-    exec_flops_rank = (2.0 * kc * d_passes + 2.0 * kc) * b_local * N * N
+    tiles = (N + 127) // 128
+    two_pass = precision == "f16" and tiles % 2 == 0              # the symmetric two-pass form (csrc/fa_position_ab.cuh)
+    # minimal tensor work: the gradient contraction (4CN^2) + D once -- all of it for a fused pass (4CN^2), its upper triangle
+    # when the symmetry D_ij = D_ji is used (2CN^2)
+    min_flops_rank = (6.0 if two_pass else 8.0) * b_local * C * N * N
+    if two_pass:
+        # executed: pass A computes the tiles j >= 2p of every pair of row tiles (T^2/2 + T of the T^2 tiles), pass B the whole
+        # gradient contraction
+        exec_flops_rank = (2.0 * kc * (0.5 + 1.0 / tiles) + 2.0 * kc) * b_local * N * N
+        kernels = "fa_pos_pack, " + ("fa_pos_tau, " if exact else "") + "fa_pos_dsign, " + ("fa_pos_resolve, " if exact else "") + "fa_pos_grad"
+    else:
+        # fused kernels: D is computed once per row tile except by the TF32 kernels with two channel groups (Kc > 256), which
+        # compute it in both
+        d_passes = 2 if (kc > 256 and precision != "f16") else 1
+        exec_flops_rank = (2.0 * kc * d_passes + 2.0 * kc) * b_local * N * N
+        kernels = ("fa_pos_pack, " + ("fa_pos_tau, " if exact else "") + "fa_pos_tiles_pair" + (", fa_pos_resolve, fa_pos_finish" if exact else ""))
     achieved = alg_flops_rank / (step_ms * 1e-3) / 1e12
-    kernels = ("fa_pos_pack, " + ("fa_pos_tau, " if exact else "") +
-               ("fa_pos_tiles_quad" if (precision == "f16" and kc > 256) else "fa_pos_tiles_pair") +
-               (", fa_pos_resolve, fa_pos_finish" if exact else ""))
 
     res = {
         "metric": "fa_fwd_bwd_gpairs_per_s", "unit": "Gpairs/s",
@@ -742,7 +750,7 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
                    "sign_resolution": ("every entry of S1 - S2 whose tensor-core value lies within ~3.5 sigma of the operand-rounding error is "
                                        "re-decided from the unrounded features (FP32 with a rigorous bound, FP64 below it) inside the timed step"
                                        if exact else "none: the signs of S1 - S2 are taken from the tensor-core values (flip-limited gradient)"),
-                   "l2": "working set per step (1.6 GB per sample) larger than L2, no flush",
+                   "l2": "working set per step (features, gradients and sign planes: ~0.5 GB per sample) larger than L2, no flush",
                    "parallelism": f"dp{world} (batch shard, no data-path collective" +
                                   ("; the 8-byte mean-loss all-reduce over NCCL, distributed.all_reduce_mean_loss, is inside the timed step)" if world > 1 else ")"),
                    "loss": loss_global},
@@ -752,12 +760,16 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
                      "peak_source": peaks["source"] + (" dense bf16 burst (kind::f16 runs at the bf16 hardware rate)" if precision == "f16" else
                                                        " dense bf16 burst; the kernel runs kind::tf32, whose hardware rate is half of bf16"),
                      "algorithmic_flops_per_step_per_gpu": alg_flops_rank,
-                     "note": "achieved / frac use SURVEY 8d's algorithmic count 12*B*C*N^2 (forward, recompute, two gradient GEMMs); the kernel "
-                             "executes the minimal fused pass, so the fraction of the tensor peak it actually occupies is frac_minimal_work",
+                     "note": "achieved / frac use SURVEY 8d's algorithmic count 12*B*C*N^2 (forward, recompute, two gradient GEMMs; dense, no "
+                             "symmetry credit) as the contract prescribes, so frac may exceed 1: the kernels EXECUTE " +
+                             ("about 6*B*C*N^2 -- D = S1 - S2 is computed once and only for the tiles j >= i (its signs are stored as bit planes and "
+                              "reused transposed), then the gradient contraction. " if two_pass else "8*B*C*N^2 or more (one fused pass). ") +
+                             "The share of the tensor peak the kernels actually occupy is executed_tflops / peak = frac_executed",
                      "minimal_flops_per_step_per_gpu": min_flops_rank,
                      "frac_minimal_work": min_flops_rank / (step_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
                      "executed_tensor_flops_per_step_per_gpu": exec_flops_rank,
                      "executed_tflops": exec_flops_rank / (step_ms * 1e-3) / 1e12,
+                     "frac_executed": exec_flops_rank / (step_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
                      "kernel": f"{kernels} (one step = {launches_per_step} launches, timed together)"},
         "gpu_launches": int(sum_over_ranks(launches_per_step * steps, world, dev)),
         "clocks": clk.summary(),

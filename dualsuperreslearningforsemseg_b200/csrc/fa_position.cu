@@ -602,7 +602,11 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
     const float tau = listing ? __ldg(a.tau + b) : 0.f;                    // 0: nothing is ever listed
     const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * c.nsub + (size_t)(c.sub + half);
     unsigned nlisted = 0;
-    for (int jj = 0; jj < nt; ++jj) {
+    // (the FP64 add of the tile sums sits in an outer loop: as `if ((jj & 7) == 7)` the compiler predicates it into a DADD per tile)
+    for (int jj0 = 0; jj0 < nt; jj0 += 8) {
+    const int jj1 = min(jj0 + 8, nt);
+#pragma unroll 1
+    for (int jj = jj0; jj < jj1; ++jj) {
         const int buf = jj & 1, j = j0 + jj;
         TWAIT(w_d, mbar_wait(&d_full[buf], (jj >> 1) & 1, 3));
         fence_after_sync();
@@ -680,9 +684,10 @@ __device__ __forceinline__ void epilogue_role(const PosGeom &g, const PosArgs &a
         // tile sums are gathered in FP32 over eight tiles (<= 2 * 64 * 8 per thread: rounding ~1e-7 of the running sum) before
         // they enter the FP64 total -- a DADD per tile was a quarter of the epilogue warps' stall samples (FP64 pipe)
         facc += (kGrad || diag) ? tsum : 2.f * tsum;
-        if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
     }
     acc += (double)facc;
+    facc = 0.f;
+    }
     if (listing) a.fcnt[gsub] = nlisted;
 #ifdef DSRL_POS_TIMING
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
@@ -1457,7 +1462,10 @@ fa_pos_tiles_quad(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         float facc = 0.f;
         long long w_d = 0, w_xe = 0, t_conv = 0, t_ship = 0;
         const long long t_begin = clock64();
-        for (int k = 0; k < nr; ++k) {
+        for (int k0 = 0; k0 < nr; k0 += 8) {
+        const int k1 = min(k0 + 8, nr);
+#pragma unroll 1
+        for (int k = k0; k < k1; ++k) {
             const int buf = k & 1, j = j0 + 2 * k + grp;
             const uint32_t php = (uint32_t)(k >> 1) & 1u;
             TWAIT(w_d, mbar_wait(&d_full[buf], php, 26));
@@ -1536,12 +1544,13 @@ fa_pos_tiles_quad(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 mbar_arrive(&c_done[buf]);
             }
             facc += tsum;
-            if ((k & 7) == 7) { acc += (double)facc; facc = 0.f; }
 #ifdef DSRL_POS_TIMING
             t_ship += clock64() - t2;
 #endif
         }
         acc += (double)facc;
+        facc = 0.f;
+        }
         if (g.exact) a.fcnt[gsub] = nlisted;
 #ifdef DSRL_POS_TIMING
         if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 64) {

@@ -189,7 +189,13 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         unsigned nlisted = 0;
         double acc = 0.0;
         float facc = 0.f;
-        for (int jj = 0; jj < nt; ++jj) {
+        // tile sums are gathered in FP32 over eight tiles before they enter the FP64 total.  The FP64 add sits in an OUTER loop:
+        // written as `if ((jj & 7) == 7) acc += facc` the compiler predicates it and issues a DADD per tile and warp, which
+        // was the top stall of this kernel (FP64 pipe, ncu r02d: 13 % of the samples)
+        for (int jj0 = 0; jj0 < nt; jj0 += 8) {
+        const int jj1 = min(jj0 + 8, nt);
+#pragma unroll 1
+        for (int jj = jj0; jj < jj1; ++jj) {
             const int buf = jj & (kDBufs - 1), j = jbeg + jj;
             mbar_wait(&d_full[buf], (uint32_t)(jj / kDBufs) & 1u, 35);
             fence_after_sync();
@@ -260,11 +266,11 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 if (__any_sync(0xffffffffu, Z != 0u)) tz = pair_order(transpose32(Z, lane));
                 *(reinterpret_cast<uint2 *>(sb + ((size_t)(j * T + itile) * 2 + (q >> 1)) * kTile + cg * 32 + tcol) + (q & 1)) = make_uint2(tn, tz);
             }
-            // tile sums gathered in FP32 over eight tiles before they enter the FP64 total (see epilogue_role)
             facc += diag ? tsum : 2.f * tsum;
-            if ((jj & 7) == 7) { acc += (double)facc; facc = 0.f; }
         }
         acc += (double)facc;
+        facc = 0.f;
+        }
         if (listing) a.fcnt[gsub] = nlisted;
         // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
         {

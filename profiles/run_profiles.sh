@@ -15,10 +15,11 @@ CMD="python bench.py --workload fa_stress --steps 2 --warmup 3 --no-extra"
 $CMD > $OUT/${TAG}_fa_stress_plain.log 2>&1 &&
 $NCU --metrics gpu__time_duration.sum -k regex:"fa_pos|fa_ref|seg_counts" -c 60 --csv --log-file $OUT/${TAG}_fa_stress_launches.csv $CMD > $OUT/${TAG}_fa_stress_ncu.log 2>&1
 $CMD > /dev/null 2>&1 &&
-$NCU --set full --import-source on -k regex:fa_pos_tiles -s 3 -c 1 -f -o $OUT/${TAG}_fa_stress_full $CMD > $OUT/${TAG}_fa_stress_full.log 2>&1
-# the exact-sign passes around the tile engine (round 2): near-tie resolve (L2 gather bound) and the finish pass (HBM bound)
+# the dominant kernel: the gradient pass of the two-pass form (fa_pos_grad; fa_pos_tiles* when a fused kernel runs instead)
+$NCU --set full --import-source on -k regex:"fa_pos_grad|fa_pos_tiles" -s 3 -c 1 -f -o $OUT/${TAG}_fa_stress_full $CMD > $OUT/${TAG}_fa_stress_full.log 2>&1
+# the other kernels of the step: pass A (upper-triangle D tiles -> sign planes) and the near-tie resolve (L2 gather bound)
+$NCU --set full --import-source on -k regex:fa_pos_dsign -s 3 -c 1 -f -o $OUT/${TAG}_fa_dsign_full $CMD > $OUT/${TAG}_fa_dsign_full.log 2>&1
 $NCU --set full --import-source on -k regex:fa_pos_resolve -s 3 -c 1 -f -o $OUT/${TAG}_fa_resolve_full $CMD > $OUT/${TAG}_fa_resolve_full.log 2>&1
-$NCU --set full --import-source on -k regex:fa_pos_finish -s 3 -c 1 -f -o $OUT/${TAG}_fa_finish_full $CMD > $OUT/${TAG}_fa_finish_full.log 2>&1
 fi
 
 # ---- seg_counts (BASELINE configs[2])
