@@ -78,6 +78,8 @@ struct PosGeom {
     int raw_o;                    // the tile kernel stores raw accumulator rows, fa_pos_finish completes them (jsplit > 1 or exact)
     int ab;                       // FP16 form as two symmetric passes (fa_position_ab.cuh): D tiles j >= i -> sign planes -> gradient
     int a_chunk, a_units;         // pass A: column tiles per work unit (tiles: no split), work units per sample
+    int a_stages;                 // pass A: depth of the K ring (stages of four 64-channel chunks of this CTA's 64 rows = 32 KB)
+    size_t a_smem_bytes;
     int b_stages;                 // pass B: depth of the V ring
     size_t b_smem_bytes, sb_bytes;   // pass B shared memory; sign planes of all samples
     size_t smem_bytes, pair_smem_bytes, half_smem_bytes, half1_smem_bytes;
@@ -178,7 +180,9 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
     // planes (N^2 / 4 bytes per sample) stay below the cap
     {
         g.sb_bytes = (size_t)B * g.tiles * g.tiles * kSignBlockBytes;
-        g.ab = g.half_pair && g.sb_bytes <= kSignPlaneCapBytes;
+        // (with tensor-core signs and few channels both passes are bound by their conversion warps and the fused pair kernel,
+        // which converts every tile once, is ahead: 3.0 vs 3.5 ms at C = 32 per branch, batch 8)
+        g.ab = g.half_pair && g.sb_bytes <= kSignPlaneCapBytes && (exact || g.Kc > 128);
         if (const char *e = getenv("DSRL_POS_AB")) { if (atoi(e) == 0) g.ab = 0; }
         if (!g.ab) g.sb_bytes = 0;
         // pass A: a pair of row tiles against its column tiles j >= 2p is one work unit when there are plenty of them; small
@@ -192,9 +196,16 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         }
         g.a_units = 0;
         for (int p = 0; p < g.tiles / 2; ++p) g.a_units += (g.tiles - 2 * p + g.a_chunk - 1) / g.a_chunk;
-        g.b_stages = (int)((kSmemBudget - 1024 - kSmemAux) / kBoxBytes);
-        if (g.b_stages > 12) g.b_stages = 12;
-        g.b_smem_bytes = 1024 + (size_t)g.b_stages * kBoxBytes + kSmemAux;
+        {
+            const long long room = (long long)kSmemBudget - 1024 - (long long)kSmemAux - (long long)g.nkh * kBoxBytes;
+            g.a_stages = room > 0 ? (int)(room / (2 * kBoxBytes)) : 0;
+            if (g.a_stages > 6) g.a_stages = 6;
+            g.a_smem_bytes = 1024 + (size_t)g.nkh * kBoxBytes + (size_t)g.a_stages * 2 * kBoxBytes + kSmemAux;
+            if (g.a_smem_bytes < kOneCtaSmem) g.a_smem_bytes = kOneCtaSmem;
+            if (g.a_stages < 2) { g.ab = 0; g.sb_bytes = 0; }
+        }
+        g.b_stages = 8;                                           // 8 x 16 KB V boxes (4 tiles of MMA time ahead) + 4 boxes of own feature rows
+        g.b_smem_bytes = 1024 + (size_t)(g.b_stages + 4) * kBoxBytes + 6144;      // barriers, reduction scratch, projection parts [4][2][128]
         if (g.ab) g.quad = 0;
     }
     // exact signs: about 1e-3 of a row's entries are near ties (|D| below ~3.5 sigma of the operand-rounding error, whatever
@@ -440,6 +451,8 @@ struct PosArgs {
 // accumulator (normalisation Jacobian, or the raw partial rows when the column range is split); finally the loss.
 // kPair: the barrier the MMA issuer waits on lives in the leader CTA of the pair.
 struct EpiCtx {
+    const unsigned char *fsm = nullptr;   // FP16 form: the CTA's own feature rows of its channel group in shared memory (TMA boxes of 128 rows
+                                          // x 64 channels, 128-byte swizzle), or nullptr: read them from global memory
     uint64_t *d_full, *p_full, *o_full;
     double *red;          // [16]
     int *flag;
@@ -450,6 +463,13 @@ struct EpiCtx {
     int sub, nsub;              // exact signs: this CTA's sub-list pair (sub + column half) among a row's nsub sub-lists
 };
 
+// four consecutive channels (cl = channel - first channel of the group, a multiple of 4) of row r from the swizzled boxes
+__device__ __forceinline__ float4 load_f4_smem(const unsigned char *fsm, int r, int cl) {
+    const int box = cl >> 6, k = (cl & 63) >> 3;                     // 16-byte chunk k of the 128-byte row, stored at chunk k ^ (r & 7)
+    const uint2 q = *reinterpret_cast<const uint2 *>(fsm + (size_t)box * kBoxBytes + r * 128 + ((k ^ (r & 7)) << 4) + ((cl & 4) << 1));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&q.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 // four consecutive channels of the normalised feature row at channel c (fp32 copy, or the FP16 copy of the FP16 form)
 template <bool kHalf>
 __device__ __forceinline__ float4 load_f4(const float *frow, const __half *frow_h, int c) {
@@ -489,8 +509,15 @@ __device__ __forceinline__ void epilogue_finish(const PosGeom &g, const PosArgs 
         }
     } else if (kGrad) {
         // normalisation Jacobian of the gradient accumulator, stored channel-major (coalesced along positions)
+#ifdef DSRL_POS_TIMING
+        const long long te0 = clock64();
+#endif
         mbar_wait(o_full, 0, 7);
         fence_after_sync();
+#ifdef DSRL_POS_TIMING
+        const long long te1 = clock64();
+        long long te2 = 0;
+#endif
         const int row = itile * kTile + r;
         const float *frow = a.Fpm + ((size_t)b * g.Npad + row) * g.Kc;
         const __half *frow_h = a.FpmH + ((size_t)b * g.Npad + row) * g.Kc;
@@ -506,13 +533,16 @@ __device__ __forceinline__ void epilogue_finish(const PosGeom &g, const PosArgs 
                 tmem_ld_wait();
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 f = load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
+                    const float4 f = (kHalf && c.fsm) ? load_f4_smem(c.fsm, r, c0 + 4 * e4 - gbeg) : load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
                     proj = fmaf(f.x, __uint_as_float(v[e4 * 4 + 0]), proj);
                     proj = fmaf(f.y, __uint_as_float(v[e4 * 4 + 1]), proj);
                     proj = fmaf(f.z, __uint_as_float(v[e4 * 4 + 2]), proj);
                     proj = fmaf(f.w, __uint_as_float(v[e4 * 4 + 3]), proj);
                 }
             }
+#ifdef DSRL_POS_TIMING
+            te2 = clock64();
+#endif
             // the two column halves of a row each hold part of the projection
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             projbuf[half * kTile + r] = proj;
@@ -535,7 +565,7 @@ __device__ __forceinline__ void epilogue_finish(const PosGeom &g, const PosArgs 
                 const int nreal = a.direct ? (row < g.N ? Cr - (c0 - cb) : 0) : 32;      // channels of this strip that exist in dX
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 f = load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
+                    const float4 f = (kHalf && c.fsm) ? load_f4_smem(c.fsm, r, c0 + 4 * e4 - gbeg) : load_f4<kHalf>(frow, frow_h, c0 + 4 * e4);
                     if (e4 * 4 + 0 < nreal) dst[(size_t)(e4 * 4 + 0) * pitch] = (__uint_as_float(v[e4 * 4 + 0]) - f.x * proj) * scale * gmul;
                     if (e4 * 4 + 1 < nreal) dst[(size_t)(e4 * 4 + 1) * pitch] = (__uint_as_float(v[e4 * 4 + 1]) - f.y * proj) * scale * gmul;
                     if (e4 * 4 + 2 < nreal) dst[(size_t)(e4 * 4 + 2) * pitch] = (__uint_as_float(v[e4 * 4 + 2]) - f.z * proj) * scale * gmul;
@@ -543,6 +573,12 @@ __device__ __forceinline__ void epilogue_finish(const PosGeom &g, const PosArgs 
                 }
             }
         }
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+            tm[20] = te1 - te0; tm[21] = te2 - te1; tm[22] = clock64() - te2;
+        }
+#endif
     }
 
     // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
@@ -1638,8 +1674,8 @@ constexpr float kSafe32 = 3.0e-6f;
 // warp instruction per 10 bytes it gathers, so the instruction count matters as much as the bytes: addresses are one
 // 64-bit multiply-add per row, the loads carry immediate offsets, both branches share one warp reduction.
 // kBits (two-pass form): nothing is accumulated -- the exact sign of a listed entry (i, j), j > i, is written into the sign
-// planes at (i, j) and at (j, i) wherever it differs from the tensor-core sign (inside a diagonal tile always: its lower half
-// was converted from its own tensor-core values).
+// planes at (i, j) wherever it differs from the tensor-core sign, and inside a diagonal tile at (j, i) always (its lower half
+// was converted from its own tensor-core values); off-diagonal blocks below the diagonal do not exist.
 template <int kNU, bool kBits = false>
 __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
     constexpr int kR = 4;                         // entries per round: up to 16 independent 16-byte loads in flight per lane
@@ -1749,9 +1785,11 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
                     const int j = (int)(en[h] & 0x7fffffffu);
                     const bool fix = s_exact != s_used;
                     if (fix) { ++n_fix; worst = fmaxf(worst, dabs / tau); }
-                    if ((fix || (j >> 7) == (irow >> 7)) && lane == 0) {
+                    // only the blocks (tile of i) <= (tile of j) exist: pass B reads them transposed for the lower triangle.  A
+                    // diagonal tile holds both (i, j) and (j, i), each from its own tensor-core value: the mirror is set regardless
+                    if (lane == 0) {
                         if (fix) sign_plane_set(sbw, g.tiles, irow, j, s_exact);
-                        sign_plane_set(sbw, g.tiles, j, irow, s_exact);
+                        if ((j >> 7) == (irow >> 7)) sign_plane_set(sbw, g.tiles, j, irow, s_exact);
                     }
                     continue;
                 }
@@ -2119,12 +2157,12 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
         if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
         if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
         if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
-        if ((rc = opt_in_smem(fa_pos_dsign, g.half_smem_bytes))) return rc;
-        fa_pos_dsign<<<dim3(2 * g.a_units, 1, B), kDsignThreads, g.half_smem_bytes, st>>>(tm_pm, tm_k, g, a);
+        if ((rc = opt_in_smem(fa_pos_dsign, g.a_smem_bytes))) return rc;
+        fa_pos_dsign<<<dim3(2 * g.a_units, 1, B), kDsignThreads, g.a_smem_bytes, st>>>(tm_pm, tm_k, g, a);
         DSRL_LAUNCH_CHECK();
         if (g.exact && (rc = resolve())) return rc;
         if ((rc = opt_in_smem(fa_pos_grad, g.b_smem_bytes))) return rc;
-        fa_pos_grad<<<grid, kThreads, g.b_smem_bytes, st>>>(tm_v, g, a);
+        fa_pos_grad<<<grid, kGradThreads, g.b_smem_bytes, st>>>(tm_v, tm_pm, g, a);
         DSRL_LAUNCH_CHECK();
         if (g.raw_o && (rc = finish(a))) return rc;
         return DSRL_OK;

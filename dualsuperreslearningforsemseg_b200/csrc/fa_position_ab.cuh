@@ -7,21 +7,23 @@
 // clusters of four), the work is split into two tensor-bound passes over CTA pairs (clusters of two, every SM busy):
 //
 //   pass A  fa_pos_dsign   D(i, j) for the tiles j >= i only (2 C N^2): |D| sums (the loss, off-diagonal tiles counted twice),
-//                          near-tie lists (exact signs), and the sign / is-zero BITS of the tile written twice into the
-//                          "sign planes": as computed for block (i, j) and bit-transposed (32 x 32 warp butterflies) for
-//                          block (j, i).  Four D buffers in tensor memory (all 512 columns) decouple the MMA issuer from
-//                          the conversion warps.
-//   resolve fa_pos_resolve (exact signs) re-decides the listed near ties from the unrounded features and SETS THE BITS --
-//                          both (i, j) and (j, i) -- so no accumulator is ever corrected and no raw rows are kept.
-//   pass B  fa_pos_grad    O_i = sum_j sign(D_ij) Fh_j (4 C N^2): per column tile the conversion warps expand 4 KB of bits
-//                          into the packed FP16 sign tile in tensor memory (A-from-TMEM operand), the issuer runs the
-//                          gradient MMAs against the V_j boxes; normalisation Jacobian and dX / dP in the epilogue.
+//                          near-tie lists (exact signs), and the sign / is-zero BITS of the tile written into the "sign
+//                          planes", block (i, j).  Four D buffers in tensor memory (all 512 columns) decouple the MMA
+//                          issuer from the conversion warps, which are what bounds this pass (issue slots): everything that
+//                          can wait is left to pass B.
+//   resolve fa_pos_resolve (exact signs) re-decides the listed near ties from the unrounded features and SETS THE BITS,
+//                          so no accumulator is ever corrected and no raw rows are kept.
+//   pass B  fa_pos_grad    O_i = sum_j sign(D_ij) Fh_j (4 C N^2): per column tile the conversion warps read 4 KB of bits --
+//                          block (i, j) for j >= i, block (j, i) bit-TRANSPOSED across the warp (five shuffle butterflies)
+//                          for j < i -- and expand them into the packed FP16 sign tile in tensor memory (A-from-TMEM
+//                          operand); the issuer runs the gradient MMAs against the V_j boxes (tensor bound: the conversion
+//                          warps have the slack pass A lacks); normalisation Jacobian and dX / dP in the epilogue.
 //
 // Executed tensor work: 6 C N^2 per sample (4 for the gradient, 2 for the upper triangle of D) instead of 8.
 // Sign planes: per sample T x T blocks of 4 KB, block (I, J) = [column half h][row r] x 16 bytes {neg s0, zero s0, neg s1,
 // zero s1}: the sign and is-zero bits of row r of tile I against the two 32-column strips s of half h of tile J, bit e of a
 // word = entry 2e, bit 16 + e = entry 2e + 1 of the strip (the order expand_signs() wants).  N^2 / 4 bytes per sample
-// (268 MB at N = 32768), written once and read once per channel group; geometries whose planes would exceed the cap
+// (268 MB at N = 32768; only the blocks I <= J are ever touched), written once and read twice per channel group; geometries whose planes would exceed the cap
 // fall back to the fused kernels (kSignPlaneCapBytes).
 
 constexpr size_t kSignBlock = kSignBlockBytes;       // bytes per (row tile, column tile)
@@ -31,6 +33,9 @@ constexpr uint32_t kColS = 256;
 constexpr int kDsignEpiWarps = 16;                   // pass A: one conversion warp per (lane quarter, 32-column strip)
 constexpr int kDsignEpiThreads = kDsignEpiWarps * 32;
 constexpr int kDsignThreads = 64 + kDsignEpiThreads;
+constexpr int kGradConvWarps = 16;                   // pass B: two sets of eight conversion warps (lane quarter x column half) that alternate over the tiles; warps 2..9 also run the epilogue
+constexpr int kGradThreads = 64 + kGradConvWarps * 32;
+constexpr int kGradFBoxes = 4;                       // pass B: boxes (128 rows x 64 channels) of the CTA's own feature rows kept for the epilogue
 
 // 32 x 32 bit transpose across a warp: lane l enters with row l, leaves with column l (bit b = row b's bit l)
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
@@ -66,9 +71,9 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
     constexpr int kElems = 64;                                      // FP16 operand elements per 128-byte row
     constexpr int kUnitBytes = kPairKBox;                           // this CTA's 64 rows of one 64-channel chunk of K_j
-    constexpr int kStageBytes = 4 * kPairKBox;
-    constexpr int kUPS = 4;
-    const int S = g.half_stages, nkc = g.nkh;
+    constexpr int kStageBytes = 4 * kPairKBox;                      // 32 KB (stages of 16 KB were measured: 2165 -> 2727 cycles per tile --
+    constexpr int kUPS = 4;                                         // twice the barrier round trips for the same bytes in flight)
+    const int S = g.a_stages, nkc = g.nkh;
     unsigned char *qreg = sm;
     unsigned char *ring = sm + (size_t)nkc * kBoxBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
@@ -144,14 +149,17 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
             const uint32_t id_pos = idesc_f16(2 * kTile, kTile, false), id_neg = idesc_f16(2 * kTile, kTile, true);
             const int q_neg = g.C1p / 16;                           // first K step (16 channels) of branch 2 (subtracted)
+            long long w_full = 0, w_de = 0;
+            const long long t_begin = clock64();
             mbar_wait(q_full, 0, 32);
+            const long long t_q = clock64();
             for (int jj = 0; jj < nt; ++jj) {
                 const int buf = jj & (kDBufs - 1);
                 const uint32_t dcol = tmem + (uint32_t)buf * kTile;
-                mbar_wait(&d_empty[buf], ((uint32_t)(jj / kDBufs) & 1u) ^ 1u, 33);      // the tile that used this buffer has been read
+                TWAIT(w_de, mbar_wait(&d_empty[buf], ((uint32_t)(jj / kDBufs) & 1u) ^ 1u, 33));      // the tile that used this buffer has been read
                 fence_after_sync();
                 for (int kc0 = 0; kc0 < nkc; kc0 += kUPS) {
-                    mbar_wait(&full[slot], ph, 34);
+                    TWAIT(w_full, mbar_wait(&full[slot], ph, 34));
                     const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
                     const int ss = slot;
                     RING_ADVANCE();
@@ -173,6 +181,14 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                     __syncwarp();
                 }
             }
+#ifdef DSRL_POS_TIMING
+            if (blockIdx.x == 0 && blockIdx.z == 0 && lane == 0) {
+                long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;      // saved[64..256): role clocks of CTA (0,0,0)
+                tm[0] = t_q - t_begin; tm[1] = clock64() - t_q; tm[2] = w_full; tm[3] = w_de; tm[4] = nt;
+            }
+#else
+            (void)t_begin; (void)t_q; (void)w_full; (void)w_de;
+#endif
         }
     } else {
         // ===================================== conversion warps =====================================
@@ -184,11 +200,12 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         const bool listing = g.exact != 0;
         const float tau = listing ? __ldg(a.tau + b) : 0.f;
         const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * g.fnsub + (size_t)(4 * chunk + cg);
-        uint4 *sb = a.sb + (size_t)b * T * T * (kSignBlock / 16);
-        const int tcol = lane < 16 ? 2 * lane : 2 * (lane - 16) + 1;      // the strip column whose transposed word this lane holds
+        uint2 *srow = reinterpret_cast<uint2 *>(a.sb + ((size_t)b * T * T + (size_t)itile * T + jbeg) * (kSignBlock / 16) + (size_t)(cg >> 1) * kTile + r) + (cg & 1);
         unsigned nlisted = 0;
         double acc = 0.0;
         float facc = 0.f;
+        long long w_d = 0;
+        const long long t_begin = clock64();
         // tile sums are gathered in FP32 over eight tiles before they enter the FP64 total.  The FP64 add sits in an OUTER loop:
         // written as `if ((jj & 7) == 7) acc += facc` the compiler predicates it and issues a DADD per tile and warp, which
         // was the top stall of this kernel (FP64 pipe, ncu r02d: 13 % of the samples)
@@ -197,7 +214,7 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 #pragma unroll 1
         for (int jj = jj0; jj < jj1; ++jj) {
             const int buf = jj & (kDBufs - 1), j = jbeg + jj;
-            mbar_wait(&d_full[buf], (uint32_t)(jj / kDBufs) & 1u, 35);
+            TWAIT(w_d, mbar_wait(&d_full[buf], (uint32_t)(jj / kDBufs) & 1u, 35));
             fence_after_sync();
             const bool diag = j == itile, lower = j < itile;       // lower: tile (2p + 1, 2p), supplied by the transpose of (2p, 2p + 1)
             uint32_t v[32];
@@ -257,21 +274,22 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                     ++nlisted;
                 }
             }
-            // block (itile, j): this thread's row, its strip's two words
-            *(reinterpret_cast<uint2 *>(sb + ((size_t)(itile * T + j) * 2 + (cg >> 1)) * kTile + r) + (cg & 1)) = make_uint2(M, Z);
-            if (!diag) {
-                // block (j, itile): this warp's 32 rows are 32 columns there (quarter q -> half q / 2, strip q % 2)
-                const uint32_t tn = pair_order(transpose32(M, lane));
-                uint32_t tz = 0u;
-                if (__any_sync(0xffffffffu, Z != 0u)) tz = pair_order(transpose32(Z, lane));
-                *(reinterpret_cast<uint2 *>(sb + ((size_t)(j * T + itile) * 2 + (q >> 1)) * kTile + cg * 32 + tcol) + (q & 1)) = make_uint2(tn, tz);
-            }
+            // block (itile, j): this thread's row, its strip's two words (consecutive column tiles are one block apart)
+            srow[(size_t)jj * (kSignBlock / 8)] = make_uint2(M, Z);
             facc += diag ? tsum : 2.f * tsum;
         }
         acc += (double)facc;
         facc = 0.f;
         }
         if (listing) a.fcnt[gsub] = nlisted;
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+            tm[5] = clock64() - t_begin; tm[6] = w_d;
+        }
+#else
+        (void)t_begin; (void)w_d;
+#endif
         // loss: per-CTA partial, finished in a fixed order by the last CTA to arrive (deterministic)
         {
             const int et = threadIdx.x - 64;
@@ -310,11 +328,79 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
 }
 
+// Epilogue of pass B when the CTA's feature rows are in shared memory: normalisation Jacobian of the accumulator rows,
+//   dF_i = (O_i - Fh_i <Fh_i, O_i>) * (+-2 / Z) / ||F_i||    per branch,
+// by all sixteen conversion warps (TMEM lane quarter q x channel part: 32-channel chunks part, part + 4, ...), the features
+// read with conflict-free 16-byte shared-memory loads (a quarter warp covers the eight swizzled chunks of a 128-byte row).
+// Stored channel-major -- dP (padded) or, fused forward + backward without pooling, dX itself scaled by *go -- coalesced
+// along positions.  Same arithmetic, same bits as epilogue_finish.
+constexpr int kGradParts = 4;
+__device__ __forceinline__ void grad_epilogue_smem(const PosGeom &g, const PosArgs &a, const unsigned char *fsm, float *projbuf /* [parts][2][128] */,
+                                                   uint32_t tmem, int itile, int b, int gN, int gbeg) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, r = q * 32 + lane, part = (warp - 2) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int row = itile * kTile + r;
+    auto feat8 = [&](int cl, float (&f)[8]) {                      // channels gbeg + cl .. + 7 (cl a multiple of 8) of this thread's row
+        const uint4 w = *reinterpret_cast<const uint4 *>(fsm + (size_t)(cl >> 6) * kBoxBytes + r * 128 + ((((cl & 63) >> 3) ^ (r & 7)) << 4));
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&w.w));
+        f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
+    };
+    float proj[2] = {0.f, 0.f};
+    for (int c0 = 32 * part; c0 < gN; c0 += 32 * kGradParts) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float p = 0.f;
+#pragma unroll
+        for (int e8 = 0; e8 < 4; ++e8) {
+            float f[8];
+            feat8(c0 + 8 * e8, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) p = fmaf(f[e], __uint_as_float(v[e8 * 8 + e]), p);
+        }
+        if (gbeg + c0 >= g.C1p) proj[1] += p; else proj[0] += p;
+    }
+    projbuf[(part * 2 + 0) * kTile + r] = proj[0];
+    projbuf[(part * 2 + 1) * kTile + r] = proj[1];
+    asm volatile("bar.sync 1, %0;" ::"n"(kGradConvWarps * 32) : "memory");
+    float scale[2];
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+        float sp = 0.f;
+#pragma unroll
+        for (int i = 0; i < kGradParts; ++i) sp += projbuf[(i * 2 + br) * kTile + r];
+        const float n = a.nrm[((size_t)b * 2 + br) * g.Npad + row];
+        proj[br] = n > 1e-12f ? sp : 0.f;                           // F / eps branch of the clamp: no projection
+        scale[br] = (br ? -a.grad_scale : a.grad_scale) / fmaxf(n, 1e-12f);
+    }
+    const float gmul = a.direct ? __ldg(a.go) : 1.f;               // applied as a second multiply: the bits fa_pos_unpool would produce
+    for (int c0 = 32 * part; c0 < gN; c0 += 32 * kGradParts) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int c = gbeg + c0, br = c >= g.C1p, cb = br ? g.C1p : 0, Cr = br ? g.C2 : g.C1;
+        const size_t pitch = a.direct ? (size_t)g.N : (size_t)g.Npad;
+        float *dst = a.direct ? a.dx[br] + ((size_t)b * Cr + (c - cb)) * pitch + row : a.dP + ((size_t)b * g.Kc + c) * pitch + row;
+        const int nreal = a.direct ? (row < g.N ? Cr - (c - cb) : 0) : 32;       // channels of this chunk that exist in dX
+        const float pr = proj[br], sc = scale[br];
+#pragma unroll
+        for (int e8 = 0; e8 < 4; ++e8) {
+            float f[8];
+            feat8(c0 + 8 * e8, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e8 * 8 + e < nreal) dst[(size_t)(e8 * 8 + e) * pitch] = (__uint_as_float(v[e8 * 8 + e]) - f[e] * pr) * sc * gmul;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pass B: sign planes -> gradient contraction -> normalisation Jacobian -> dX / dP (or raw partial rows, jsplit > 1)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGradThreads, 1)
+fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_q, const PosGeom g, const PosArgs a) {
     extern __shared__ unsigned char smraw[];
     const uint32_t raw = smem_u32(smraw);
     unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
@@ -322,15 +408,17 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
     constexpr int kStageBytes = kBoxBytes;                          // one V box: this CTA's half of the group's channels x 64 positions
     const int S = g.b_stages;
     unsigned char *ring = sm;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)S * kStageBytes);
+    unsigned char *fbuf = ring + (size_t)S * kStageBytes;           // kGradFBoxes boxes: the CTA's own feature rows (epilogue operand)
+    uint64_t *full = reinterpret_cast<uint64_t *>(fbuf + (size_t)kGradFBoxes * kBoxBytes);
     uint64_t *empty = full + S;
     uint64_t *p_full = empty + S;           // [kSBufs] (in the leader: both CTAs' conversion warps have written the sign tile)
     uint64_t *p_empty = p_full + kSBufs;    // [kSBufs] the gradient MMAs of the tile that used this buffer have completed
     uint64_t *o_full = p_empty + kSBufs;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
-    double *red = reinterpret_cast<double *>(o_full + 2);
+    uint64_t *f_full = o_full + 1;          // this CTA's own feature rows have landed in fbuf
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 2);
+    double *red = reinterpret_cast<double *>(o_full + 3);
     int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
-    float *projbuf = reinterpret_cast<float *>(flag + 2);
+    float *projbuf = reinterpret_cast<float *>(flag + 2);           // [kGradParts][2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -344,8 +432,9 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_v);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int i = 0; i < kSBufs; ++i) { mbar_init(&p_full[i], 2 * kEpiWarps); mbar_init(&p_empty[i], 1); }
+        for (int i = 0; i < kSBufs; ++i) { mbar_init(&p_full[i], 2 * kEpiWarps); mbar_init(&p_empty[i], 1); }          // the eight warps of the tile's set, both CTAs
         mbar_init(o_full, 1);
+        mbar_init(f_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
@@ -353,6 +442,12 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
     cluster_sync();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    // the epilogue multiplies the accumulator rows with the CTA's own normalised feature rows.  Read per thread from global
+    // memory that is one 128-byte line per lane and load (a row is 1 KB): the L1 wavefronts of those loads made the epilogue
+    // 9 % of a CTA's life (role clocks r02g: 8.6 k + 14.5 k cycles for the two passes).  The rows are instead fetched by TMA at
+    // the start of the kernel: gN / 64 boxes of 128 rows x 64 channels, 128-byte swizzle.
+    const int fboxes = gN / 64;
+    const bool f_smem = !g.raw_o && gN % 64 == 0 && fboxes <= kGradFBoxes;
 
     int slot = 0;
     uint32_t ph = 0;
@@ -361,6 +456,14 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
     if (warp == 0) {
         // ===================================== TMA producer: the V_j boxes =====================================
         const int row_v = b * g.Kc + gbeg + (int)rank * vrows;                        // this CTA's half of the group's channels
+        if (f_smem) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(f_full, (uint32_t)fboxes * kBoxBytes);
+                for (int i = 0; i < fboxes; ++i)
+                    tma_load_2d(fbuf + (size_t)i * kBoxBytes, &tm_q, f_full, gbeg + i * kElems, b * g.Npad + itile * kTile);
+            }
+            __syncwarp();
+        }
         for (int jj = 0; jj < nt; ++jj) {
             for (int jc = 0; jc < 2; ++jc) {
                 mbar_wait(&empty[slot], ph ^ 1, 41);
@@ -378,13 +481,16 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
             constexpr uint64_t kStageDesc = kStageBytes >> 4;
             const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring));
             const uint32_t id_g = idesc_f16(2 * kTile, gN, false);
+            long long w_full = 0, w_p = 0, t_first = 0;
+            const long long t_begin = clock64();
             for (int jj = 0; jj < nt; ++jj) {
                 const int buf = jj & (kSBufs - 1);
                 const uint32_t pcol = tmem + kColS + (uint32_t)buf * 64u;
-                mbar_wait(&p_full[buf], (uint32_t)(jj / kSBufs) & 1u, 42);
+                TWAIT(w_p, mbar_wait(&p_full[buf], (uint32_t)(jj / kSBufs) & 1u, 42));
                 fence_after_sync();
                 for (int jc = 0; jc < 2; ++jc) {
-                    mbar_wait(&full[slot], ph, 43);
+                    TWAIT(w_full, mbar_wait(&full[slot], ph, 43));
+                    if (jj == 0 && jc == 0) t_first = clock64();
                     const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
                     const int ss = slot;
                     RING_ADVANCE();
@@ -400,24 +506,62 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
                     __syncwarp();
                 }
             }
+#ifdef DSRL_POS_TIMING
+            if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {
+                long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+                tm[12] = t_first - t_begin; tm[13] = clock64() - t_first; tm[14] = w_full; tm[15] = w_p; tm[16] = nt;
+            }
+            if (blockIdx.x == gridDim.x - 2 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) {     // a row tile whose column tiles are all below the diagonal
+                long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+                tm[8] = clock64() - t_first; tm[9] = w_full; tm[10] = w_p;
+            }
+#else
+            (void)t_begin; (void)t_first; (void)w_full; (void)w_p;
+#endif
         }
     } else {
         // ===================================== conversion warps: bits -> packed FP16 sign tiles =====================================
-        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+        // Two sets of eight warps take the column tiles in turn (set s: tiles with jj % 2 == s), so a warp has two tiles of MMA
+        // time for one conversion -- with the transposed read of the lower triangle a single set fell behind the tensor pipe on
+        // the row tiles that are mostly below the diagonal.  Inside a set: one warp per (TMEM lane quarter q, column half).
+        //   column tiles j >= itile: this thread's row of block (itile, j), the 16 bytes of its half;
+        //   column tiles j <  itile: only the mirror block (j, itile) exists -- for each strip cg of its half, lane l loads the
+        //     words of ITS ROW c = 32 cg + l there (bits = this warp's 32 rows: strip q % 2 of half q / 2), the warp transposes
+        //     them (transpose32) and each lane picks up the word of its own row: bits over the 32 columns of the strip.
+        const int cw = warp - 2, set = cw >> 3;
+        const int q = warp & 3, r = q * 32 + lane, half = (cw >> 2) & 1;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        // this thread's 16 bytes of block (itile, j): consecutive column tiles are one block (4 KB) apart
-        const uint4 *src = a.sb + ((size_t)b * T * T + (size_t)itile * T + j0) * (kSignBlock / 16) + (size_t)half * kTile + r;
-        constexpr int kAhead = 3;                                      // loads in flight: ~3 tiles of MMA time cover an L2 / HBM round trip
+        const uint4 *blocks = a.sb + (size_t)b * T * T * (kSignBlock / 16);
+        const uint4 *up = blocks + (size_t)itile * T * (kSignBlock / 16) + (size_t)half * kTile + r;         // + j blocks
+        const uint2 *lo = reinterpret_cast<const uint2 *>(blocks + (size_t)itile * (kSignBlock / 16) + (size_t)(q >> 1) * kTile + 64 * half + lane) + (q & 1);   // + j * T blocks; strip 1: 32 units on
+        auto bits_of = [&](int j) {
+            if (j >= itile) return ldg_stream_u4(up + (size_t)j * (kSignBlock / 16));
+            const uint2 *pl = lo + (size_t)j * T * (kSignBlock / 8);
+            const uint2 s0 = ldg_stream_u2(pl), s1 = ldg_stream_u2(pl + 64);
+            return make_uint4(s0.x, s0.y, s1.x, s1.y);
+        };
+        const int src_lane = (lane >> 1) + ((lane & 1) << 4);       // the lane that holds this lane's row after the transpose (paired order)
+        constexpr int kAhead = 2;                                      // this set's tiles in flight: 4 tiles of MMA time cover an L2 / HBM round trip
         uint4 pre[kAhead];
 #pragma unroll
-        for (int i = 0; i < kAhead; ++i) pre[i] = i < nt ? ldg_stream_u4(src + (size_t)i * (kSignBlock / 16)) : make_uint4(0u, 0u, 0u, 0u);
-        for (int jj = 0; jj < nt; ++jj) {
-            const int buf = jj & (kSBufs - 1);
-            const uint4 cur = pre[0];
+        for (int i = 0; i < kAhead; ++i) pre[i] = set + 2 * i < nt ? bits_of(j0 + set + 2 * i) : make_uint4(0u, 0u, 0u, 0u);
+        long long w_pe = 0;
+        const long long t_begin = clock64();
+        for (int jj = set; jj < nt; jj += 2) {
+            const int buf = jj & (kSBufs - 1), j = j0 + jj;
+            uint4 cur = pre[0];
 #pragma unroll
             for (int i = 0; i + 1 < kAhead; ++i) pre[i] = pre[i + 1];
-            if (jj + kAhead < nt) pre[kAhead - 1] = ldg_stream_u4(src + (size_t)(jj + kAhead) * (kSignBlock / 16));
-            mbar_wait(&p_empty[buf], ((uint32_t)(jj / kSBufs) & 1u) ^ 1u, 44);
+            if (jj + 2 * kAhead < nt) pre[kAhead - 1] = bits_of(j + 2 * kAhead);
+            if (j < itile) {                                         // warp-uniform
+                cur.x = pair_order(__shfl_sync(0xffffffffu, transpose32(cur.x, lane), src_lane));
+                cur.z = pair_order(__shfl_sync(0xffffffffu, transpose32(cur.z, lane), src_lane));
+                if (__any_sync(0xffffffffu, (cur.y | cur.w) != 0u)) {
+                    cur.y = pair_order(__shfl_sync(0xffffffffu, transpose32(cur.y, lane), src_lane));
+                    cur.w = pair_order(__shfl_sync(0xffffffffu, transpose32(cur.w, lane), src_lane));
+                }
+            }
+            TWAIT(w_pe, mbar_wait(&p_empty[buf], ((uint32_t)(jj / kSBufs) & 1u) ^ 1u, 44));
             fence_after_sync();
             uint32_t pk[16];
             expand_signs(cur.x, cur.y, pk);
@@ -429,13 +573,31 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&p_full[buf]);
         }
-        EpiCtx c;
-        c.d_full = nullptr; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
-        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
-        c.part_index = -1;                   // the loss was finished by pass A
-        c.nparts = 0;
-        c.sub = 0; c.nsub = g.fnsub;
-        epilogue_finish<true, true>(g, a, c, 0.0);
+#ifdef DSRL_POS_TIMING
+        const long long t_conv = clock64();
+#endif
+        if (f_smem) {
+            // every conversion warp: accumulator complete, feature rows landed
+            mbar_wait(o_full, 0, 47);
+            fence_after_sync();
+            mbar_wait(f_full, 0, 46);
+            grad_epilogue_smem(g, a, fbuf, projbuf, tmem, itile, b, gN, gbeg);
+        } else if (warp < 2 + kEpiWarps) {
+            EpiCtx c;
+            c.d_full = nullptr; c.p_full = p_full; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
+            c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
+            c.part_index = -1;                   // the loss was finished by pass A
+            c.nparts = 0;
+            c.sub = 0; c.nsub = g.fnsub;
+            epilogue_finish<true, true>(g, a, c, 0.0);
+        }
+#ifdef DSRL_POS_TIMING
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
+            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
+            tm[17] = t_conv - t_begin; tm[18] = w_pe; tm[19] = clock64() - t_conv;
+        }
+#endif
+        (void)t_begin; (void)w_pe;
     }
 #undef RING_ADVANCE
 
@@ -445,7 +607,8 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const Pos
 }
 
 // One entry of the sign planes set to an exactly known sign (resolve pass, one lane): entry (i, j) of a sample whose planes
-// start at `sbw`.  Integer atomics on different bits commute, so the planes are bit-repeatable.
+// start at `sbw`; the caller passes entries of existing blocks only (tile of i <= tile of j).  Integer atomics on different
+// bits commute, so the planes are bit-repeatable.
 __device__ __forceinline__ void sign_plane_set(uint32_t *sbw, int T, int i, int j, int s) {
     const size_t unit = ((size_t)((i >> 7) * T + (j >> 7)) * 2 + ((j >> 6) & 1)) * kTile + (i & 127);
     uint32_t *w = sbw + unit * 4 + 2 * ((j >> 5) & 1);
