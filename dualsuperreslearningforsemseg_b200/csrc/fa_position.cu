@@ -188,8 +188,10 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         // pass A: a pair of row tiles against its column tiles j >= 2p is one work unit when there are plenty of them; small
         // grids cut the column range into chunks (no accumulator: a chunk only re-loads the pair's own rows) so that the
         // triangle balances over the SMs.  Near-tie sub-lists are per (chunk, column half): at most 8 chunks.
+        // (a unit pays ~4 tiles of time for loading its own rows, so whole rows win as soon as every SM pair has one: list
+        // scheduling of the 128 rows of one N = 32768 sample on 74 pairs is 86 % efficient unsplit, 81 % in chunks of 32 tiles)
         g.a_chunk = g.tiles;
-        if ((long long)B * (g.tiles / 2) < 8LL * (sms / 2)) g.a_chunk = (g.tiles + 7) / 8 < 8 ? (g.tiles < 8 ? g.tiles : 8) : (g.tiles + 7) / 8;
+        if ((long long)B * (g.tiles / 2) < sms / 2) g.a_chunk = (g.tiles + 7) / 8 < 8 ? (g.tiles < 8 ? g.tiles : 8) : (g.tiles + 7) / 8;
         if (const char *e = getenv("DSRL_POS_ACHUNK")) {          // test hook
             const int v = atoi(e);
             if (v >= 1 && (g.tiles + v - 1) / v <= 8) g.a_chunk = v < g.tiles ? v : g.tiles;
