@@ -177,9 +177,9 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         if (const char *e = getenv("DSRL_POS_QUAD")) { if (atoi(e) == 0) g.quad = 0; }
     }
     // FP16 form as two symmetric passes over CTA pairs (fa_position_ab.cuh): whenever the pair form applies and the sign
-    // planes (N^2 / 4 bytes per sample) stay below the cap
+    // planes (N^2 / 8 bytes per sample) stay below the cap
     {
-        g.sb_bytes = (size_t)B * g.tiles * g.tiles * kSignBlockBytes;
+        g.sb_bytes = (size_t)B * ((size_t)g.tiles * (g.tiles + 1) / 2) * kSignBlockBytes;      // packed upper triangle of blocks
         // (with tensor-core signs and few channels both passes are bound by their conversion warps and the fused pair kernel,
         // which converts every tile once, is ahead: 3.0 vs 3.5 ms at C = 32 per branch, batch 8)
         g.ab = g.half_pair && g.sb_bytes <= kSignPlaneCapBytes && (exact || g.Kc > 128);
@@ -1724,7 +1724,7 @@ __global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs 
 #pragma unroll
         for (int t = 0; t < 4 * kNU; ++t) s_corr[warp][t][lane] = 0;
     }
-    uint32_t *sbw = kBits ? reinterpret_cast<uint32_t *>(ex.sb + (size_t)b * g.tiles * g.tiles * (kSignBlockBytes / 16)) : nullptr;
+    uint32_t *sbw = kBits ? reinterpret_cast<uint32_t *>(ex.sb + (size_t)b * sign_blocks(g.tiles) * (kSignBlockBytes / 16)) : nullptr;
     unsigned n_fix = 0;
     float worst = 0.f;
     const unsigned *ent = ex.fent + grow * g.fcap;

@@ -21,9 +21,10 @@
 //
 // Executed tensor work: 6 C N^2 per sample (4 for the gradient, 2 for the upper triangle of D) instead of 8.
 // Sign planes: per sample T x T blocks of 4 KB, block (I, J) = [column half h][row r] x 16 bytes {neg s0, zero s0, neg s1,
-// zero s1}: the sign and is-zero bits of row r of tile I against the two 32-column strips s of half h of tile J, bit e of a
-// word = entry 2e, bit 16 + e = entry 2e + 1 of the strip (the order expand_signs() wants).  N^2 / 4 bytes per sample
-// (268 MB at N = 32768; only the blocks I <= J are ever touched), written once and read twice per channel group; geometries whose planes would exceed the cap
+// zero s1}: the sign and is-zero bits of row r of tile I against the two 32-column strips s of half h of tile J (only I <= J is
+// stored, as a packed upper triangle of blocks: the lower triangle is read transposed), bit e of a
+// word = entry 2e, bit 16 + e = entry 2e + 1 of the strip (the order expand_signs() wants).  N^2 / 8 bytes per sample
+// (134 MB at N = 32768), written once and read twice per channel group; geometries whose planes would exceed the cap
 // fall back to the fused kernels (kSignPlaneCapBytes).
 
 constexpr size_t kSignBlock = kSignBlockBytes;       // bytes per (row tile, column tile)
@@ -57,6 +58,10 @@ __device__ __forceinline__ uint32_t pair_order(uint32_t x) {
     ev = (ev | (ev >> 8)) & 0x0000ffffu; od = (od | (od >> 8)) & 0x0000ffffu;
     return ev | (od << 16);
 }
+
+// Only the blocks I <= J exist: they are stored as the packed upper triangle, row by row.
+__host__ __device__ inline size_t sign_blocks(int T) { return (size_t)T * (T + 1) / 2; }                       // per sample
+__host__ __device__ inline size_t sign_block_index(int T, int I, int J) { return (size_t)I * (2 * T - I + 1) / 2 + (size_t)(J - I); }
 
 // work unit of pass A: (pair of row tiles p, column chunk) -- column tiles [2p + chunk * Lc, ... + Lc) of the rows [256 p, 256 p + 256)
 __host__ __device__ inline int dsign_chunks(int T, int Lc, int p) { return (T - 2 * p + Lc - 1) / Lc; }
@@ -200,7 +205,7 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         const bool listing = g.exact != 0;
         const float tau = listing ? __ldg(a.tau + b) : 0.f;
         const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * g.fnsub + (size_t)(4 * chunk + cg);
-        uint2 *srow = reinterpret_cast<uint2 *>(a.sb + ((size_t)b * T * T + (size_t)itile * T + jbeg) * (kSignBlock / 16) + (size_t)(cg >> 1) * kTile + r) + (cg & 1);
+        uint2 *srow = reinterpret_cast<uint2 *>(a.sb + ((size_t)b * sign_blocks(T) + sign_block_index(T, itile, max(jbeg, itile))) * (kSignBlock / 16) + (size_t)(cg >> 1) * kTile + r) + (cg & 1);
         unsigned nlisted = 0;
         double acc = 0.0;
         float facc = 0.f;
@@ -275,7 +280,7 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 }
             }
             // block (itile, j): this thread's row, its strip's two words (consecutive column tiles are one block apart)
-            srow[(size_t)jj * (kSignBlock / 8)] = make_uint2(M, Z);
+            srow[(size_t)(j - max(jbeg, itile)) * (kSignBlock / 8)] = make_uint2(M, Z);
             facc += diag ? tsum : 2.f * tsum;
         }
         acc += (double)facc;
@@ -531,12 +536,12 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CU
         const int cw = warp - 2, set = cw >> 3;
         const int q = warp & 3, r = q * 32 + lane, half = (cw >> 2) & 1;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint4 *blocks = a.sb + (size_t)b * T * T * (kSignBlock / 16);
-        const uint4 *up = blocks + (size_t)itile * T * (kSignBlock / 16) + (size_t)half * kTile + r;         // + j blocks
-        const uint2 *lo = reinterpret_cast<const uint2 *>(blocks + (size_t)itile * (kSignBlock / 16) + (size_t)(q >> 1) * kTile + 64 * half + lane) + (q & 1);   // + j * T blocks; strip 1: 32 units on
+        const uint4 *blocks = a.sb + (size_t)b * sign_blocks(T) * (kSignBlock / 16);
+        const uint4 *up = blocks + sign_block_index(T, itile, itile) * (kSignBlock / 16) + (size_t)half * kTile + r;         // + (j - itile) blocks
+        const uint2 *lo = reinterpret_cast<const uint2 *>(blocks + (size_t)(q >> 1) * kTile + 64 * half + lane) + (q & 1);      // + block (j, itile); strip 1: 32 units on
         auto bits_of = [&](int j) {
-            if (j >= itile) return ldg_stream_u4(up + (size_t)j * (kSignBlock / 16));
-            const uint2 *pl = lo + (size_t)j * T * (kSignBlock / 8);
+            if (j >= itile) return ldg_stream_u4(up + (size_t)(j - itile) * (kSignBlock / 16));
+            const uint2 *pl = lo + sign_block_index(T, j, itile) * (kSignBlock / 8);
             const uint2 s0 = ldg_stream_u2(pl), s1 = ldg_stream_u2(pl + 64);
             return make_uint4(s0.x, s0.y, s1.x, s1.y);
         };
@@ -610,7 +615,7 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CU
 // start at `sbw`; the caller passes entries of existing blocks only (tile of i <= tile of j).  Integer atomics on different
 // bits commute, so the planes are bit-repeatable.
 __device__ __forceinline__ void sign_plane_set(uint32_t *sbw, int T, int i, int j, int s) {
-    const size_t unit = ((size_t)((i >> 7) * T + (j >> 7)) * 2 + ((j >> 6) & 1)) * kTile + (i & 127);
+    const size_t unit = (sign_block_index(T, i >> 7, j >> 7) * 2 + ((j >> 6) & 1)) * kTile + (i & 127);
     uint32_t *w = sbw + unit * 4 + 2 * ((j >> 5) & 1);
     const uint32_t bit = 1u << (((j & 31) >> 1) + 16 * (j & 1));
     if (s < 0) atomicOr(w, bit); else atomicAnd(w, ~bit);
