@@ -59,7 +59,6 @@ constexpr size_t kSmemAux = 1536;   // barriers, TMEM pointer, reduction scratch
 constexpr size_t kOneCtaSmem = 116 * 1024;
 constexpr size_t kSignBlockBytes = 2 * 128 * 16;              // two-pass form: sign planes, bytes per (row tile, column tile)
 constexpr size_t kSignPlaneCapBytes = (size_t)6 << 30;        // largest sign-plane footprint the two-pass form may use
-constexpr int kXchgBytes = 2 * 2 * 128 * 16;   // fa_pos_tiles_quad: two slots x (two column halves x 128 rows x 16 bytes of sign / zero bits)
 
 struct PosGeom {
     int B, C1, C2, H, W, k, h, w, N, Npad, C1p, C2p, Kc, G;
@@ -69,8 +68,6 @@ struct PosGeom {
     int q_resident, stages;
     int jsplit;             // gradient variant: the column tiles of one row tile are spread over jsplit CTAs (small grids)
     int pair, pair_stages;  // CTA-pair form of the gradient variant usable for this geometry; its ring depth
-    int quad, quad_stages;  // FP16 form, two channel groups: cluster of two CTA pairs that split the D tiles between them (fa_pos_tiles_quad)
-    size_t quad_smem_bytes;
     int half, nkh, half_stages;   // FP16 operands (kind::f16) requested; Kc / 64 chunks; ring depth of the pair form
     int half_pair, half1_stages;  // pair form usable for this geometry; ring depth of the single-CTA form
     int exact, fnsub, fsub, fcap; // exact signs: near-tie entries of D are listed per row -- 2 * jsplit private sub-lists (one per
@@ -163,19 +160,6 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         const int s = atoi(force);
         if ((s == 1 || s == 2 || s == 4) && g.tiles % s == 0) g.jsplit = s;
     }
-    // FP16 form with two equal channel groups: a cluster of two CTA pairs on the same two row tiles, each pair computing the D
-    // tiles of every other column tile and shipping their signs to the other pair (fa_pos_tiles_quad): needs an even number of
-    // column tiles per column share
-    {
-        const size_t qbytes = (size_t)g.nkh * kBoxBytes;
-        const long long room = (long long)kSmemBudget - 1024 - (long long)kSmemAux - (long long)qbytes - kXchgBytes;
-        g.quad_stages = room > 0 ? (int)(room / kBoxBytes) : 0;
-        if (g.quad_stages > 8) g.quad_stages = 8;
-        g.quad_smem_bytes = 1024 + qbytes + (size_t)g.quad_stages * kBoxBytes + kXchgBytes + kSmemAux;
-        if (g.quad_smem_bytes < kOneCtaSmem) g.quad_smem_bytes = kOneCtaSmem;
-        g.quad = g.half_pair && g.G == 2 && g.gcnt[0] == g.gcnt[1] && (g.tiles / g.jsplit) % 2 == 0 && g.quad_stages >= 3;
-        if (const char *e = getenv("DSRL_POS_QUAD")) { if (atoi(e) == 0) g.quad = 0; }
-    }
     // FP16 form as two symmetric passes over CTA pairs (fa_position_ab.cuh): whenever the pair form applies and the sign
     // planes (N^2 / 8 bytes per sample) stay below the cap
     {
@@ -208,7 +192,6 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         }
         g.b_stages = 8;                                           // 8 x 16 KB V boxes (4 tiles of MMA time ahead) + 4 boxes of own feature rows
         g.b_smem_bytes = 1024 + (size_t)(g.b_stages + 4) * kBoxBytes + 6144;      // barriers, reduction scratch, projection parts [4][2][128]
-        if (g.ab) g.quad = 0;
     }
     // exact signs: about 1e-3 of a row's entries are near ties (|D| below ~3.5 sigma of the operand-rounding error, whatever
     // C is: threshold and spread of D both scale like 1/sqrt(C)); the per-row list holds 4x that, at least 32 entries
@@ -217,7 +200,7 @@ inline bool make_geom(int B, int C1, int C2, int H, int W, int k, int split, Pos
         // sub-lists per row: column half x column share (x 2 when the two channel groups split the column tiles between them);
         // expected N * 1.1e-3 / nsub entries each, room for 4x that + 16.  Two-pass form: column half x column chunk of pass A
         // (upper triangle only, so a row holds at most what a full row would): one sub-list per 32-column strip of a tile and chunk.
-        const int nsub = g.fnsub = g.ab ? 4 * ((g.tiles + g.a_chunk - 1) / g.a_chunk) : 2 * g.jsplit * (g.quad ? 2 : 1);
+        const int nsub = g.fnsub = g.ab ? 4 * ((g.tiles + g.a_chunk - 1) / g.a_chunk) : 2 * g.jsplit;
         g.fsub = (int)align_up((size_t)(N / (200 * nsub)) + 16, 8);
         if (g.fsub > 2048) g.fsub = 2048;
         g.fcap = g.fsub * nsub;
@@ -440,6 +423,11 @@ struct PosArgs {
     const float *tau;
     unsigned *fcnt, *fent;
     uint4 *sb;          // two-pass form: the sign planes
+    // two-pass form: pass A derives the tie threshold itself while its operand rows load (the arithmetic of fa_pos_tau)
+    const float *Ppm;
+    const double *inv64;
+    float *tau_out;
+    float tau_r2, tau_floor2, tau_ksigma;
 };
 
 #ifdef DSRL_POS_TIMING
@@ -1264,21 +1252,13 @@ fa_pos_tiles_pair(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Two channel groups without computing D twice (FP16 form; cluster of 4 = two CTA pairs on the same two row tiles)
+// sign / is-zero bits -> packed FP16 sign values (pass B of the two-pass form)
 // ---------------------------------------------------------------------------------------------------------------
-// With more than 256 channels in all, the gradient accumulator of a row tile does not fit the tensor memory of one SM next
-// to a D tile, so each channel group (= branch) has its own CTA pair.  fa_pos_tiles_pair lets both pairs compute every D
-// tile (executed work 12 C N^2 per sample instead of 8 C N^2).  Here the two pairs of a cluster split the column tiles:
-// pair `grp` computes D(i, j) for the tiles j = j0 + 2k + grp of round k, converts it as usual (|D| sum, near-tie listing,
-// packed FP16 sign tile in its own tensor memory) and ships the SIGNS -- one sign bit and one is-zero bit per entry, 4 KB per
-// tile and CTA -- to the CTA of the other pair that owns the same rows, through distributed shared memory.  That CTA
-// expands the bits into the spare columns of the same tensor-memory buffer, and each pair runs the gradient MMAs of BOTH
-// tiles of the round for its own channels.  Per round and pair: one D tile + two gradient tiles instead of two + two.
-//   x_full[slot]  (in the receiver)  the partner's bits of this round have landed       (st.async stores count their bytes on it)
-//   x_empty[slot] (in the sender)    the partner has consumed the bits written two rounds ago
-//   p_own / p_rem (in the pair leader) sign tile of the own / the received tile is in tensor memory (both CTAs' epilogue warps)
-// Sign / zero bits of a 32-entry strip travel as two 32-bit words laid out for a cheap expansion: bit e = entry 2e,
-// bit 16 + e = entry 2e + 1 (e < 16), so that the packed FP16 pair e is ((bits << (15 - e)) & 0x80008000) | 1.0|1.0.
+// The bits of a 32-entry strip are laid out for a cheap expansion: bit e = entry 2e, bit 16 + e = entry 2e + 1 (e < 16), so
+// that the packed FP16 pair e is ((bits << (15 - e)) & 0x80008000) | 1.0|1.0.
+// (Round 2 first removed the D recompute of two channel groups with a cluster of four CTAs -- two CTA pairs splitting the
+// column tiles and shipping sign bits through distributed shared memory, st.async + mbarrier -- which reached 11.7 ms at
+// BASELINE configs[3]; it could only occupy 132 of the 148 SMs (profiles/r02b) and was superseded by the two-pass form.)
 __device__ __forceinline__ void expand_signs(uint32_t neg, uint32_t zero, uint32_t (&pk)[16]) {
     if (zero == 0u) {
 #pragma unroll
@@ -1292,363 +1272,6 @@ __device__ __forceinline__ void expand_signs(uint32_t neg, uint32_t zero, uint32
     }
 }
 
-constexpr int kQuadThreads = kThreads + 128;      // + warps 10..13: one per TMEM lane quarter, expand the received sign bits
-
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kQuadThreads, 1)
-fa_pos_tiles_quad(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                  const __grid_constant__ CUtensorMap tm_v, const PosGeom g, const PosArgs a) {
-    extern __shared__ unsigned char smraw[];
-    const uint32_t raw = smem_u32(smraw);
-    unsigned char *sm = smraw + (((raw + 1023u) & ~1023u) - raw);
-    constexpr int kElems = 64;                                      // FP16 operand elements per 128-byte row
-    constexpr int kStageBytes = kBoxBytes;                          // 16 KB: two K boxes (64 rows of K_j each) or one V box
-    const int S = g.quad_stages, nkc = g.nkh;
-    unsigned char *qreg = sm;
-    unsigned char *ring = sm + (size_t)nkc * kBoxBytes;
-    unsigned char *xchg = ring + (size_t)S * kStageBytes;           // [2 slots][2 halves][128 rows] x 16 bytes, written by the partner
-    uint64_t *full = reinterpret_cast<uint64_t *>(xchg + kXchgBytes);
-    uint64_t *empty = full + S;
-    uint64_t *q_full = empty + S;
-    uint64_t *d_full = q_full + 1;      // [2]
-    uint64_t *p_own = d_full + 2;       // [2]
-    uint64_t *p_rem = p_own + 2;        // [2]
-    uint64_t *o_full = p_rem + 2;
-    uint64_t *x_full = o_full + 1;      // [2]
-    uint64_t *x_empty = x_full + 2;     // [2]
-    uint64_t *c_done = x_empty + 2;     // [2] this CTA's conversion warps are done with the D buffer (its spare columns may be written)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(c_done + 2);
-    double *red = reinterpret_cast<double *>(c_done + 3);
-    int *flag = reinterpret_cast<int *>(red + 2 * kEpiWarps);
-    float *projbuf = reinterpret_cast<float *>(flag + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = (rank & 1u) == 0;                            // of its pair
-    const int grp = (int)(rank >> 1);                               // channel group = pair index inside the cluster
-    const uint32_t partner = rank ^ 2u;                             // same rows, other channel group
-    const int T = g.tiles, Th = T / 2;
-    const int pairidx = blockIdx.x >> 2, js = pairidx / Th;
-    const int itile = 2 * (pairidx - js * Th) + (int)(rank & 1u), b = blockIdx.z;
-    const int nt = T / g.jsplit, j0 = js * nt, nr = nt / 2;         // rounds: one own + one received column tile each
-    const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], vrows = gN / 2;
-    const uint32_t vbytes = (uint32_t)vrows * 128u;
-    const int row_q = b * g.Npad + itile * kTile;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tm_q);
-        prefetch_tmap(&tm_k);
-        prefetch_tmap(&tm_v);
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&d_full[i], 1);
-            mbar_init(&p_own[i], 2 * kEpiWarps);
-            mbar_init(&p_rem[i], 2 * 4);            // the four expansion warps of both CTAs
-            mbar_init(&x_full[i], 1);               // armed per round with the 4 KB the partner's st.async stores deliver
-            mbar_init(&x_empty[i], 4);              // the partner's four expansion warps
-            mbar_init(&c_done[i], kEpiWarps);
-        }
-        mbar_init(o_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
-    fence_before_sync();
-    cluster_sync();
-    fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    int slot = 0;
-    uint32_t ph = 0;
-#define RING_ADVANCE() do { if (++slot == S) { slot = 0; ph ^= 1; } } while (0)
-
-    if (warp == 0) {
-        // ===================================== TMA producer (every CTA, for its own shared memory) =====================================
-        long long w_empty = 0;
-        const long long t_begin = clock64();
-        if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(q_full, 2u * (uint32_t)nkc * kBoxBytes);
-            for (int kc = 0; kc < nkc; ++kc) tma_load_2d_pair(qreg + (size_t)kc * kBoxBytes, &tm_q, q_full, kc * kElems, row_q);
-        }
-        __syncwarp();
-#define STAGE_FILL(bytes_per_cta, ...)                                                                   \
-        do {                                                                                             \
-            TWAIT(w_empty, mbar_wait(&empty[slot], ph ^ 1, 21));                                         \
-            if (elect_one()) {                                                                           \
-                unsigned char *dst = ring + (size_t)slot * kStageBytes;                                  \
-                uint64_t *bar = &full[slot];                                                             \
-                if (leader) mbar_arrive_expect_tx(bar, 2u * (uint32_t)(bytes_per_cta));                  \
-                __VA_ARGS__                                                                              \
-            }                                                                                            \
-            __syncwarp();                                                                                \
-            RING_ADVANCE();                                                                              \
-        } while (0)
-        auto load_k = [&](int j) {
-            const int row_k = b * g.Npad + j * kTile + (int)(rank & 1u) * (kTile / 2);       // this CTA's 64 rows of K_j
-            for (int kc0 = 0; kc0 < nkc; kc0 += 2) {
-                const int nu = min(2, nkc - kc0);
-                STAGE_FILL(nu * kPairKBox, {
-                    for (int u = 0; u < nu; ++u) tma_load_2d_pair(dst + (size_t)u * kPairKBox, &tm_k, bar, (kc0 + u) * kElems, row_k);
-                });
-            }
-        };
-        auto load_v = [&](int j) {
-            const int row_v = b * g.Kc + gbeg + (int)(rank & 1u) * vrows;                    // this CTA's half of the group's channels
-            for (int jc = 0; jc < 2; ++jc) STAGE_FILL(vbytes, { tma_load_2d_pair(dst, &tm_v, bar, j * kTile + jc * kElems, row_v); });
-        };
-        load_k(j0 + grp);
-        for (int k = 0; k < nr; ++k) {
-            if (k + 1 < nr) load_k(j0 + 2 * (k + 1) + grp);
-            load_v(j0 + 2 * k + grp);
-            load_v(j0 + 2 * k + (grp ^ 1));
-        }
-#undef STAGE_FILL
-#ifdef DSRL_POS_TIMING
-        if (blockIdx.x == 0 && blockIdx.z == 0 && lane == 0) {
-            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
-            tm[0] = clock64() - t_begin; tm[1] = w_empty;
-        }
-#else
-        (void)t_begin; (void)w_empty;
-#endif
-    } else if (warp == 1) {
-        // ===================================== MMA issuer (the leader of each pair) =====================================
-        if (leader) {
-            constexpr uint64_t kBoxDesc = kBoxBytes >> 4, kKDesc = kPairKBox >> 4, kStageDesc = kStageBytes >> 4;
-            const uint64_t ring_desc = smem_desc_sw128(smem_u32(ring)), q_desc = smem_desc_sw128(smem_u32(qreg));
-            const uint32_t id_pos = idesc_f16(2 * kTile, kTile, false), id_neg = idesc_f16(2 * kTile, kTile, true);
-            const uint32_t id_g = idesc_f16(2 * kTile, gN, false);
-            const uint16_t cmask = (uint16_t)(3u << (2 * grp));     // the two CTAs of this pair
-            const int q_neg = g.C1p / 16;                           // first K step (16 channels) of branch 2 (subtracted)
-            long long w_full = 0, w_own = 0, w_rem = 0;
-            const long long t_begin = clock64();
-            auto gemm_d = [&](int k) {
-                const int buf = k & 1;
-                const uint32_t dcol = tmem + kColD + (uint32_t)buf * kTile;
-                for (int kc0 = 0; kc0 < nkc; kc0 += 2) {
-                    TWAIT(w_full, mbar_wait(&full[slot], ph, 22));
-                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
-                    const int ss = slot;
-                    RING_ADVANCE();
-                    fence_after_sync();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int kc = kc0 + u;
-                            if (kc < nkc) {
-                                const uint64_t ad = q_desc + (uint64_t)kc * kBoxDesc, bd = sd + (uint64_t)u * kKDesc;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    mma_f16_ss_pair(dcol, ad + 2 * ks, bd + 2 * ks, 4 * kc + ks >= q_neg ? id_neg : id_pos, (kc | ks) != 0);
-                            }
-                        }
-                        umma_commit_pair(&empty[ss], cmask);
-                        if (kc0 + 2 >= nkc) umma_commit_pair(&d_full[buf], cmask);
-                    }
-                    __syncwarp();
-                }
-            };
-            // which = 0: the tile this pair converted itself (packed signs at columns [0,32) and [64,96) of the buffer),
-            // which = 1: the tile received from the other pair (columns [32,64) and [96,128))
-            auto gemm_g = [&](int k, int which, bool last) {
-                const int buf = k & 1;
-                const uint32_t pcol = tmem + kColD + (uint32_t)buf * kTile + (uint32_t)which * 32u;
-                if (which) TWAIT(w_rem, mbar_wait(&p_rem[buf], (k >> 1) & 1, 23)); else TWAIT(w_own, mbar_wait(&p_own[buf], (k >> 1) & 1, 23));
-                for (int jc = 0; jc < 2; ++jc) {
-                    TWAIT(w_full, mbar_wait(&full[slot], ph, 24));
-                    const uint64_t sd = ring_desc + (uint64_t)slot * kStageDesc;
-                    const int ss = slot;
-                    RING_ADVANCE();
-                    fence_after_sync();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_f16_ts_pair(tmem, pcol + (uint32_t)(jc * 64 + ks * 8), sd + 2 * ks, id_g, (k | which | jc | ks) != 0);
-                        umma_commit_pair(&empty[ss], cmask);
-                        if (last && jc == 1) umma_commit_pair(o_full, cmask);
-                    }
-                    __syncwarp();
-                }
-            };
-            mbar_wait(q_full, 0, 25);
-            gemm_d(0);
-            for (int k = 0; k < nr; ++k) {
-                if (k + 1 < nr) gemm_d(k + 1);
-                gemm_g(k, 0, false);
-                gemm_g(k, 1, k == nr - 1);
-            }
-#ifdef DSRL_POS_TIMING
-            if (blockIdx.x == 0 && blockIdx.z == 0 && lane == 0) {
-                long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
-                tm[2] = clock64() - t_begin; tm[3] = w_full; tm[4] = w_own; tm[5] = w_rem;
-            }
-#else
-            (void)t_begin; (void)w_full; (void)w_own; (void)w_rem;
-#endif
-        }
-    } else if (warp < 2 + kEpiWarps) {
-        // ===================================== conversion warps: the tiles this pair computed =====================================
-        // |D| sum, near-tie listing, packed FP16 signs -> own tensor memory, sign / zero bits -> the partner CTA
-        const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t x_remote = map_to_cta(xchg, partner) + (uint32_t)((half * kTile + r) * 16);      // where this thread's bits go
-        const uint32_t xfull_remote = map_to_cta(x_full, partner);
-        const float tau = g.exact ? __ldg(a.tau + b) : 0.f;
-        const int nsub = g.fnsub;
-        const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * nsub + (size_t)((2 * js + half) * 2 + grp);
-        unsigned nlisted = 0;
-        double acc = 0.0;
-        float facc = 0.f;
-        long long w_d = 0, w_xe = 0, t_conv = 0, t_ship = 0;
-        const long long t_begin = clock64();
-        for (int k0 = 0; k0 < nr; k0 += 8) {
-        const int k1 = min(k0 + 8, nr);
-#pragma unroll 1
-        for (int k = k0; k < k1; ++k) {
-            const int buf = k & 1, j = j0 + 2 * k + grp;
-            const uint32_t php = (uint32_t)(k >> 1) & 1u;
-            TWAIT(w_d, mbar_wait(&d_full[buf], php, 26));
-            fence_after_sync();
-#ifdef DSRL_POS_TIMING
-            const long long t1 = clock64();
-#endif
-            const bool diag = j == itile;
-            float tsum = 0.f;
-            uint32_t negm[2], zerom[2];
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int cg = 2 * half + s;
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + cg * 32), v);
-                tmem_ld_wait();
-                if (diag && cg == q) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) if (e == lane) v[e] = 0u;
-                }
-                float zmin = 3.0e38f;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float x = __uint_as_float(v[e]);
-                    tsum += fabsf(x);
-                    zmin = fminf(zmin, fabsf(x));
-                }
-                if (zmin < tau) {                            // near ties (exact signs), see epilogue_role
-                    uint32_t m = 0u, neg = 0u;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float ax = fabsf(__uint_as_float(v[e]));
-                        m |= (ax < tau && ax != 0.f) ? (1u << e) : 0u;
-                        neg |= (v[e] >> 31) << e;
-                    }
-                    while (m) {
-                        const int e = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (nlisted < (unsigned)g.fsub) a.fent[gsub * g.fsub + nlisted] = (uint32_t)(j * kTile + cg * 32 + e) | (((neg >> e) & 1u) << 31);
-                        ++nlisted;
-                    }
-                }
-                uint32_t pk[16], M = 0u, Z = 0u;
-                if (zmin != 0.f) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const uint32_t sg = __byte_perm(v[2 * e], v[2 * e + 1], 0x7632) & 0x80008000u;
-                        pk[e] = sg | 0x3c003c00u;
-                        M = (M >> 1) | sg;                   // after the last pair: bit e = sign of entry 2e, bit 16 + e = of entry 2e + 1
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const uint32_t lo = v[2 * e], hi = v[2 * e + 1];
-                        const uint32_t zz = ((lo & 0x7fffffffu) ? 0u : 0x8000u) | ((hi & 0x7fffffffu) ? 0u : 0x80000000u);
-                        const uint32_t sg = __byte_perm(lo, hi, 0x7632) & 0x80008000u & ~zz;
-                        pk[e] = sg | (0x3c003c00u & ~((zz >> 2) | (zz >> 3) | (zz >> 4) | (zz >> 5)));      // no 1.0 where the entry is zero
-                        M = (M >> 1) | sg;
-                        Z = (Z >> 1) | zz;
-                    }
-                }
-                negm[s] = M; zerom[s] = Z;
-                tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + half * 64 + s * 16), pk);
-            }
-            tmem_st_wait();
-            fence_before_sync();
-#ifdef DSRL_POS_TIMING
-            const long long t2 = clock64();
-            t_conv += t2 - t1;
-#endif
-            if (k >= 2) TWAIT(w_xe, mbar_wait(&x_empty[buf], php ^ 1u, 27));       // the partner has expanded what this slot held two rounds ago
-            st_async_v4(x_remote + (uint32_t)buf * (kXchgBytes / 2), xfull_remote + (uint32_t)buf * 8u, negm[0], negm[1], zerom[0], zerom[1]);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_leader(&p_own[buf]);
-                mbar_arrive(&c_done[buf]);
-            }
-            facc += tsum;
-#ifdef DSRL_POS_TIMING
-            t_ship += clock64() - t2;
-#endif
-        }
-        acc += (double)facc;
-        facc = 0.f;
-        }
-        if (g.exact) a.fcnt[gsub] = nlisted;
-#ifdef DSRL_POS_TIMING
-        if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 64) {
-            long long *tm = reinterpret_cast<long long *>(a.sum_out) + 8;
-            tm[6] = clock64() - t_begin; tm[7] = w_d; tm[9] = w_xe; tm[10] = t_conv; tm[11] = t_ship;
-        }
-#else
-        (void)t_begin; (void)w_d; (void)w_xe; (void)t_conv; (void)t_ship;
-#endif
-        EpiCtx c;
-        c.d_full = d_full; c.p_full = p_own; c.o_full = o_full; c.red = red; c.flag = flag; c.proj = projbuf; c.tmem = tmem;
-        c.itile = itile; c.js = js; c.grp = grp; c.b = b; c.j0 = j0; c.nt = nt; c.gN = gN; c.gbeg = gbeg; c.T = T;
-        c.part_index = (int)(blockIdx.z * gridDim.x + blockIdx.x);               // every CTA converted its own share of the D tiles
-        c.nparts = (int)(gridDim.x * gridDim.z);
-        c.sub = 0; c.nsub = nsub;
-        epilogue_finish<true, true>(g, a, c, acc);
-    } else {
-        // ===================================== expansion warps: the tiles the other pair computed =====================================
-        // sign / zero bits from this CTA's exchange slot -> packed FP16 signs in the spare columns of the same D buffer
-        const int q = warp & 3, r = q * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t xempty_remote = map_to_cta(x_empty, partner);
-        long long w_xf = 0;
-        for (int k = 0; k < nr; ++k) {
-            const int buf = k & 1;
-            const uint32_t php = (uint32_t)(k >> 1) & 1u;
-            if (warp == 2 + kEpiWarps && lane == 0) mbar_arrive_expect_tx(&x_full[buf], kXchgBytes / 2);     // this round's 4 KB
-            TWAIT(w_xf, mbar_wait(&x_full[buf], php, 28));
-            mbar_wait(&c_done[buf], php, 29);          // the spare columns still hold D until this CTA's conversion warps have read it
-            fence_after_sync();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint4 bits = *reinterpret_cast<const uint4 *>(xchg + (size_t)buf * (kXchgBytes / 2) + (size_t)((h * kTile + r) * 16));
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    uint32_t pk[16];
-                    expand_signs(s ? bits.y : bits.x, s ? bits.w : bits.z, pk);
-                    tmem_st16(tmem + lane_addr + kColD + (uint32_t)(buf * kTile + h * 64 + 32 + s * 16), pk);
-                }
-            }
-            tmem_st_wait();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_leader(&p_rem[buf]);
-                mbar_arrive_cluster_relaxed(xempty_remote + (uint32_t)buf * 8u);
-            }
-        }
-#ifdef DSRL_POS_TIMING
-        if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == kThreads) reinterpret_cast<long long *>(a.sum_out)[8 + 8] = w_xf;
-#else
-        (void)w_xf;
-#endif
-    }
-#undef RING_ADVANCE
-
-    fence_before_sync();
-    cluster_sync();                         // MMAs read peer shared / tensor memory, partners write each other's exchange slots
-    if (warp == 1) tmem_dealloc2(tmem, kTmemCols);
-}
 
 #include "fa_position_ab.cuh"      // the symmetric two-pass form (fa_pos_dsign, fa_pos_grad, sign planes)
 
@@ -2079,6 +1702,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     pex.Ppm = reinterpret_cast<float *>(ws + wo.Ppm);
     pex.inv64 = reinterpret_cast<double *>(ws + wo.inv64);
     pex.stats = reinterpret_cast<unsigned long long *>(saved + 8);
+    float ksigma = 3.5f, tau_r = kRound11;
     ResolveArgs rex;
     rex.Ppm = pex.Ppm; rex.inv64 = pex.inv64; rex.stats = pex.stats;
     rex.fcnt = reinterpret_cast<unsigned *>(ws + wo.fcnt);
@@ -2089,11 +1713,12 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     // FP16 form: the FP16 copies are the only ones written (and read back by the normalisation Jacobian)
     if (g.exact) {
         fa_pos_pack<true><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
-        DSRL_LAUNCH_CHECK();
-        float ksigma = 3.5f;
         if (const char *e = getenv("DSRL_POS_KSIGMA")) { const float v = (float)atof(e); if (v >= 0.f && v < 1e6f) ksigma = v; }   // tuning / test hook
-        const float r = g.split ? kRound11 * kRound11 : kRound11;      // 3xTF32: the products missing from the split are second order
-        fa_pos_tau<<<B, 1024, 0, st>>>(g, pex.Ppm, pex.inv64, r * r, kAccNoise * kAccNoise, ksigma, reinterpret_cast<float *>(ws + wo.tau));
+        tau_r = g.split ? kRound11 * kRound11 : kRound11;      // 3xTF32: the products missing from the split are second order
+        if (!(need_grad && g.ab)) {        // the two-pass form computes the threshold in pass A's prologue (one launch and ~20 us less)
+            DSRL_LAUNCH_CHECK();
+            fa_pos_tau<<<B, 1024, 0, st>>>(g, pex.Ppm, pex.inv64, tau_r * tau_r, kAccNoise * kAccNoise, ksigma, reinterpret_cast<float *>(ws + wo.tau));
+        }
     } else {
         fa_pos_pack<false><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
     }
@@ -2152,6 +1777,8 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     if (fused_out) *fused_out = a.direct;
     const dim3 grid(need_grad ? g.tiles * g.jsplit : g.tiles, need_grad ? g.G : 1, B);
     a.sb = rex.sb;
+    a.Ppm = pex.Ppm; a.inv64 = pex.inv64; a.tau_out = reinterpret_cast<float *>(ws + wo.tau);
+    a.tau_r2 = tau_r * tau_r; a.tau_floor2 = kAccNoise * kAccNoise; a.tau_ksigma = ksigma;
     if (need_grad && g.ab) {
         // symmetric two-pass form (fa_position_ab.cuh): D tiles j >= i -> loss, near-tie lists, sign planes; [exact signs: the
         // resolve pass sets the bits of the near ties]; sign planes -> gradient contraction -> dX / dP
@@ -2174,13 +1801,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
         const bool same = g.G == 1 || g.gcnt[0] == g.gcnt[1];
         if (same) {
             CUtensorMap tm_k, tm_v;
-            if (g.quad) {
-                if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
-                if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
-                if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;
-                if ((rc = opt_in_smem(fa_pos_tiles_quad, g.quad_smem_bytes))) return rc;
-                fa_pos_tiles_quad<<<dim3(2 * g.tiles * g.jsplit, 1, B), kQuadThreads, g.quad_smem_bytes, st>>>(tm_pm, tm_k, tm_v, g, a);
-            } else if (g.half) {
+            if (g.half) {
                 if ((rc = make_map(&tm_pm, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile, true))) return rc;
                 if ((rc = make_map(&tm_k, FpmH, (uint64_t)B * g.Npad, (uint64_t)g.Kc, kTile / 2, true))) return rc;
                 if ((rc = make_map(&tm_v, FcmH, (uint64_t)B * g.Kc + kTile, (uint64_t)g.Npad, g.gcnt[0] / 2, true))) return rc;

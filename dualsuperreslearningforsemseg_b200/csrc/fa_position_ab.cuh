@@ -203,7 +203,39 @@ fa_pos_dsign(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         const int q = warp & 3, r = q * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const bool listing = g.exact != 0;
-        const float tau = listing ? __ldg(a.tau + b) : 0.f;
+        float tau = 0.f;
+        if (listing) {
+            // the tie threshold of this sample, while the operand rows load: the arithmetic of fa_pos_tau, operation for operation
+            // (every CTA of the sample derives the same bits; the fused kernels use that kernel, and the near-tie lists of the two
+            // forms are compared entry for entry by the tests)
+            const int et = threadIdx.x - 64, M = g.N < 64 ? g.N : 64, step = g.N / M;
+            float mu = 0.f;
+            if (et < g.Kc) {
+                const double *inv = a.inv64 + ((size_t)b * 2 + (et >= g.C1p)) * g.Npad;
+                const float *pc = a.Ppm + (size_t)b * g.Npad * g.Kc + et;
+                float m0 = 0.f, m1 = 0.f;
+#pragma unroll 8
+                for (int m = 0; m < M; m += 2) { const int i = m * step; const float f = pc[(size_t)i * g.Kc] * (float)inv[i]; m0 = fmaf(f, f, m0); }
+#pragma unroll 8
+                for (int m = 1; m < M; m += 2) { const int i = m * step; const float f = pc[(size_t)i * g.Kc] * (float)inv[i]; m1 = fmaf(f, f, m1); }
+                mu = (m0 + m1) / (float)M;
+            }
+            float *redf = reinterpret_cast<float *>(red);
+            const float wsum = warp_sum(mu * mu);
+            if (lane == 0) redf[et >> 5] = wsum;
+            asm volatile("bar.sync 1, %0;" ::"n"(kDsignEpiThreads) : "memory");
+            if (et < 32) {
+                const float t = warp_sum(lane < kDsignEpiWarps ? redf[lane] : 0.f);
+                if (lane == 0) {
+                    const float tv = a.tau_ksigma * sqrtf(2.f * a.tau_r2 * t + a.tau_floor2);
+                    redf[32] = tv;
+                    if (blockIdx.x == 0) a.tau_out[b] = tv;          // for the resolve pass's statistics
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDsignEpiThreads) : "memory");
+            tau = redf[32];
+            asm volatile("bar.sync 1, %0;" ::"n"(kDsignEpiThreads) : "memory");      // red is reused by the loss reduction
+        }
         const size_t gsub = ((size_t)b * g.Npad + (size_t)itile * kTile + r) * g.fnsub + (size_t)(4 * chunk + cg);
         uint2 *srow = reinterpret_cast<uint2 *>(a.sb + ((size_t)b * sign_blocks(T) + sign_block_index(T, itile, max(jbeg, itile))) * (kSignBlock / 16) + (size_t)(cg >> 1) * kTile + r) + (cg & 1);
         unsigned nlisted = 0;

@@ -262,24 +262,5 @@ __device__ __forceinline__ void mma_ts_pair(uint32_t d, uint32_t a, uint64_t b, 
     if (kF16) mma_f16_ts_pair(d, a, b, id, acc); else mma_tf32_ts_pair(d, a, b, id, acc);
 }
 
-// ---- distributed shared memory between the CTAs of a cluster (sign-tile exchange of fa_pos_tiles_quad) ------------------
-// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-// 16 bytes into another CTA's shared memory; the store itself signals `mbar` (a barrier in the same CTA as `addr`) with its
-// byte count when it has landed -- no fence and no separate arrival on the sender's side (a release at cluster scope costs
-// ~2000 cycles here: it drains the thread's memory operations device-wide)
-__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%2, %3, %4, %5}, [%1];"
-                 ::"r"(addr), "r"(mbar), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-// arrive on a barrier in another CTA without ordering anything (the signal itself is the message: "I have consumed your data")
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-
 }  // namespace tc
 }  // namespace dsrl

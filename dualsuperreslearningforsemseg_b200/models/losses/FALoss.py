@@ -48,7 +48,7 @@ _size_cache = {}
 
 def _layout_hooks():
     """Test / tuning hooks of the library that change the workspace layout (part of every size-cache key)."""
-    return tuple(os.environ.get(k) for k in ("DSRL_POS_JSPLIT", "DSRL_POS_AB", "DSRL_POS_ACHUNK", "DSRL_POS_QUAD", "DSRL_POS_PAIR"))
+    return tuple(os.environ.get(k) for k in ("DSRL_POS_JSPLIT", "DSRL_POS_AB", "DSRL_POS_ACHUNK", "DSRL_POS_PAIR"))
 
 
 def _sizes(mode, precision, B, C1, C2, H, W, k):

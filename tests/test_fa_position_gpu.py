@@ -75,7 +75,7 @@ def test_matches_autograd_golden(name):
 
 CASES = [
     # (shape1, shape2, k, reduction): ragged N (not a multiple of 128), channel padding, one and two TMEM channel
-    # groups (equal groups at FP16: the cluster-of-four kernel), operand chunks resident and streamed
+    # groups, operand chunks resident and streamed; FP16 operands with an even tile count: the symmetric two-pass form
     ((2, 64, 32, 32), (2, 64, 32, 32), 1, "mean"),
     ((1, 128, 24, 40), (1, 128, 24, 40), 1, "mean"),
     ((1, 40, 50, 30), (1, 33, 50, 30), 2, "sum"),
@@ -87,6 +87,7 @@ CASES = [
     ((1, 3, 32, 32), (1, 19, 32, 32), 1, "mean"),        # the real model's channel counts (RGB / 19 classes)
     ((1, 200, 24, 40), (1, 200, 24, 40), 1, "mean"),     # two groups, 64 padded positions (zero rows / columns of D)
     ((2, 256, 32, 64), (2, 256, 32, 64), 1, "sum"),      # two groups, 16 row tiles, batch 2
+    ((1, 48, 64, 128), (1, 80, 64, 128), 2, "mean"),     # pooling + the two-pass form: dP and the unpool pass, unequal branches in one group
 ]
 
 
@@ -162,7 +163,7 @@ def test_full_size_sample_of_config4():
 
 def test_full_size_c256_sampled_rows():
     """BASELINE configs[3] at its bench size for one sample -- N = 32768, C = 256 per branch, relu(randn) inputs, FP16 operands:
-    the bench's exact kernels (cluster of four, column split, near-tie resolution).  The float64 oracle is evaluated on 384
+    the bench's exact kernels (two-pass form, column split at one sample, near-tie resolution).  The float64 oracle is evaluated on 384
     sampled positions (their gradient columns are exact); the loss is cross-checked between the gradient kernel, the
     forward-only kernel and the 3xTF32 path."""
     x1, x2 = pos_inputs((1, 256, 128, 256), (1, 256, 128, 256), 54321)
@@ -233,22 +234,6 @@ def test_two_pass_column_chunks_agree(chunk, monkeypatch):
     assert relnorm(d1, base[1]) <= 1e-6 and relnorm(d2, base[2]) <= 1e-6
 
 
-def test_cluster_of_four_matches_the_pair_kernel(monkeypatch):
-    """Two equal channel groups at FP16, fused kernels (DSRL_POS_AB=0): the cluster-of-four kernel (each D tile computed
-    once, signs shipped through distributed shared memory) against the CTA-pair kernel that computes every D tile in both
-    groups -- same loss to FP32 summation order, same gradients (the sign tiles are bit-identical), same near-tie lists."""
-    x1, x2 = pos_inputs((2, 256, 32, 64), (2, 256, 32, 64), 11)
-    monkeypatch.setenv("DSRL_POS_AB", "0")
-    res = {}
-    for quad in ("1", "0"):
-        monkeypatch.setenv("DSRL_POS_QUAD", quad)
-        res[quad] = run(x1, x2, 1, "mean", precision="f16", stats=True)
-    (la, a1, a2, sa), (lb, b1, b2, sb) = res["1"], res["0"]
-    assert abs(la - lb) <= 1e-6 * abs(lb), (la, lb)
-    assert relnorm(a1, b1) <= 1e-6 and relnorm(a2, b2) <= 1e-6, (relnorm(a1, b1), relnorm(a2, b2))
-    assert sa["listed"] == sb["listed"] and sa["corrected"] == sb["corrected"], (sa, sb)
-
-
 @pytest.mark.parametrize("exact", [True, False])
 def test_repeatable_and_one_sided_grad(exact):
     from dualsuperreslearningforsemseg_b200.models.losses import FALoss
@@ -284,8 +269,8 @@ def test_upstream_gradient_and_retained_graph():
 
 def test_identical_branches_give_zero_loss():
     # S1 - S2 is accumulated as ONE contraction (branch-2 products subtracted), so identical branches cancel to FP32
-    # accumulation noise rather than to an exact 0 (typical losses are 0.05-0.2); with two channel groups (C = 256) the
-    # zero entries travel between the CTA pairs as zero bits
+    # accumulation noise rather than to an exact 0 (typical losses are 0.05-0.2); in the two-pass form exact zeros travel
+    # to the gradient pass as is-zero bits of the sign planes
     for shape in ((1, 64, 16, 16), (1, 256, 16, 32)):
         x1, _ = pos_inputs(shape, shape, 3)
         for prec in PRECISIONS:

@@ -24,7 +24,7 @@ CASES = [
     ((1, 96, 12, 32), (1, 96, 12, 32), 1, "sum"),
     ((1, 3, 32, 32), (1, 19, 32, 32), 1, "mean"),
     ((1, 64, 64, 128), (1, 64, 64, 128), 1, "mean"),
-    ((1, 200, 24, 40), (1, 200, 24, 40), 1, "mean"),      # two channel groups (quad kernel), 64 padded positions
+    ((1, 200, 24, 40), (1, 200, 24, 40), 1, "mean"),      # two channel groups, 64 padded positions
     ((2, 256, 32, 64), (2, 256, 32, 64), 1, "sum"),
 ]
 

@@ -39,6 +39,6 @@ if prec == "f16" and os.environ.get("DSRL_POS_AB", "1") != "0" and T % 2 == 0:
           f"  pass B issuer of the last pair of row tiles (all column tiles below the diagonal): loop {tm[8]} = {tm[8] / max(tm[16], 1):.0f} clk/tile, wait_full {tm[9]}, wait_p_full {tm[10]}\n"
           f"  pass B conversion warp: loop {tm[17]}, wait_p_empty {tm[18]} | epilogue (Jacobian, dX) {tm[19]}: wait last MMAs {tm[20]}, projection pass {tm[21]}, output pass {tm[22]}")
     sys.exit(0)
-print(f"B={B} C={C} prec={prec} exact={exact} tiles={T} QUAD={os.environ.get('DSRL_POS_QUAD', '1')}: producer total {tm[0]} wait_empty {tm[1]} | "
+print(f"B={B} C={C} prec={prec} exact={exact} tiles={T}: producer total {tm[0]} wait_empty {tm[1]} | "
       f"mma total {tm[2]} wait_full {tm[3]} wait_p(own) {tm[4]} wait_p_rem/drain {tm[5]} | epi total {tm[6]} wait_d {tm[7]} wait_xfull {tm[8]} wait_xempty {tm[9]}"
       f" conv {tm[10]} ship {tm[11]} | per column tile: mma {tm[2] / T:.0f} clk")
