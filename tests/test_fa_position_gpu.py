@@ -219,6 +219,34 @@ def test_two_pass_form_matches_the_fused_kernels(shape, exact, monkeypatch):
         assert sa["dropped"] == 0 and sb["dropped"] == 0
 
 
+def test_two_pass_form_on_random_geometries():
+    """Seeded sweep over geometries that take the two-pass form (FP16 operands, even tile count): batch, unequal channel
+    counts with padding, one or two channel groups, ragged N, pooling, both reductions -- loss and gradients against the
+    float64 oracle at the north star's tolerances, no near tie dropped."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 10:
+        B = int(rng.integers(1, 4))
+        C1, C2 = int(rng.integers(3, 257)), int(rng.integers(3, 257))
+        k = int(rng.choice([1, 1, 2]))
+        h, w = int(rng.integers(8, 49)), int(rng.integers(8, 49))
+        N = h * w
+        if ((N + 127) // 128) % 2 or N > 2304:
+            continue
+        two_groups = ((C1 + 31) // 32 + (C2 + 31) // 32) * 32 > 256
+        if two_groups and (C1 + 31) // 32 != (C2 + 31) // 32:
+            continue                                           # unequal channel groups run the fused single-CTA kernel
+        red = str(rng.choice(["mean", "sum"]))
+        x1, x2 = pos_inputs((B, C1, h * k, w * k), (B, C2, h * k, w * k), int(rng.integers(1 << 30)))
+        go = float(rng.uniform(0.2, 2.0))
+        ol, o1, o2 = fa_oracle.fa_position(x1, x2, k, red, grad_out=go)
+        loss, d1, d2, st = run(x1, x2, k, red, go=go, precision="f16", stats=True)
+        assert abs(loss - ol) <= LOSS_RTOL * abs(ol), ((B, C1, C2, h, w, k, red), loss, ol)
+        assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, ((B, C1, C2, h, w, k, red), relnorm(d1, o1), relnorm(d2, o2), st)
+        assert st["dropped"] == 0, st
+        done += 1
+
+
 @pytest.mark.parametrize("chunk", ["1", "3", "8"])
 def test_two_pass_column_chunks_agree(chunk, monkeypatch):
     """Pass A may cut the column range of a pair of row tiles into chunks (small grids; DSRL_POS_ACHUNK forces the chunk
