@@ -113,3 +113,55 @@ def test_host_pipeline_graph_replay():
         ref_loss, ref_d1, ref_d2 = _autograd(torch.from_numpy(y1).to(dev), torch.from_numpy(y2).to(dev), 8, 0.5)
         assert abs(loss - float(ref_loss)) <= 1e-6 * abs(float(ref_loss))
         assert float((pipe.dx1 - ref_d1).norm() / ref_d1.norm()) <= 1e-6 and float((pipe.dx2 - ref_d2).norm() / ref_d2.norm()) <= 1e-6
+
+
+@pytest.mark.parametrize("case", [
+    ((2, 64, 16, 32), (2, 64, 16, 32), 1, "f16", True),        # two-pass form, one channel group
+    ((1, 200, 24, 40), (1, 200, 24, 40), 1, "f16", True),      # two groups, padded positions and channels
+    ((1, 48, 32, 64), (1, 80, 32, 64), 2, "f16", True),        # pooling: dP + unpool
+    ((1, 256, 16, 32), (1, 256, 16, 32), 1, "f16", False),     # tensor-core signs
+    ((1, 96, 12, 32), (1, 96, 12, 32), 1, "f16", True),        # odd tile count: fused single-CTA kernel
+    ((1, 64, 32, 32), (1, 64, 32, 32), 1, "tf32", True),       # fused pair kernel + resolve + finish
+    ((6, 1, 64, 128), (6, 1, 64, 128), 8, "reference", True),  # reference semantics, training shape
+])
+def test_calls_stay_inside_their_buffers(case):
+    """Guard bands instead of compute-sanitizer (closed on this pool): workspace, saved blob, gradients and loss are carved
+    out of one allocation with 64 KB canary regions between them; after a forward + backward through the C-ABI at exactly
+    the sizes the library asks for, every canary byte is intact (and the result equals the ordinary plan's)."""
+    import ctypes
+    from dualsuperreslearningforsemseg_b200 import _lib
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    from _inputs import pos_inputs
+    s1, s2, k, prec, exact = case
+    dev = torch.device("cuda", 0)
+    if prec == "reference":
+        a, b = fa_inputs(s1, "relu", 7)
+        kw = {}
+    else:
+        a, b = pos_inputs(s1, s2, 7)
+        kw = {"affinity": "position", "precision": prec, "exact_signs": exact}
+    x1, x2 = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    plan = FAPlan(s1, s2, subsample_factor=k, device=dev, **kw)
+    go = torch.full((), 0.75, device=dev)
+    ref = [t.clone() for t in plan.forward_backward(x1, x2, go)]
+    G = 65536
+    sizes = [plan.ws_bytes, plan.saved_bytes, x1.numel() * 4, x2.numel() * 4, 4]
+    offs, off = [], G
+    for n in sizes:
+        offs.append(off)
+        off += (n + 255) // 256 * 256 + G
+    arena = torch.full((off,), 0xA5, dtype=torch.uint8, device=dev)
+    ws, saved, d1, d2, loss = (arena[o:o + n] for o, n in zip(offs, sizes))
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    for _ in range(2):
+        _lib.check(_lib.lib().dsrl_fa_forward_backward(plan.mode, plan.prec, p(x1), p(x2), plan.B, plan.C1, plan.C2, plan.H, plan.W,
+                                                       plan.k, plan.red, p(go), p(loss), p(d1), p(d2), p(saved), plan.saved_bytes,
+                                                       p(ws), plan.ws_bytes, st))
+    torch.cuda.synchronize()
+    keep = torch.ones(off, dtype=torch.bool, device=dev)
+    for o, n in zip(offs, sizes):
+        keep[o:o + n] = False
+    assert bool((arena[keep] == 0xA5).all()), "a kernel wrote outside the buffers it was given"
+    assert torch.equal(loss.view(torch.float32).reshape(()), ref[0])
+    assert torch.equal(d1.view(torch.float32).reshape(x1.shape), ref[1]) and torch.equal(d2.view(torch.float32).reshape(x2.shape), ref[2])
