@@ -728,7 +728,7 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
         # executed: pass A computes the tiles j >= 2p of every pair of row tiles (T^2/2 + T of the T^2 tiles), pass B the whole
         # gradient contraction
         exec_flops_rank = (2.0 * kc * (0.5 + 1.0 / tiles) + 2.0 * kc) * b_local * N * N
-        kernels = "fa_pos_pack, " + ("fa_pos_tau, " if exact else "") + "fa_pos_dsign, " + ("fa_pos_resolve, " if exact else "") + "fa_pos_grad"
+        kernels = "fa_pos_pack, fa_pos_dsign, " + ("fa_pos_resolve, " if exact else "") + "fa_pos_grad" + (", fa_pos_finish" if b_local * tiles < 296 else "")
     else:
         # fused kernels: D is computed once per row tile except by the TF32 kernels with two channel groups (Kc > 256), which
         # compute it in both
