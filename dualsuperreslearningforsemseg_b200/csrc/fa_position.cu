@@ -265,21 +265,22 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
     const float inv_kk = 1.f / (float)(g.k * g.k);
 
     if (g.k == 1) {
-        // no pooling: one coalesced 128-byte row per (channel, strip); eight independent loads in flight per warp
+        // no pooling: one coalesced 128-byte row per (channel, strip); eight independent loads in flight per warp.  One loop per
+        // branch with a running row pointer: the kernel was bound by its instruction count (ncu r02g: issue slots 70 % busy at
+        // 3.5 TB/s), most of it index arithmetic around these loads and the stores below
         const size_t hw = (size_t)g.H * g.W;
-        for (int c8 = warp * 8; c8 < g.Kc; c8 += 64) {
-            float v[8];
+#pragma unroll 1
+        for (int br = 0; br < 2; ++br) {
+            const int Cr = br ? g.C2 : g.C1, Cp = br ? g.C2p : g.C1p;      // real / padded channels of the branch (Cp a multiple of 32)
+            const float *xr = (br ? x2 : x1) + ((size_t)b * Cr + warp * 8) * hw + (valid ? p : 0);
+            float *tr = T + ((br ? g.C1p : 0) + warp * 8) * 33 + lane;
+            for (int c8 = warp * 8; c8 < Cp; c8 += 64, xr += 64 * hw, tr += 64 * 33) {
+                float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = c8 + u;
-                const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
-                const bool ok = valid && c < g.Kc && cc < Cr;
-                const float *x = (br ? x2 : x1) + ((size_t)b * Cr + (ok ? cc : 0)) * hw + (ok ? p : 0);
-                v[u] = ok ? ldg_stream_f32(x) : 0.f;
+                for (int u = 0; u < 8; ++u) v[u] = (valid && c8 + u < Cr) ? ldg_stream_f32(xr + u * hw) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) tr[u * 33] = v[u];
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (c8 + u < g.Kc) T[(c8 + u) * 33 + lane] = v[u];
         }
     } else {
         // k x k mean (FALoss.py:23-24).  With k % 4 == 0 every window row is k/4 aligned 16-byte vectors and a warp's 32
@@ -345,11 +346,18 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
         nrm[((size_t)b * 2 + warp) * g.Npad + p] = n;
     }
     __syncthreads();
-    for (int c = warp; c < g.Kc; c += 8) {            // channel-major rows: 128 contiguous bytes per warp store
-        const int br = c >= g.C1p;
-        const float f = T[c * 33 + lane] * s_inv[br][lane];
-        if (Fcm) Fcm[((size_t)b * g.Kc + c) * g.Npad + p] = round_tf32(f);
-        if (FcmH) FcmH[((size_t)b * g.Kc + c) * g.Npad + p] = __float2half_rn(f);
+    {                                                 // channel-major rows: 128 (fp32) / 64 (FP16) contiguous bytes per warp store
+        const size_t o0 = ((size_t)b * g.Kc + warp) * g.Npad + p, ostep = (size_t)8 * g.Npad;
+        float *pc = Fcm ? Fcm + o0 : nullptr;
+        __half *ph = FcmH ? FcmH + o0 : nullptr;
+        const float *tr = T + warp * 33 + lane;
+        const float i1 = s_inv[0][lane], i2 = s_inv[1][lane];
+#pragma unroll 4
+        for (int c = warp; c < g.Kc; c += 8, tr += 8 * 33) {
+            const float f = *tr * (c >= g.C1p ? i2 : i1);
+            if (pc) { *pc = round_tf32(f); pc += ostep; }
+            if (ph) { *ph = __float2half_rn(f); ph += ostep; }
+        }
     }
     for (int q = warp; q < 32; q += 8) {              // position-major rows: Kc contiguous floats per position
         float *dst = Fpm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
