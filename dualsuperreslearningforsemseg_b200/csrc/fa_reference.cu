@@ -36,7 +36,7 @@ struct RefGeom {
 };
 
 struct RefSaved {  // byte offsets into the opaque `saved` blob
-    size_t P, S, sigma, u, v, dA, cnt, total;
+    size_t P, S, sigma, u, v, dA, cnt, gpart, gtick, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -77,6 +77,8 @@ inline RefSaved make_saved(const RefGeom &g) {
     s.v = off;      off = align_up(off + bc2 * g.w * 4, 16);
     s.dA = off;     off = align_up(off + bc2 * g.h * g.w * 4, 16);
     s.cnt = off;    off = align_up(off + bc2 * g.n * 4, 16);
+    s.gpart = off;  off = align_up(off + bc2 * (size_t)((g.h + 7) / 8) * 8, 16);   // fa_ref_grad_rows: <G^, P> per 8-row chunk
+    s.gtick = off;  off = align_up(off + bc2 * 4, 16);                            // ... and its last-CTA ticket per (b, c, branch)
     s.total = off;
     return s;
 }
@@ -103,10 +105,29 @@ inline PairsPlan make_pairs_plan(const RefGeom &g) {
 // prepare: pool, sigma/u1/v1, S
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPowerMaxM = 32;  // short side up to which the squaring + power-iteration solver is used
-struct PrepSmem { size_t A, Wm, vec, scratch, total; int sepW; };
+constexpr int kMidMaxM = 128;   // ... and up to which it is TRIED first (one M buffer aliases the pooled matrix), Jacobi being the fallback
+struct PrepSmem { size_t A, Wm, vec, scratch, total; int sepW; int mid; size_t M0; };
 inline PrepSmem make_prep_smem(const RefGeom &g, size_t limit) {
     PrepSmem s;
+    s.mid = 0; s.M0 = 0;
     const size_t a_bytes = align_up((size_t)g.h * g.lda * 4, 16);
+    if (g.m > kPowerMaxM && g.m <= kMidMaxM) {
+        // Large maps (e.g. 128 x 256 pooled cells): the one-sided Jacobi sweeps of a single CTA took 9.6 of the 10 ms of a
+        // forward + backward at w = 256.  The squaring solver is tried first: region X holds the pooled matrix, then the second
+        // matrix buffer of the squarings, then the pooled matrix again (reloaded from what this CTA wrote) for the power steps --
+        // and, should they not converge (tiny spectral gap), the Jacobi work area; region Y holds the first matrix buffer.
+        const size_t mm = align_up((size_t)g.m * g.m * 4, 16), jw = align_up((size_t)g.m_pad * g.L * 4, 16);
+        const size_t X = a_bytes > jw ? (a_bytes > mm ? a_bytes : mm) : (jw > mm ? jw : mm);
+        const size_t tail = align_up((size_t)(g.h + g.w + g.m_pad + 32) * 8, 16) + 40 * 8 + 16;
+        if (X + mm + tail <= limit) {
+            s.mid = 1; s.sepW = 0;
+            s.A = 0; s.Wm = 0; s.M0 = X;
+            s.vec = X + mm;
+            s.scratch = s.vec + align_up((size_t)(g.h + g.w + g.m_pad + 32) * 8, 16);
+            s.total = s.scratch + 40 * 8 + 16;
+            return s;
+        }
+    }
     const size_t w_bytes = g.m <= kPowerMaxM ? align_up((size_t)2 * g.m * g.m * 4, 16) : align_up((size_t)g.m_pad * g.L * 4, 16);
     const size_t tail = align_up((size_t)(g.h + g.w + g.m_pad + 32) * 8, 16) + 40 * 8 + 16;
     s.sepW = g.m <= kPowerMaxM || (a_bytes + w_bytes + tail) <= limit;   // the power solver never aliases
@@ -198,8 +219,13 @@ __device__ __forceinline__ T group_sum(T v, T *scratch /* >= 33 */, const Grp &g
 //  1) M = V V^T (fp32);  2) p squarings with trace normalisation -- M^(2^p) is numerically rank one unless the
 //  spectral gap is tiny;  3) fp64 power steps on V itself until sigma stalls (its error is second order in the
 //  vector error).  On exit xs (len m) and xl (len L) are unit vectors with V^T xs = sigma xl.
+// reload != nullptr: M1 aliases the pooled matrix -- it is rebuilt from `reload` (h x w, row-major, written by this CTA) into
+// sAw (row stride lda) once the squarings are done.  *stalled (if given) tells whether the power steps ended because sigma
+// stopped moving (converged) rather than at the iteration limit.
 __device__ double top_singular_power(const float *sA, int rs, int cs, int m, int L, float *M0, float *M1, double *xs,
-                                     double *xs2, double *xl, double *scratch, const Grp &grp) {
+                                     double *xs2, double *xl, double *scratch, const Grp &grp,
+                                     const float *reload = nullptr, float *sAw = nullptr, int h = 0, int w = 0, int lda = 0,
+                                     int *stalled = nullptr) {
     const int tid = grp.tid, nt = grp.nt, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     for (int o = tid; o < m * m; o += nt) {
         const int i = o / m, j = o - i * m;
@@ -227,6 +253,11 @@ __device__ double top_singular_power(const float *sA, int rs, int cs, int m, int
     int best = 0;
     for (int i = 1; i < m; ++i) if (cur[i * m + i] > cur[best * m + best]) best = i;
     if (tid < m) xs[tid] = (double)cur[tid * m + best];
+    if (reload != nullptr) {
+        grp.sync();
+        for (int cell = tid; cell < h * w; cell += nt) { const int py = cell / w; sAw[py * lda + (cell - py * w)] = reload[cell]; }
+    }
+    bool stall = false;
     double sig = 0.0, sig_prev = -1.0;
     for (int it = 0; it < 60; ++it) {
         grp.sync();
@@ -256,9 +287,10 @@ __device__ double top_singular_power(const float *sA, int rs, int cs, int m, int
         for (int i = 0; i < m; ++i) s2 += xs2[i] * xs2[i];
         sig = sqrt(s2);
         double *t = xs; xs = xs2; xs2 = t;
-        if (it >= 1 && fabs(sig - sig_prev) <= 1e-11 * sig) break;
+        if (it >= 1 && fabs(sig - sig_prev) <= 1e-11 * sig) { stall = true; break; }
         sig_prev = sig;
     }
+    if (stalled != nullptr) *stalled = stall || !(sig > 0.0);
     grp.sync();
     // final consistent pair: us = xs/|xs|, xl = V^T us, sigma = |xl|
     double ns = 0.0;
@@ -424,16 +456,17 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
     int *gcnt = reinterpret_cast<int *>(saved + so.cnt) + slot * g.n;
 
     // 1. pool (FALoss.py:23-24)
-    const bool small = g.m <= kPowerMaxM;
+    const bool small = g.m <= kPowerMaxM, mid = ps.mid != 0;
     const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     for (int cell = tid; cell < h * w; cell += nt) {
         const int py = cell / w, px = cell - py * w;
         const float v = pool_cell(x, g.W, g.k, py, px, vec4);
         gP[cell] = v;
-        if (ps.sepW) sA[py * lda + px] = v;
-        if (!small) { if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v; }
+        if (ps.sepW || mid) sA[py * lda + px] = v;
+        if (!small && !mid) { if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v; }
     }
     for (int i = tid; i < g.n; i += nt) gcnt[i] = 0;
+    if (tid == 0) reinterpret_cast<unsigned *>(saved + so.gtick)[slot] = 0u;
     __syncthreads();
 
     // 2. top singular triple (sigma, u1, v1)
@@ -446,6 +479,24 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
         if (!g.transposed) sigma = top_singular_power(sA, lda, 1, g.m, g.L, M0, M1, du, xs2a, dv, scratch, all);
         else               sigma = top_singular_power(sA, 1, lda, g.m, g.L, M0, M1, dv, xs2a, du, scratch, all);
     } else {
+      int conv = 0;
+      if (mid) {
+        // squarings + power steps first (see make_prep_smem); the vectors end up in du / dv like in the small case
+        float *M0 = reinterpret_cast<float *>(smraw + ps.M0), *M1 = sA;
+        const Grp all{tid, nt, 0};
+        if (!g.transposed) sigma = top_singular_power(sA, lda, 1, g.m, g.L, M0, M1, du, nrm, dv, scratch, all, gP, sA, h, w, lda, &conv);
+        else               sigma = top_singular_power(sA, 1, lda, g.m, g.L, M0, M1, dv, nrm, du, scratch, all, gP, sA, h, w, lda, &conv);
+        __syncthreads();
+        if (!conv) {                                         // uniform: every thread computed the same sigma sequence
+            for (int cell = tid; cell < h * w; cell += nt) {
+                const int py = cell / w, px = cell - py * w;
+                const float v = gP[cell];
+                if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v;
+            }
+            __syncthreads();
+        }
+      }
+      if (!conv) {
         // one-sided Jacobi in fp32, then one power step in fp64 (error in sigma is second order)
         jacobi_rows(sW, g.m, g.m_pad, g.L, flag);
         {
@@ -493,6 +544,7 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
         };
         if (!g.transposed) { mul_A(); normalise(du, h); mul_At(); sigma = normalise(dv, w); }
         else               { mul_At(); normalise(dv, w); mul_A(); sigma = normalise(du, h); }
+      }
     }
     const float sigf = (float)sigma;
     float *gu = reinterpret_cast<float *>(saved + so.u) + slot * h;
@@ -776,6 +828,117 @@ __global__ void fa_ref_grad(RefGeom g, RefSaved so, unsigned char *__restrict__ 
     for (int cell = tid; cell < h * w; cell += nt) {   // each thread re-reads exactly what it wrote
         const int y = cell / w, xo = cell - y * w;
         gdA[cell] = gdA[cell] / sigma - coef * su[y] * sv[xo];
+    }
+}
+
+// Wide maps (w > 64, where G + G^T no longer fits next to A^ in shared memory): the product above took 4.7 of the 6.3 ms of a
+// forward + backward at 128 x 256 pooled cells because ONE CTA per (b, c, branch) did all h * w * w multiply-adds with both G
+// operands read from global memory, one of them with stride w.  Here a CTA owns kGradRows rows of G^ (grid.z chunks), stages
+// 32 x 256 tiles of G + G^T in shared memory (both parts read along rows of G) and keeps one accumulator per owned row and
+// column; the summation order per cell is the one of fa_ref_grad (ascending x', one fmaf chain), so the two kernels agree bit
+// for bit.  <G^, P> goes through per-chunk partials and a self-resetting ticket: the last CTA of a (b, c, branch) adds them in
+// chunk order (deterministic) and applies the spectral-norm term to the whole map.
+constexpr int kGradRows = 8, kGradCols = 256, kGradTile = 32;
+inline size_t grad_rows_smem(const RefGeom &g) {
+    return align_up((size_t)kGradRows * g.w * 4, 16) + align_up((size_t)kGradTile * (kGradCols + 1) * 4, 16) + 40 * 8 + 16;
+}
+__global__ void __launch_bounds__(kGradCols) fa_ref_grad_rows(RefGeom g, RefSaved so, unsigned char *__restrict__ saved,
+                                                              const float *__restrict__ gfl, float g_scale,
+                                                              const double *__restrict__ partials, int num_partials,
+                                                              double loss_div, float *__restrict__ loss_out) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int tid = threadIdx.x, nt = kGradCols, h = g.h, w = g.w, ldt = kGradCols + 1;
+    float *sA = reinterpret_cast<float *>(smraw);                                                  // [kGradRows][w]
+    float *sT = reinterpret_cast<float *>(smraw + align_up((size_t)kGradRows * w * 4, 16));       // [kGradTile][ldt]
+    double *scratch = reinterpret_cast<double *>(smraw + align_up((size_t)kGradRows * w * 4, 16) + align_up((size_t)kGradTile * ldt * 4, 16));
+    int *s_last = reinterpret_cast<int *>(scratch + 40);
+
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && loss_out != nullptr) {  // deterministic loss finish
+        double s = 0.0;
+        for (int i = tid; i < num_partials; i += nt) s += partials[i];
+        s = block_sum(s, scratch);
+        if (tid == 0) {
+            *reinterpret_cast<double *>(saved) = s;
+            *loss_out = (float)(s / loss_div);
+        }
+        __syncthreads();
+    }
+
+    const int bc = blockIdx.x, br = blockIdx.y, y0 = blockIdx.z * kGradRows, nchunks = gridDim.z;
+    const int rows = min(kGradRows, h - y0);
+    const size_t slot = (size_t)br * g.BC + bc;
+    const float *gP = reinterpret_cast<const float *>(saved + so.P) + slot * h * w;
+    const int *gcnt = reinterpret_cast<const int *>(saved + so.cnt) + slot * g.n;
+    const float *gg = gfl ? gfl + slot * g.n : nullptr;
+    float *gdA = reinterpret_cast<float *>(saved + so.dA) + slot * h * w;
+    const float sigma = reinterpret_cast<const float *>(saved + so.sigma)[slot];
+    auto gval = [&](int idx) -> float { return gg ? gg[idx] : (float)gcnt[idx] * g_scale; };
+
+    for (int o = tid; o < kGradRows * w; o += nt) {
+        const int r = o / w;
+        sA[o] = r < rows ? gP[(size_t)(y0 + r) * w + (o - r * w)] / sigma : 0.f;
+    }
+
+    double inner = 0.0;
+    for (int cb = 0; cb < w; cb += kGradCols) {
+        float acc[kGradRows];
+#pragma unroll
+        for (int r = 0; r < kGradRows; ++r) acc[r] = 0.f;
+        const int xo = cb + tid;
+        for (int xp0 = 0; xp0 < w; xp0 += kGradTile) {
+            __syncthreads();
+            // G part of the tile: rows x' of G, this thread's column
+#pragma unroll 4
+            for (int xl = 0; xl < kGradTile; ++xl) {
+                const int xp = xp0 + xl;
+                sT[xl * ldt + tid] = (xp < w && xo < w) ? gval(xp * w + xo) : 0.f;
+            }
+            __syncthreads();
+            // G^T part: rows (cb + c) of G, 32 consecutive x' per warp
+            {
+                const int xl = tid & 31, xp = xp0 + xl;
+                for (int c = tid >> 5; c < kGradCols; c += kGradCols / 32) {
+                    if (xp < w && cb + c < w) sT[xl * ldt + c] += gval((cb + c) * w + xp);
+                }
+            }
+            __syncthreads();
+            const int lim = min(kGradTile, w - xp0);
+            for (int xl = 0; xl < lim; ++xl) {
+                const float t = sT[xl * ldt + tid];
+#pragma unroll
+                for (int r = 0; r < kGradRows; ++r) acc[r] = fmaf(sA[r * w + xp0 + xl], t, acc[r]);
+            }
+        }
+        if (xo < w) {
+#pragma unroll
+            for (int r = 0; r < kGradRows; ++r) {
+                if (r < rows) {
+                    const size_t cell = (size_t)(y0 + r) * w + xo;
+                    gdA[cell] = acc[r];
+                    inner += (double)acc[r] * (double)gP[cell];
+                }
+            }
+        }
+    }
+    inner = block_sum(inner, scratch);
+    double *gpart = reinterpret_cast<double *>(saved + so.gpart) + slot * nchunks;
+    if (tid == 0) {
+        gpart[blockIdx.z] = inner;
+        __threadfence();
+        const unsigned old = atomicInc(reinterpret_cast<unsigned *>(saved + so.gtick) + slot, (unsigned)nchunks - 1u);
+        *s_last = old == (unsigned)nchunks - 1u;
+    }
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    double tot = 0.0;
+    for (int i = 0; i < nchunks; ++i) tot += __ldcg(gpart + i);     // same order in every thread
+    const float coef = (float)(tot / ((double)sigma * (double)sigma));
+    const float *gu = reinterpret_cast<const float *>(saved + so.u) + slot * h;
+    const float *gv = reinterpret_cast<const float *>(saved + so.v) + slot * w;
+    for (int cell = tid; cell < h * w; cell += nt) {
+        const int y = cell / w, x = cell - y * w;
+        gdA[cell] = __ldcg(gdA + cell) / sigma - coef * gu[y] * gv[x];
     }
 }
 
@@ -1150,6 +1313,16 @@ int opt_in_smem(K kern, size_t bytes) {
 
 int launch_grad(const RefGeom &g, const RefSaved &so, unsigned char *saved, const float *gfl, float g_scale,
                 const double *partials, int num_partials, double loss_div, float *loss_out, int do_grad, cudaStream_t st) {
+    if (do_grad && g.w > 64) {
+        const size_t smem = grad_rows_smem(g);
+        if (smem > kSmemLimit) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(reference): pooled map %dx%d too wide for shared memory", g.h, g.w);
+        int rc = opt_in_smem(fa_ref_grad_rows, smem);
+        if (rc) return rc;
+        fa_ref_grad_rows<<<dim3(g.BC, 2, (g.h + kGradRows - 1) / kGradRows), kGradCols, smem, st>>>(g, so, saved, gfl, g_scale, partials,
+                                                                                              num_partials, loss_div, loss_out);
+        DSRL_LAUNCH_CHECK();
+        return DSRL_OK;
+    }
     GradSmem gs = make_grad_smem(g);
     if (gs.total > kSmemLimit) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(reference): pooled map %dx%d too large for shared memory", g.h, g.w);
     int rc = opt_in_smem(fa_ref_grad, gs.total);

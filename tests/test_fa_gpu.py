@@ -78,6 +78,33 @@ def test_large_maps_against_sorted_oracle(shape, k):
     assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize("shape,k,dist", [((2, 1, 48, 80), 1, "randn"), ((1, 2, 80, 48), 1, "randn"), ((1, 1, 96, 160), 2, "relu"),
+                                          ((1, 1, 100, 36), 1, "relu"), ((1, 1, 37, 300), 1, "relu")])
+def test_mid_size_maps_both_solvers(shape, k, dist):
+    """Short side 33..128: the squaring + power solver is tried first and the one-sided Jacobi takes over when the power steps
+    do not converge.  Signed Gaussian maps have a spectral gap of a few per cent (Jacobi fallback), post-ReLU maps a dominant
+    Perron vector (squarings converge); wide and tall maps.  Maps wider than 64 cells also take the row-chunked gradient kernel
+    (fa_ref_grad_rows; 37 x 300: ragged last row chunk, two column blocks).  Against the float64 oracle."""
+    x1, x2 = fa_inputs(shape, dist, 17)
+    loss, d1, d2 = run(x1, x2, k, "mean")
+    ol, o1, o2 = fa_oracle.fa_reference(x1, x2, k, "mean")
+    assert abs(float(loss) - ol) <= LOSS_RTOL * abs(ol), (float(loss), ol)
+    assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
+
+
+def test_wide_map_reduction_none():
+    """reduction='none' on a map wider than 64 cells: the upstream-weighted g values reach the row-chunked gradient kernel as
+    floats (not as integer counts)."""
+    shape, k = (1, 2, 10, 72), 1
+    x1, x2 = fa_inputs(shape, "relu", 23)
+    n = 72 * 72
+    go = np.random.default_rng(24).standard_normal((1, 2, n * n)).astype(np.float32)
+    loss, d1, d2 = run(x1, x2, k, "none", go)
+    ol, o1, o2 = fa_oracle.fa_reference(x1, x2, k, "none", grad_out=go)
+    np.testing.assert_allclose(loss, ol, rtol=LOSS_RTOL, atol=1e-6)
+    assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
+
+
 @pytest.mark.parametrize("shape", [(2, 1, 256, 512), (2, 1, 1024, 1024), (2, 1, 512, 1152)])
 def test_dead_channel_on_every_all_pairs_path(shape):
     """sigma = 0 (an all-zero pooled map) must give a NaN loss, NaN gradient for the dead (b, c) of the dead branch and an
