@@ -856,6 +856,47 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
                   "note": "the drop-in FALoss(affinity='position') itself: both feature maps copied from pinned host memory, forward (one fused "
                           "pass: loss + dX), backward(), loss read back with .item() -- copy, then compute, as the reference's loop does",
                   "h2d_floor_ms": h2d_ms, "h2d_gb_per_s": h2d_bytes / (h2d_ms * 1e-3) / 1e9}
+    # (a') the same drop-in module called by a loop that feeds it sample chunks: samples are independent units of the loss
+    #      ('mean' over the batch = mean of the chunk means, weighted), so the copy of chunk i+1 can run on a copy stream while
+    #      FALoss + backward() work on chunk i.  Same module, same bytes over PCIe, same loss and gradients.
+    if b_local >= 2:
+        from dualsuperreslearningforsemseg_b200.functional import chunk_bounds
+        bounds = chunk_bounds(b_local, 2 if b_local >= 4 else 1)
+        copy_stream = torch.cuda.Stream(device=dev)
+        events = [torch.cuda.Event() for _ in bounds]
+
+        def e2e_module_chunked():
+            cur = torch.cuda.current_stream(dev)
+            copy_stream.wait_stream(cur)
+            parts = []
+            with torch.cuda.stream(copy_stream):
+                for i, (lo, hi) in enumerate(bounds):
+                    parts.append((p1[lo:hi].to(dev, non_blocking=True), p2[lo:hi].to(dev, non_blocking=True)))
+                    events[i].record(copy_stream)
+            total, grads = None, []
+            for i, (lo, hi) in enumerate(bounds):
+                cur.wait_event(events[i])
+                u, v = parts[i]
+                u.record_stream(cur); v.record_stream(cur)
+                u.requires_grad_(True); v.requires_grad_(True)
+                loss = loss_fn(u, v) * ((hi - lo) / b_local)
+                loss.backward()
+                grads.append((u.grad, v.grad))
+                total = loss.detach() if total is None else total + loss.detach()
+            return total.item()
+
+        assert abs(e2e_module_chunked() - loss_local) <= 1e-5 * abs(loss_local), "chunked FALoss loop != device-resident plan"
+        chunked_ms = time_e2e(e2e_module_chunked)
+        res["e2e"]["single_call"] = {"value": res["e2e"]["value"], "ms_per_step": mod_ms, "note": res["e2e"]["note"]}
+        if chunked_ms < mod_ms:
+            res["e2e"].update({
+                "value": pairs_total / (chunked_ms * 1e-3) / 1e9, "ms_per_step": chunked_ms,
+                "note": "the drop-in FALoss(affinity='position') module called per chunk of samples (sizes "
+                        f"{[hi - lo for lo, hi in bounds]}) by a two-stream loop: chunk i+1 is copied from pinned host memory while FALoss "
+                        "forward (fused pass: loss + dX) and backward() run on chunk i; chunk losses weighted into the batch mean and read "
+                        "back with .item().  All H2D bytes and the D2H of the loss are inside the timed region; `single_call` is the same "
+                        "module on the whole batch, copy first, then compute"})
+        del copy_stream, events
     if not light:
         del loss_fn
         torch.cuda.empty_cache()
