@@ -918,6 +918,40 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
     return res
 
 
+def bench_fa_reference_large(args, rank, world, dev, peaks, steps=10, warmup=3):
+    """SURVEY 8d cfg 4's reference-mode counterpart: relu(randn(8, 1, 1024, 2048)), k = 8 -> pooled 128 x 256, S 256 x 256,
+    n = 65536 values per side, 4.29 G pairs per sample -- the reference cannot materialise it (17 GB per operand and sample).
+    General path of csrc/fa_reference.cu: prepare (pool, squaring + power solver, S), sorted all pairs, row-chunked gradient,
+    unpool.  Checked in-run against the float64 sorted oracle on sample 0."""
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    shape, k = (8, 1, 1024, 2048), 8
+    b_local = shape[0] // world if shape[0] % world == 0 and shape[0] >= world else shape[0]
+    shape = (b_local,) + shape[1:]
+    g = torch.Generator(device=dev); g.manual_seed(SEED + rank)
+    x1 = torch.relu(torch.randn(shape, device=dev, generator=g)); x2 = torch.relu(torch.randn(shape, device=dev, generator=g))
+    plan = FAPlan(shape, subsample_factor=k, device=dev)
+    go = torch.ones((), device=dev)
+
+    def step():
+        plan.forward_backward(x1, x2, go)
+
+    ms = max_over_ranks(timed_steps(step, steps, warmup, world), world, dev) / steps
+    w = shape[3] // k
+    pairs = shape[0] * world * shape[1] * w ** 4
+    res = {"metric": "fa_fwd_bwd_gpairs_per_s", "value": pairs / (ms * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": ms,
+           "config": {"workload": f"fa_reference_large: reference semantics on {shape} per GPU, k={k} (pooled 128x256, n=65536 per side)"}}
+    if rank == 0:
+        from oracle import fa_oracle
+        one = FAPlan((1,) + shape[1:], subsample_factor=k, device=dev)
+        l0, d1, d2 = one.forward_backward(x1[:1].contiguous(), x2[:1].contiguous(), go)
+        ol, o1, o2 = fa_oracle.fa_reference(x1[:1].cpu().numpy(), x2[:1].cpu().numpy(), k, "mean", materialise_limit=0)
+        rn = lambda a, b: float(np.linalg.norm(a.cpu().numpy().astype(np.float64) - b) / np.linalg.norm(b))
+        res["config"]["parity"] = {"loss_rel": abs(float(l0) - ol) / abs(ol), "grad_relnorm": max(rn(d1, o1), rn(d2, o2)),
+                                   "checker": "oracle/fa_oracle.py::fa_reference (float64, sorted all pairs) on sample 0 of the timed inputs",
+                                   "tolerance": {"loss_rel": 1e-4, "grad_relnorm": 1e-3}}
+    return res
+
+
 def cpu_fa_stress(budget_s=15.0, threads=None, C=None, rows=256):
     """Bounded sample of configs[3] on the host: PyTorch-CPU fp32 port, a block of `rows` affinity rows of one sample."""
     from oracle import fa_position_torch_port as tp
@@ -1185,6 +1219,8 @@ def summarise_secondary(extra):
         "train_step_ms_with_stage3_loss": get("train_step", "with_dsrl_b200_stage3_loss", "ms_per_step"),
         "train_step_ms_with_pytorch_eager_fa": get("train_step", "with_pytorch_eager_fa", "ms_per_step"),
         "ce_loss_ms": get("ce_loss", "ms_per_step"),
+        "fa_reference_large_ms": get("fa_reference_large", "ms_per_step"), "fa_reference_large_gpairs_per_s": get("fa_reference_large", "value"),
+        "fa_reference_large_parity": get("fa_reference_large", "config", "parity"),
     }
     for name, v in extra.items():
         if name.startswith("fa_stress") and isinstance(v, dict) and "error" not in v:
@@ -1276,6 +1312,7 @@ def main():
         attempt("seg_logits", lambda: bench_seg_logits(args, rank, world, dev, peaks))
         attempt("train_step", lambda: bench_train_step(args, rank, world, dev, peaks))
         attempt("ce_loss", lambda: bench_ce_loss(args, rank, world, dev, peaks))
+        attempt("fa_reference_large", lambda: bench_fa_reference_large(args, rank, world, dev, peaks))
         if args.workload != "fa_stress":
             attempt("fa_stress", lambda: bench_fa_stress(args, rank, world, dev, peaks, steps=3, warmup=3, light=True))
         else:

@@ -154,6 +154,23 @@ __device__ __forceinline__ float pool_cell(const float *__restrict__ x, int W, i
     return s / (float)(k * k);
 }
 
+__device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, int W, int k, bool vec4, bool act, float a, float b);
+// Large maps: the pooling of a (b, c, branch) read 8 MB through ONE SM when fa_ref_prepare did it (0.5 of its 0.76 ms at
+// 1024 x 2048, k = 8); this grid-wide pass writes the pooled maps into the saved blob first and fa_ref_prepare loads them.
+__global__ void __launch_bounds__(256) fa_ref_pool(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g, RefSaved so,
+                                                   unsigned char *__restrict__ saved) {
+    const long long hw = (long long)g.h * g.w, total = 2LL * g.BC * hw;
+    float *P = reinterpret_cast<float *>(saved + so.P);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long slot = idx / hw;
+        const int cell = (int)(idx - slot * hw), py = cell / g.w, px = cell - py * g.w;
+        const int br = slot >= g.BC;
+        const float *x = (br ? x2 : x1) + (size_t)(slot - (long long)br * g.BC) * g.H * g.W;
+        const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+        P[idx] = pool_cell_rolled(x + (size_t)py * g.k * g.W + (size_t)px * g.k, g.W, g.k, vec4, false, 1.f, 0.f);
+    }
+}
+
 // One-sided (Hestenes) Jacobi on the rows of Wm (m rows of length L, m_pad = even round-up; the extra row is a
 // dummy that never pairs).  Round-robin ordering: m_pad/2 disjoint pairs per round, one warp per pair.
 __device__ void jacobi_rows(float *Wm, int m, int m_pad, int L, int *flag) {
@@ -215,6 +232,38 @@ __device__ __forceinline__ T group_sum(T v, T *scratch /* >= 33 */, const Grp &g
     return scratch[32];
 }
 
+// C[i*m + j] = scale * sum_{k < K} X[i*xr + k*xc] * Y[k*yr + j*yc]  (i, j < m) by a whole group: a warp owns 4 rows x 128 columns,
+// lane l the columns j0 + l + 32 q (consecutive lanes read consecutive words of Y: no bank conflicts for row-major Y and none
+// for a transposed Y with an odd row stride; the four X values are broadcasts).  One fmaf chain over k per entry -- the same
+// rounding as the plain loop it replaces, 16 multiply-adds per 8 shared loads instead of 1 per 2.
+__device__ void group_mm_tiled(const float *X, int xr, int xc, const float *Y, int yr, int yc, int m, int K, float scale,
+                               float *C, const Grp &grp) {
+    const int lane = grp.tid & 31, wid = grp.tid >> 5, nw = grp.nt >> 5;
+    const int it = (m + 3) / 4, jb = (m + 127) / 128;
+    for (int task = wid; task < it * jb; task += nw) {
+        const int i0 = (task % it) * 4, j0 = (task / it) * 128 + lane;
+        int xo[4], yo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xo[q] = min(i0 + q, m - 1) * xr; yo[q] = min(j0 + 32 * q, m - 1) * yc; }
+        float acc[4][4] = {};
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = X[xo[q] + k * xc]; b[q] = Y[k * yr + yo[q]]; }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a[p], b[q], acc[p][q]);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i0 + p < m && j0 + 32 * q < m) C[(i0 + p) * m + j0 + 32 * q] = acc[p][q] * scale;
+    }
+}
+
 // Top singular triple of the m x L view V[i][c] = sA[i*rs + c*cs] (m <= kPowerMaxM is the short side).
 //  1) M = V V^T (fp32);  2) p squarings with trace normalisation -- M^(2^p) is numerically rank one unless the
 //  spectral gap is tiny;  3) fp64 power steps on V itself until sigma stalls (its error is second order in the
@@ -227,11 +276,16 @@ __device__ double top_singular_power(const float *sA, int rs, int cs, int m, int
                                      const float *reload = nullptr, float *sAw = nullptr, int h = 0, int w = 0, int lda = 0,
                                      int *stalled = nullptr) {
     const int tid = grp.tid, nt = grp.nt, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    for (int o = tid; o < m * m; o += nt) {
-        const int i = o / m, j = o - i * m;
-        float s = 0.f;
-        for (int c = 0; c < L; ++c) s = fmaf(sA[i * rs + c * cs], sA[j * rs + c * cs], s);
-        M0[o] = s;
+    const bool tiled = m > kPowerMaxM;                  // short sides 33..128: register tiles (the plain loops are bound by shared-memory loads)
+    if (tiled) {
+        group_mm_tiled(sA, rs, cs, sA, cs, rs, m, L, 1.f, M0, grp);
+    } else {
+        for (int o = tid; o < m * m; o += nt) {
+            const int i = o / m, j = o - i * m;
+            float s = 0.f;
+            for (int c = 0; c < L; ++c) s = fmaf(sA[i * rs + c * cs], sA[j * rs + c * cs], s);
+            M0[o] = s;
+        }
     }
     float *cur = M0, *nxt = M1;
     const int p = m <= 16 ? 8 : 6;
@@ -241,11 +295,15 @@ __device__ double top_singular_power(const float *sA, int rs, int cs, int m, int
         for (int i = 0; i < m; ++i) tr += cur[i * m + i];
         if (!(tr > 0.f)) break;                         // zero (or NaN) matrix: uniform exit
         const float inv = 1.f / tr;
-        for (int o = tid; o < m * m; o += nt) {
-            const int i = o / m, j = o - i * m;
-            float s = 0.f;
-            for (int k = 0; k < m; ++k) s = fmaf(cur[i * m + k], cur[k * m + j], s);
-            nxt[o] = s * inv * inv;
+        if (tiled) {
+            group_mm_tiled(cur, m, 1, cur, m, 1, m, m, inv * inv, nxt, grp);
+        } else {
+            for (int o = tid; o < m * m; o += nt) {
+                const int i = o / m, j = o - i * m;
+                float s = 0.f;
+                for (int k = 0; k < m; ++k) s = fmaf(cur[i * m + k], cur[k * m + j], s);
+                nxt[o] = s * inv * inv;
+            }
         }
         float *t = cur; cur = nxt; nxt = t;
     }
@@ -437,7 +495,7 @@ __device__ __noinline__ float top_singular_warp(const float *sA, int rs, int cs,
 }
 
 __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g, RefSaved so,
-                               unsigned char *__restrict__ saved, PrepSmem ps) {
+                               unsigned char *__restrict__ saved, PrepSmem ps, int pooled, int gram_later) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float *sA = reinterpret_cast<float *>(smraw + ps.A);
     float *sW = reinterpret_cast<float *>(smraw + ps.Wm);
@@ -460,8 +518,9 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
     const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     for (int cell = tid; cell < h * w; cell += nt) {
         const int py = cell / w, px = cell - py * w;
-        const float v = pool_cell(x, g.W, g.k, py, px, vec4);
-        gP[cell] = v;
+        float v;
+        if (pooled) v = gP[cell];                              // fa_ref_pool ran first
+        else { v = pool_cell(x, g.W, g.k, py, px, vec4); gP[cell] = v; }
         if (ps.sepW || mid) sA[py * lda + px] = v;
         if (!small && !mid) { if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v; }
     }
@@ -554,6 +613,7 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
     if (tid == 0) reinterpret_cast<float *>(saved + so.sigma)[slot] = sigf;
 
     // 3. S = A^^T A^ (FALoss.py:10-11); sigma == 0 gives 0/0 = NaN exactly like the reference
+    if (gram_later) return;                                    // wide maps: fa_ref_gram does it on the whole grid
     for (int cell = tid; cell < h * w; cell += nt) { const int py = cell / w; float *p = &sA[py * lda + (cell - py * w)]; *p = *p / sigf; }
     __syncthreads();
     if (w < 64) {
@@ -584,6 +644,48 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
                     if (ti + p < w && tj + q < w) gS[(size_t)(ti + p) * w + tj + q] = acc[p][q];
         }
     }
+}
+
+// S = A^^T A^ for wide maps as its own grid-wide pass (inside fa_ref_prepare one SM per (b, c, branch) spent 0.17 ms on it at
+// w = 256): a CTA owns a 64 x 64 tile of S, a thread 4 rows x 4 columns (columns tx + 16 q: conflict-free), the contraction
+// over the pooled rows runs in ascending order with one fmaf chain per entry like the in-kernel form.
+constexpr int kGramTile = 64, kGramRows = 32;
+__global__ void __launch_bounds__(256) fa_ref_gram(RefGeom g, RefSaved so, unsigned char *__restrict__ saved) {
+    __shared__ __align__(16) float sI[kGramRows][kGramTile], sJ[kGramRows][kGramTile];
+    const int slot = blockIdx.z, i0 = blockIdx.y * kGramTile, j0 = blockIdx.x * kGramTile, tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4, h = g.h, w = g.w;
+    const float *gP = reinterpret_cast<const float *>(saved + so.P) + (size_t)slot * h * w;
+    float *gS = reinterpret_cast<float *>(saved + so.S) + (size_t)slot * g.n;
+    const float sigf = reinterpret_cast<const float *>(saved + so.sigma)[slot];
+    float acc[4][4] = {};
+    for (int y0 = 0; y0 < h; y0 += kGramRows) {
+        __syncthreads();
+        for (int o = tid; o < kGramRows * kGramTile; o += 256) {
+            const int r = o >> 6, c = o & 63, y = y0 + r;
+            sI[r][c] = (y < h && i0 + c < w) ? gP[(size_t)y * w + i0 + c] / sigf : 0.f;
+            sJ[r][c] = (y < h && j0 + c < w) ? gP[(size_t)y * w + j0 + c] / sigf : 0.f;
+        }
+        __syncthreads();
+        const int lim = min(kGramRows, h - y0);
+        for (int r = 0; r < lim; ++r) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&sI[r][ty * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b[q] = sJ[r][tx + 16 * q];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a[p], b[q], acc[p][q]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + ty * 4 + p, j = j0 + tx + 16 * q;
+            if (i < w && j < w) gS[(size_t)i * w + j] = acc[p][q];
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1390,8 +1492,20 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
     int rc = opt_in_smem(fa_ref_prepare, ps.total);
     if (rc) return rc;
     const int pthreads = g.h * g.w >= 8192 ? 512 : 256;
-    fa_ref_prepare<<<dim3(g.BC, 2), pthreads, ps.total, st>>>(x1, x2, g, so, saved, ps);
+    const int pooled = (long long)g.h * g.w * g.k * g.k >= (1LL << 18);    // >= 1 MB of input per (b, c, branch): pool grid-wide
+    if (pooled) {
+        const long long cells = 2LL * g.BC * g.h * g.w;
+        fa_ref_pool<<<(int)std::min<long long>((cells + 255) / 256, 148LL * 8), 256, 0, st>>>(x1, x2, g, so, saved);
+        DSRL_LAUNCH_CHECK();
+    }
+    const int gram_later = g.w >= 128 && 2 * g.BC <= 65535;
+    fa_ref_prepare<<<dim3(g.BC, 2), pthreads, ps.total, st>>>(x1, x2, g, so, saved, ps, pooled, gram_later);
     DSRL_LAUNCH_CHECK();
+    if (gram_later) {
+        const int t = (g.w + kGramTile - 1) / kGramTile;
+        fa_ref_gram<<<dim3(t, t, 2 * g.BC), 256, 0, st>>>(g, so, saved);
+        DSRL_LAUNCH_CHECK();
+    }
 
     if (reduction == DSRL_REDUCE_NONE) {
         const long long nn = (long long)g.n * g.n;

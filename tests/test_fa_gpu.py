@@ -66,11 +66,12 @@ def test_matches_reference_golden(name):
     assert relnorm(d2, g2) <= GRAD_RTOL, relnorm(d2, g2)
 
 
-@pytest.mark.parametrize("shape,k", [((1, 1, 512, 1024), 8), ((2, 1, 256, 1024), 8), ((1, 1, 1024, 2048), 8)])
+@pytest.mark.parametrize("shape,k", [((1, 1, 512, 1024), 8), ((2, 1, 256, 1024), 8), ((1, 1, 1024, 2048), 8), ((1, 2, 515, 1030), 8)])
 def test_large_maps_against_sorted_oracle(shape, k):
     """Beyond what the reference can materialise (w^4 floats): the O(n log n) oracle, validated against the
     reference at small n in tests/test_oracle_fa.py.  The last shape is the reference-mode counterpart of
-    BASELINE config 4 (pooled 128 x 256, n = 65536, 4.3 G pairs per sample)."""
+    BASELINE config 4 (pooled 128 x 256, n = 65536, 4.3 G pairs per sample).  Maps of a megabyte and more are pooled by the
+    grid-wide fa_ref_pool pass (515 x 1030: floor pooling with dropped rows / columns, unaligned scalar loads)."""
     x1, x2 = fa_inputs(shape, "relu", 99)
     loss, d1, d2 = run(x1, x2, k, "mean")
     ol, o1, o2 = fa_oracle.fa_reference(x1, x2, k, "mean", materialise_limit=0)
