@@ -320,10 +320,14 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
     __syncthreads();
     if (kExact) {
         // FP64 sums of squares, the channels spread over the eight warps (fixed order: deterministic)
-        double s1 = 0.0, s2 = 0.0;
-        for (int c = warp; c < g.Kc; c += 8) {
-            const double t = (double)T[c * 33 + lane];
-            if (c < g.C1p) s1 = fma(t, t, s1); else s2 = fma(t, t, s2);
+        double s1 = 0.0, s2 = 0.0;                  // C1p is a multiple of 32: branch 2 starts at a channel = warp (mod 8) too
+        {
+            const float *tr = T + warp * 33 + lane;
+            int c = warp;
+#pragma unroll 4
+            for (; c < g.C1p; c += 8, tr += 8 * 33) { const double t = (double)*tr; s1 = fma(t, t, s1); }
+#pragma unroll 4
+            for (; c < g.Kc; c += 8, tr += 8 * 33) { const double t = (double)*tr; s2 = fma(t, t, s2); }
         }
         s_part[0][warp][lane] = s1;
         s_part[1][warp][lane] = s2;
@@ -346,35 +350,52 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
         nrm[((size_t)b * 2 + warp) * g.Npad + p] = n;
     }
     __syncthreads();
-    {                                                 // channel-major rows: 128 (fp32) / 64 (FP16) contiguous bytes per warp store
-        const size_t o0 = ((size_t)b * g.Kc + warp) * g.Npad + p, ostep = (size_t)8 * g.Npad;
-        float *pc = Fcm ? Fcm + o0 : nullptr;
-        __half *ph = FcmH ? FcmH + o0 : nullptr;
-        const float *tr = T + warp * 33 + lane;
-        const float i1 = s_inv[0][lane], i2 = s_inv[1][lane];
+    // Stores, one branch at a time with running pointers (ncu r02g: two thirds of this kernel's instructions were index
+    // arithmetic and branch selects around the loads / stores of these loops).
+    const size_t prow = (size_t)b * g.Npad + p0;      // first position-major row of the strip
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+        const int c0 = br ? g.C1p : 0, Cp = br ? g.C2p : g.C1p;
+        {                                             // channel-major rows: 128 (fp32) / 64 (FP16) contiguous bytes per warp store
+            const size_t o0 = ((size_t)b * g.Kc + c0 + warp) * g.Npad + p, ostep = (size_t)8 * g.Npad;
+            const float *tr = T + (c0 + warp) * 33 + lane;
+            const float il = s_inv[br][lane];
+            if (Fcm) {
+                float *pc = Fcm + o0;
+                for (int c = warp; c < Cp; c += 8, tr += 8 * 33, pc += ostep) *pc = round_tf32(*tr * il);
+                tr = T + (c0 + warp) * 33 + lane;
+            }
+            if (FcmH) {
+                __half *ph = FcmH + o0;
 #pragma unroll 4
-        for (int c = warp; c < g.Kc; c += 8, tr += 8 * 33) {
-            const float f = *tr * (c >= g.C1p ? i2 : i1);
-            if (pc) { *pc = round_tf32(f); pc += ostep; }
-            if (ph) { *ph = __float2half_rn(f); ph += ostep; }
+                for (int c = warp; c < Cp; c += 8, tr += 8 * 33, ph += ostep) *ph = __float2half_rn(*tr * il);
+            }
         }
-    }
-    for (int q = warp; q < 32; q += 8) {              // position-major rows: Kc contiguous floats per position
-        float *dst = Fpm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
-        float *dst_lo = dst + (size_t)g.B * g.Npad * g.Kc;
-        for (int c = lane; Fpm && c < g.Kc; c += 32) {
-            const float f = T[c * 33 + q] * s_inv[c >= g.C1p][q], hi = round_tf32(f);
-            dst[c] = hi;
-            if (g.split) dst_lo[c] = round_tf32(f - hi);
-        }
-        if (FpmH) {                                   // FP16 copy: two channels per lane, 128 bytes per warp store
-            __half2 *dh = reinterpret_cast<__half2 *>(FpmH + ((size_t)b * g.Npad + p0 + q) * g.Kc);
-            for (int c = 2 * lane; c < g.Kc; c += 64)
-                dh[c >> 1] = __floats2half2_rn(T[c * 33 + q] * s_inv[c >= g.C1p][q], T[(c + 1) * 33 + q] * s_inv[c + 1 >= g.C1p][q]);
-        }
-        if (kExact) {                                 // raw pooled features, position-major: what the FP64 re-decision reads
-            float *dp = ex.Ppm + ((size_t)b * g.Npad + p0 + q) * g.Kc;
-            for (int c = lane; c < g.Kc; c += 32) dp[c] = T[c * 33 + q];
+#pragma unroll 1
+        for (int q = warp; q < 32; q += 8) {          // position-major rows: the branch's Cp contiguous channels per position
+            const float iq = s_inv[br][q];
+            const float *tq = T + c0 * 33 + q;
+            const size_t ro = (prow + q) * g.Kc + c0;
+            if (Fpm) {
+                float *dst = Fpm + ro, *dst_lo = dst + (size_t)g.B * g.Npad * g.Kc;
+                for (int c = lane; c < Cp; c += 32) {
+                    const float f = tq[c * 33] * iq, hi = round_tf32(f);
+                    dst[c] = hi;
+                    if (g.split) dst_lo[c] = round_tf32(f - hi);
+                }
+            }
+            if (FpmH) {                               // FP16 copy: two channels per lane, 128 bytes per warp store
+                __half2 *dh = reinterpret_cast<__half2 *>(FpmH + ro) + lane;
+                const float *t2 = tq + 2 * lane * 33;
+#pragma unroll 4
+                for (int c = 2 * lane; c < Cp; c += 64, dh += 32, t2 += 64 * 33) *dh = __floats2half2_rn(t2[0] * iq, t2[33] * iq);
+            }
+            if (kExact) {                             // raw pooled features, position-major: what the FP64 re-decision reads
+                float *dp = ex.Ppm + ro + lane;
+                const float *t1 = tq + lane * 33;
+#pragma unroll 4
+                for (int c = lane; c < Cp; c += 32, dp += 32, t1 += 32 * 33) *dp = *t1;
+            }
         }
     }
 }
@@ -1309,9 +1330,15 @@ constexpr float kSafe32 = 3.0e-6f;
 // kBits (two-pass form): nothing is accumulated -- the exact sign of a listed entry (i, j), j > i, is written into the sign
 // planes at (i, j) wherever it differs from the tensor-core sign, and inside a diagonal tile at (j, i) always (its lower half
 // was converted from its own tensor-core values); off-diagonal blocks below the diagonal do not exist.
+#ifndef DSRL_RESOLVE_MINB
+#define DSRL_RESOLVE_MINB 2
+#endif
+#ifndef DSRL_RESOLVE_R
+#define DSRL_RESOLVE_R 4
+#endif
 template <int kNU, bool kBits = false>
-__global__ void __launch_bounds__(256, 2) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
-    constexpr int kR = 4;                         // entries per round: up to 16 independent 16-byte loads in flight per lane
+__global__ void __launch_bounds__(256, DSRL_RESOLVE_MINB) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
+    constexpr int kR = DSRL_RESOLVE_R;            // entries per round: up to 16 independent 16-byte loads in flight per lane
     constexpr float kFix = 1073741824.f;          // 2^30
     __shared__ long long s_corr[kBits ? 1 : 8][kBits ? 1 : 4 * kNU][32];  // per warp: fixed-point correction of the lane's channels (few entries flip)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
