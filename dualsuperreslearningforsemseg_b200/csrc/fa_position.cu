@@ -1330,15 +1330,18 @@ constexpr float kSafe32 = 3.0e-6f;
 // kBits (two-pass form): nothing is accumulated -- the exact sign of a listed entry (i, j), j > i, is written into the sign
 // planes at (i, j) wherever it differs from the tensor-core sign, and inside a diagonal tile at (j, i) always (its lower half
 // was converted from its own tensor-core values); off-diagonal blocks below the diagonal do not exist.
+// Entries per round (independent row gathers in flight per warp) and CTAs per SM.  The pass is bound by the latency of its L2
+// gathers, and warps hide it better than loads per warp do: measured at cfg[3] (batch 8, 5.0 M entries) R/CTAs = 8/1: 2.73 ms,
+// 4/2: 1.56, 4/3 (spills): 1.79, 2/4: 1.32, 1/4: 1.24, 1/6 (spills): 1.41, 2/6: 1.87.
 #ifndef DSRL_RESOLVE_MINB
-#define DSRL_RESOLVE_MINB 2
+#define DSRL_RESOLVE_MINB 4
 #endif
 #ifndef DSRL_RESOLVE_R
-#define DSRL_RESOLVE_R 4
+#define DSRL_RESOLVE_R 1
 #endif
 template <int kNU, bool kBits = false>
 __global__ void __launch_bounds__(256, DSRL_RESOLVE_MINB) fa_pos_resolve(PosGeom g, ResolveArgs ex) {
-    constexpr int kR = DSRL_RESOLVE_R;            // entries per round: up to 16 independent 16-byte loads in flight per lane
+    constexpr int kR = DSRL_RESOLVE_R;            // entries per round: kR * kNU independent 16-byte loads in flight per lane
     constexpr float kFix = 1073741824.f;          // 2^30
     __shared__ long long s_corr[kBits ? 1 : 8][kBits ? 1 : 4 * kNU][32];  // per warp: fixed-point correction of the lane's channels (few entries flip)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1365,16 +1368,17 @@ __global__ void __launch_bounds__(256, DSRL_RESOLVE_MINB) fa_pos_resolve(PosGeom
     const float *lane_base = ex.Ppm + (size_t)b * g.Npad * g.Kc + 4 * lane;
     const bool last_ok = 4 * lane + 128 * (kNU - 1) < g.Kc;
     const int last_off = last_ok ? 128 * (kNU - 1) : 0;
-    float4 pi[kNU];
+    float4 pi[kNU];                               // (kept in registers: a shared-memory copy was slower at every occupancy tried)
     float bsel[kNU];                              // +1: the chunk belongs to branch 1, -1: branch 2, 0: absent
     {
         const float *ri = lane_base + (size_t)irow * g.Kc;
 #pragma unroll
         for (int u = 0; u < kNU; ++u) {
             const int off = u == kNU - 1 ? last_off : 128 * u;
-            pi[u] = __ldg(reinterpret_cast<const float4 *>(ri + off));
+            float4 t = __ldg(reinterpret_cast<const float4 *>(ri + off));
             bsel[u] = (u == kNU - 1 && !last_ok) ? 0.f : (4 * lane + 128 * u < g.C1p ? 1.f : -1.f);
-            if (bsel[u] == 0.f) pi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bsel[u] == 0.f) t = make_float4(0.f, 0.f, 0.f, 0.f);
+            pi[u] = t;
         }
     }
     const double i1 = inv1[irow], i2 = inv2[irow];
@@ -1417,8 +1421,9 @@ __global__ void __launch_bounds__(256, DSRL_RESOLVE_MINB) fa_pos_resolve(PosGeom
                 float d = 0.f;
 #pragma unroll
                 for (int u = 0; u < kNU; ++u) {
-                    float t = pi[u].x * pj[h][u].x;
-                    t = fmaf(pi[u].y, pj[h][u].y, t); t = fmaf(pi[u].z, pj[h][u].z, t); t = fmaf(pi[u].w, pj[h][u].w, t);
+                    const float4 a = pi[u];
+                    float t = a.x * pj[h][u].x;
+                    t = fmaf(a.y, pj[h][u].y, t); t = fmaf(a.z, pj[h][u].z, t); t = fmaf(a.w, pj[h][u].w, t);
                     d = fmaf(t, bsel[u] > 0.f ? w1 : w2, d);              // pi is zero where the chunk is absent
                 }
                 d = warp_sum(d);
@@ -1430,8 +1435,9 @@ __global__ void __launch_bounds__(256, DSRL_RESOLVE_MINB) fa_pos_resolve(PosGeom
                     double d1 = 0.0, d2 = 0.0;
 #pragma unroll
                     for (int u = 0; u < kNU; ++u) {
-                        const double t = (double)pi[u].x * (double)pj[h][u].x + (double)pi[u].y * (double)pj[h][u].y +
-                                         (double)pi[u].z * (double)pj[h][u].z + (double)pi[u].w * (double)pj[h][u].w;
+                        const float4 a = pi[u];
+                        const double t = (double)a.x * (double)pj[h][u].x + (double)a.y * (double)pj[h][u].y +
+                                         (double)a.z * (double)pj[h][u].z + (double)a.w * (double)pj[h][u].w;
                         if (bsel[u] > 0.f) d1 += t; else d2 += t;
                     }
                     d1 = warp_sum(d1);
