@@ -863,7 +863,7 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
         from dualsuperreslearningforsemseg_b200.functional import chunk_bounds
         bounds = chunk_bounds(b_local, 2 if b_local >= 4 else 1)
         copy_stream = torch.cuda.Stream(device=dev)
-        events = [torch.cuda.Event() for _ in bounds]
+        events = [torch.cuda.Event() for _ in range(b_local)]
 
         def e2e_module_chunked():
             cur = torch.cuda.current_stream(dev)
@@ -887,6 +887,15 @@ def bench_fa_stress(args, rank, world, dev, peaks, steps=None, warmup=None, C=No
 
         assert abs(e2e_module_chunked() - loss_local) <= 1e-5 * abs(loss_local), "chunked FALoss loop != device-resident plan"
         chunked_ms = time_e2e(e2e_module_chunked)
+        if b_local >= 4:                                  # single-sample chunks: shorter ramp, smaller launches
+            kept = bounds
+            bounds = chunk_bounds(b_local, 1)
+            assert abs(e2e_module_chunked() - loss_local) <= 1e-5 * abs(loss_local), "chunked FALoss loop != device-resident plan"
+            ones_ms = time_e2e(e2e_module_chunked)
+            if ones_ms < chunked_ms:
+                chunked_ms = ones_ms
+            else:
+                bounds = kept
         res["e2e"]["single_call"] = {"value": res["e2e"]["value"], "ms_per_step": mod_ms, "note": res["e2e"]["note"]}
         if chunked_ms < mod_ms:
             res["e2e"].update({
