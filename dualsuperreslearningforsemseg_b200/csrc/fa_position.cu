@@ -1832,7 +1832,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
         DSRL_LAUNCH_CHECK();
         if (g.exact && (rc = resolve())) return rc;
         if ((rc = opt_in_smem(fa_pos_grad, g.b_smem_bytes))) return rc;
-        fa_pos_grad<<<grid, kGradThreads, g.b_smem_bytes, st>>>(tm_v, tm_pm, g, a);
+        fa_pos_grad<<<dim3(g.tiles * g.jsplit * g.G, 1, B), kGradThreads, g.b_smem_bytes, st>>>(tm_v, tm_pm, g, a);
         DSRL_LAUNCH_CHECK();
         if (g.raw_o && (rc = finish(a))) return rc;
         return DSRL_OK;

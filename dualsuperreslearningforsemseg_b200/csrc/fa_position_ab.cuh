@@ -460,8 +460,10 @@ fa_pos_grad(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CU
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int T = g.tiles, js = blockIdx.x / T;
-    const int itile = blockIdx.x - js * T, grp = blockIdx.y, b = blockIdx.z;          // T is even: the pair shares js
+    // grid.x = clusters in the order (pair of row tiles, channel group): the channel groups of a pair run on neighbouring SM pairs
+    // at the same time and read the same sign blocks, which then come from DRAM once per pair instead of once per group
+    const int T = g.tiles, cl = (int)(blockIdx.x >> 1), grp = cl % g.G, xlin = 2 * (cl / g.G) + (int)(blockIdx.x & 1);
+    const int js = xlin / T, itile = xlin - js * T, b = blockIdx.z;                    // T is even: the pair shares js
     const int nt = T / g.jsplit, j0 = js * nt;
     const int gN = g.gcnt[grp], gbeg = g.gbeg[grp], vrows = gN / 2;
     const uint32_t vbytes = (uint32_t)vrows * 128u;
