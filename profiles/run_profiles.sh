@@ -20,6 +20,7 @@ $NCU --set full --import-source on -k regex:"fa_pos_grad|fa_pos_tiles" -s 3 -c 1
 # the other kernels of the step: pass A (upper-triangle D tiles -> sign planes) and the near-tie resolve (L2 gather bound)
 $NCU --set full --import-source on -k regex:fa_pos_dsign -s 3 -c 1 -f -o $OUT/${TAG}_fa_dsign_full $CMD > $OUT/${TAG}_fa_dsign_full.log 2>&1
 $NCU --set full --import-source on -k regex:fa_pos_resolve -s 3 -c 1 -f -o $OUT/${TAG}_fa_resolve_full $CMD > $OUT/${TAG}_fa_resolve_full.log 2>&1
+$NCU --set full --import-source on -k regex:fa_pos_pack -s 3 -c 1 -f -o $OUT/${TAG}_fa_pack_full $CMD > $OUT/${TAG}_fa_pack_full.log 2>&1
 fi
 
 # ---- seg_counts (BASELINE configs[2])

@@ -93,7 +93,7 @@ def main():
     suffix = sys.argv[2] if len(sys.argv) > 2 else ""
     traffic_path = os.path.join(PROF, "roofline_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    for wl in ("fa_stress", "seg_counts", "fa_train", "fa_dsign", "fa_resolve", "fa_finish"):
+    for wl in ("fa_stress", "seg_counts", "fa_train", "fa_dsign", "fa_resolve", "fa_pack", "fa_finish"):
         launches(tag, wl)
         v = full(tag, wl)
         if v and 'dram__bytes_read.sum' in v:
