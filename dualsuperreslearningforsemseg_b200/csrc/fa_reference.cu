@@ -1283,16 +1283,18 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
         const int lane = ht & 31;
         float v = ht < n ? fb.S[ht] : INFINITY;
         const bool has_nan = __syncthreads_or(ht < n && v != v) != 0;
+        int xbuf = 0;
 #pragma unroll 1
         for (int k = 2; k <= 256; k <<= 1) {
 #pragma unroll 1
             for (int j = k >> 1; j > 0; j >>= 1) {
                 float o;
-                if (j >= 32) {                                   // partner in another warp: through shared memory
-                    fb.sorted[ht] = v;
+                if (j >= 32) {                                   // partner in another warp: through shared memory, two buffers
+                    float *xb = xbuf ? fb.M : fb.sorted;         // in turn (M is free after the sigma solve): the barrier of the
+                    xbuf ^= 1;                                   // next exchange orders this one's reads before the buffer's reuse
+                    xb[ht] = v;
                     grp.sync();
-                    o = fb.sorted[ht ^ j];
-                    grp.sync();
+                    o = xb[ht ^ j];
                 } else {
                     o = __shfl_xor_sync(0xffffffffu, v, j);
                 }
@@ -1386,17 +1388,36 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
     }
 
     TSTAMP(7);
-    // 6. loss finish by the last CTA (fixed summation order -> deterministic)
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double s = 0.0;
+    // 6. loss finish by the last CTA (fixed summation order -> deterministic).  Up to 1024 partials (every shape the model
+    //    produces: one per (b, c)) are summed by the ticket holder's own warp alone -- it wrote `is_last` itself, so the last CTA,
+    //    which is the critical path of the launch, skips a block-wide barrier and a 512-thread reduction (3.4 k -> 0.9 k cycles).
+    if (gridDim.x <= 1024) {
+        if (tid < 32) {
+            __syncwarp();
+            if (is_last) {
+                __threadfence();
+                double s = 0.0;
 #pragma unroll 1
-        for (int i = tid; i < (int)gridDim.x; i += 512) s += __ldcg(partials + i);
-        s = group_sum_d(s, red, tid, 512, 0);
-        if (tid == 0) {
-            *reinterpret_cast<double *>(saved) = s;
-            *loss_out = (float)(s / loss_div);
+                for (int i = tid; i < (int)gridDim.x; i += 32) s += __ldcg(partials + i);
+                s = wsum_d(s);
+                if (tid == 0) {
+                    *reinterpret_cast<double *>(saved) = s;
+                    *loss_out = (float)(s / loss_div);
+                }
+            }
+        }
+    } else {
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            double s = 0.0;
+#pragma unroll 1
+            for (int i = tid; i < (int)gridDim.x; i += 512) s += __ldcg(partials + i);
+            s = group_sum_d(s, red, tid, 512, 0);
+            if (tid == 0) {
+                *reinterpret_cast<double *>(saved) = s;
+                *loss_out = (float)(s / loss_div);
+            }
         }
     }
     TSTAMP(8);
