@@ -255,42 +255,40 @@ template <bool kExact>
 __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1, const float *__restrict__ x2, PosGeom g,
                                                   float *__restrict__ Fpm, float *__restrict__ Fcm, float *__restrict__ nrm,
                                                   __half *__restrict__ FpmH, __half *__restrict__ FcmH, PackExact ex) {
-    extern __shared__ float T[];                     // [Kc][33] pooled values of a 32-position strip
-    __shared__ float s_inv[2][32];
-    __shared__ double s_part[kExact ? 2 : 1][kExact ? 8 : 1][kExact ? 32 : 1];
+    // One CTA = one 32-position strip of ONE branch (blockIdx.z): the norm is per branch, so nothing couples the two, and half
+    // the shared memory doubles the resident CTAs (ncu r02j: 23 warps per SM and 45 % issue activity at 4.5 TB/s -- the kernel
+    // wanted more loads in flight, not fewer instructions).
+    extern __shared__ float T[];                     // [Cp][33] pooled values of the strip, channels of this branch
+    __shared__ float s_inv[32];
+    __shared__ double s_part[kExact ? 8 : 1][kExact ? 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y, p0 = blockIdx.x * 32, p = p0 + lane;
+    const int b = blockIdx.y, br = blockIdx.z, p0 = blockIdx.x * 32, p = p0 + lane;
     const bool valid = p < g.N;
-    const int py = valid ? p / g.w : 0, px = valid ? p - py * g.w : 0;
-    const float inv_kk = 1.f / (float)(g.k * g.k);
+    const int Cr = br ? g.C2 : g.C1, Cp = br ? g.C2p : g.C1p, c0 = br ? g.C1p : 0;      // real / padded channels, first channel in Kc
+    const float *xb = (br ? x2 : x1) + (size_t)b * Cr * g.H * g.W;
 
     if (g.k == 1) {
-        // no pooling: one coalesced 128-byte row per (channel, strip); eight independent loads in flight per warp.  One loop per
-        // branch with a running row pointer: the kernel was bound by its instruction count (ncu r02g: issue slots 70 % busy at
-        // 3.5 TB/s), most of it index arithmetic around these loads and the stores below
+        // no pooling: one coalesced 128-byte row per (channel, strip); eight independent loads in flight per warp, running pointers
         const size_t hw = (size_t)g.H * g.W;
-#pragma unroll 1
-        for (int br = 0; br < 2; ++br) {
-            const int Cr = br ? g.C2 : g.C1, Cp = br ? g.C2p : g.C1p;      // real / padded channels of the branch (Cp a multiple of 32)
-            const float *xr = (br ? x2 : x1) + ((size_t)b * Cr + warp * 8) * hw + (valid ? p : 0);
-            float *tr = T + ((br ? g.C1p : 0) + warp * 8) * 33 + lane;
-            for (int c8 = warp * 8; c8 < Cp; c8 += 64, xr += 64 * hw, tr += 64 * 33) {
-                float v[8];
+        const float *xr = xb + (size_t)warp * 8 * hw + (valid ? p : 0);
+        float *tr = T + warp * 8 * 33 + lane;
+        for (int c8 = warp * 8; c8 < Cp; c8 += 64, xr += 64 * hw, tr += 64 * 33) {
+            float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (valid && c8 + u < Cr) ? ldg_stream_f32(xr + u * hw) : 0.f;
+            for (int u = 0; u < 8; ++u) v[u] = (valid && c8 + u < Cr) ? ldg_stream_f32(xr + u * hw) : 0.f;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) tr[u * 33] = v[u];
-            }
+            for (int u = 0; u < 8; ++u) tr[u * 33] = v[u];
         }
     } else {
         // k x k mean (FALoss.py:23-24).  With k % 4 == 0 every window row is k/4 aligned 16-byte vectors and a warp's 32
         // neighbouring windows form one contiguous run per input row; all vectors of up to 8 rows are issued before summing.
+        const int py = valid ? p / g.w : 0, px = valid ? p - py * g.w : 0;
+        const float inv_kk = 1.f / (float)(g.k * g.k);
         const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0;
-        for (int c = warp; c < g.Kc; c += 8) {
-            const int br = c >= g.C1p, cc = br ? c - g.C1p : c, Cr = br ? g.C2 : g.C1;
+        for (int c = warp; c < Cp; c += 8) {
             float v = 0.f;
-            if (valid && cc < Cr) {
-                const float *x = (br ? x2 : x1) + (((size_t)b * Cr + cc) * g.H + (size_t)py * g.k) * g.W + (size_t)px * g.k;
+            if (valid && c < Cr) {
+                const float *x = xb + ((size_t)c * g.H + (size_t)py * g.k) * g.W + (size_t)px * g.k;
                 float s = 0.f;
                 if (vec4 && g.k == 8) {
                     float4 r[16];
@@ -319,83 +317,73 @@ __global__ void __launch_bounds__(256) fa_pos_pack(const float *__restrict__ x1,
     }
     __syncthreads();
     if (kExact) {
-        // FP64 sums of squares, the channels spread over the eight warps (fixed order: deterministic)
-        double s1 = 0.0, s2 = 0.0;                  // C1p is a multiple of 32: branch 2 starts at a channel = warp (mod 8) too
+        // FP64 sum of squares, the channels spread over the eight warps (fixed order: deterministic)
+        double s1 = 0.0;
         {
             const float *tr = T + warp * 33 + lane;
-            int c = warp;
 #pragma unroll 4
-            for (; c < g.C1p; c += 8, tr += 8 * 33) { const double t = (double)*tr; s1 = fma(t, t, s1); }
-#pragma unroll 4
-            for (; c < g.Kc; c += 8, tr += 8 * 33) { const double t = (double)*tr; s2 = fma(t, t, s2); }
+            for (int c = warp; c < Cp; c += 8, tr += 8 * 33) { const double t = (double)*tr; s1 = fma(t, t, s1); }
         }
-        s_part[0][warp][lane] = s1;
-        s_part[1][warp][lane] = s2;
+        s_part[warp][lane] = s1;
         __syncthreads();
-        if (warp < 2) {
+        if (warp == 0) {
             double sq = 0.0;
-            for (int i = 0; i < 8; ++i) sq += s_part[warp][i][lane];
+            for (int i = 0; i < 8; ++i) sq += s_part[i][lane];
             const double n = sqrt(sq), inv = 1.0 / fmax(n, 1e-12);
-            s_inv[warp][lane] = (float)inv;
-            nrm[((size_t)b * 2 + warp) * g.Npad + p] = (float)n;
-            ex.inv64[((size_t)b * 2 + warp) * g.Npad + p] = inv;
+            s_inv[lane] = (float)inv;
+            nrm[((size_t)b * 2 + br) * g.Npad + p] = (float)n;
+            ex.inv64[((size_t)b * 2 + br) * g.Npad + p] = inv;
         }
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) ex.stats[threadIdx.x] = 0ull;
-    } else if (warp < 2) {                            // per-position L2 norm over the channels of branch `warp`
-        const int c0 = warp ? g.C1p : 0, c1 = warp ? g.Kc : g.C1p;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && br == 0 && threadIdx.x < 4) ex.stats[threadIdx.x] = 0ull;
+    } else if (warp == 0) {                           // per-position L2 norm over the channels of the branch
         float s = 0.f;
-        for (int c = c0; c < c1; ++c) { const float t = T[c * 33 + lane]; s = fmaf(t, t, s); }
+        for (int c = 0; c < Cp; ++c) { const float t = T[c * 33 + lane]; s = fmaf(t, t, s); }
         const float n = sqrtf(s);
-        s_inv[warp][lane] = 1.f / fmaxf(n, 1e-12f);
-        nrm[((size_t)b * 2 + warp) * g.Npad + p] = n;
+        s_inv[lane] = 1.f / fmaxf(n, 1e-12f);
+        nrm[((size_t)b * 2 + br) * g.Npad + p] = n;
     }
     __syncthreads();
-    // Stores, one branch at a time with running pointers (ncu r02g: two thirds of this kernel's instructions were index
-    // arithmetic and branch selects around the loads / stores of these loops).
-    const size_t prow = (size_t)b * g.Npad + p0;      // first position-major row of the strip
-#pragma unroll 1
-    for (int br = 0; br < 2; ++br) {
-        const int c0 = br ? g.C1p : 0, Cp = br ? g.C2p : g.C1p;
-        {                                             // channel-major rows: 128 (fp32) / 64 (FP16) contiguous bytes per warp store
-            const size_t o0 = ((size_t)b * g.Kc + c0 + warp) * g.Npad + p, ostep = (size_t)8 * g.Npad;
-            const float *tr = T + (c0 + warp) * 33 + lane;
-            const float il = s_inv[br][lane];
-            if (Fcm) {
-                float *pc = Fcm + o0;
-                for (int c = warp; c < Cp; c += 8, tr += 8 * 33, pc += ostep) *pc = round_tf32(*tr * il);
-                tr = T + (c0 + warp) * 33 + lane;
-            }
-            if (FcmH) {
-                __half *ph = FcmH + o0;
+    // Stores with running pointers (ncu r02g: two thirds of this kernel's instructions were index arithmetic and branch selects
+    // around the loads / stores of these loops).
+    {                                                 // channel-major rows: 128 (fp32) / 64 (FP16) contiguous bytes per warp store
+        const size_t o0 = ((size_t)b * g.Kc + c0 + warp) * g.Npad + p, ostep = (size_t)8 * g.Npad;
+        const float *tr = T + warp * 33 + lane;
+        const float il = s_inv[lane];
+        if (Fcm) {
+            float *pc = Fcm + o0;
+            for (int c = warp; c < Cp; c += 8, tr += 8 * 33, pc += ostep) *pc = round_tf32(*tr * il);
+            tr = T + warp * 33 + lane;
+        }
+        if (FcmH) {
+            __half *ph = FcmH + o0;
 #pragma unroll 4
-                for (int c = warp; c < Cp; c += 8, tr += 8 * 33, ph += ostep) *ph = __float2half_rn(*tr * il);
+            for (int c = warp; c < Cp; c += 8, tr += 8 * 33, ph += ostep) *ph = __float2half_rn(*tr * il);
+        }
+    }
+#pragma unroll 1
+    for (int q = warp; q < 32; q += 8) {              // position-major rows: the branch's Cp contiguous channels per position
+        const float iq = s_inv[q];
+        const float *tq = T + q;
+        const size_t ro = ((size_t)b * g.Npad + p0 + q) * g.Kc + c0;
+        if (Fpm) {
+            float *dst = Fpm + ro, *dst_lo = dst + (size_t)g.B * g.Npad * g.Kc;
+            for (int c = lane; c < Cp; c += 32) {
+                const float f = tq[c * 33] * iq, hi = round_tf32(f);
+                dst[c] = hi;
+                if (g.split) dst_lo[c] = round_tf32(f - hi);
             }
         }
-#pragma unroll 1
-        for (int q = warp; q < 32; q += 8) {          // position-major rows: the branch's Cp contiguous channels per position
-            const float iq = s_inv[br][q];
-            const float *tq = T + c0 * 33 + q;
-            const size_t ro = (prow + q) * g.Kc + c0;
-            if (Fpm) {
-                float *dst = Fpm + ro, *dst_lo = dst + (size_t)g.B * g.Npad * g.Kc;
-                for (int c = lane; c < Cp; c += 32) {
-                    const float f = tq[c * 33] * iq, hi = round_tf32(f);
-                    dst[c] = hi;
-                    if (g.split) dst_lo[c] = round_tf32(f - hi);
-                }
-            }
-            if (FpmH) {                               // FP16 copy: two channels per lane, 128 bytes per warp store
-                __half2 *dh = reinterpret_cast<__half2 *>(FpmH + ro) + lane;
-                const float *t2 = tq + 2 * lane * 33;
+        if (FpmH) {                                   // FP16 copy: two channels per lane, 128 bytes per warp store
+            __half2 *dh = reinterpret_cast<__half2 *>(FpmH + ro) + lane;
+            const float *t2 = tq + 2 * lane * 33;
 #pragma unroll 4
-                for (int c = 2 * lane; c < Cp; c += 64, dh += 32, t2 += 64 * 33) *dh = __floats2half2_rn(t2[0] * iq, t2[33] * iq);
-            }
-            if (kExact) {                             // raw pooled features, position-major: what the FP64 re-decision reads
-                float *dp = ex.Ppm + ro + lane;
-                const float *t1 = tq + lane * 33;
+            for (int c = 2 * lane; c < Cp; c += 64, dh += 32, t2 += 64 * 33) *dh = __floats2half2_rn(t2[0] * iq, t2[33] * iq);
+        }
+        if (kExact) {                                 // raw pooled features, position-major: what the FP64 re-decision reads
+            float *dp = ex.Ppm + ro + lane;
+            const float *t1 = tq + lane * 33;
 #pragma unroll 4
-                for (int c = lane; c < Cp; c += 32, dp += 32, t1 += 32 * 33) *dp = *t1;
-            }
+            for (int c = lane; c < Cp; c += 32, dp += 32, t1 += 32 * 33) *dp = *t1;
         }
     }
 }
@@ -1733,7 +1721,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     float *Fpm = reinterpret_cast<float *>(ws + wo.Fpm), *Fcm = reinterpret_cast<float *>(ws + wo.Fcm);
     float *nrm = reinterpret_cast<float *>(ws + wo.nrm);
 
-    const size_t pack_smem = (size_t)g.Kc * 33 * 4;
+    const size_t finish_smem = (size_t)g.Kc * 33 * 4, pack_smem = (size_t)(g.C1p > g.C2p ? g.C1p : g.C2p) * 33 * 4;
     int rc = opt_in_smem(fa_pos_pack<false>, pack_smem);
     if (rc) return rc;
     if ((rc = opt_in_smem(fa_pos_pack<true>, pack_smem))) return rc;
@@ -1753,7 +1741,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     rex.sb = reinterpret_cast<uint4 *>(ws + wo.sb);
     // FP16 form: the FP16 copies are the only ones written (and read back by the normalisation Jacobian)
     if (g.exact) {
-        fa_pos_pack<true><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
+        fa_pos_pack<true><<<dim3(g.Npad / 32, B, 2), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
         if (const char *e = getenv("DSRL_POS_KSIGMA")) { const float v = (float)atof(e); if (v >= 0.f && v < 1e6f) ksigma = v; }   // tuning / test hook
         tau_r = g.split ? kRound11 * kRound11 : kRound11;      // 3xTF32: the products missing from the split are second order
         if (!(need_grad && g.ab)) {        // the two-pass form computes the threshold in pass A's prologue (one launch and ~20 us less)
@@ -1761,7 +1749,7 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
             fa_pos_tau<<<B, 1024, 0, st>>>(g, pex.Ppm, pex.inv64, tau_r * tau_r, kAccNoise * kAccNoise, ksigma, reinterpret_cast<float *>(ws + wo.tau));
         }
     } else {
-        fa_pos_pack<false><<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
+        fa_pos_pack<false><<<dim3(g.Npad / 32, B, 2), 256, pack_smem, st>>>(x1, x2, g, g.half ? nullptr : Fpm, g.half ? nullptr : Fcm, nrm, FpmH, FcmH, pex);
     }
     DSRL_LAUNCH_CHECK();
     // the tile kernel's raw accumulator rows -> dP / dX (all variants share it)
@@ -1789,8 +1777,8 @@ int fa_pos_forward_impl(int precision, const float *x1, const float *x2, int B, 
     auto finish = [&](const PosArgs &a) -> int {
         int rc2;
         if (g.exact && !g.ab && (rc2 = resolve())) return rc2;
-        if ((rc2 = opt_in_smem(fa_pos_finish, pack_smem))) return rc2;
-        fa_pos_finish<<<dim3(g.Npad / 32, B), 256, pack_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
+        if ((rc2 = opt_in_smem(fa_pos_finish, finish_smem))) return rc2;
+        fa_pos_finish<<<dim3(g.Npad / 32, B), 256, finish_smem, st>>>(g, a.opart, g.half ? nullptr : Fcm, FcmH, nrm, a.grad_scale, a.dP, a.dx[0], a.dx[1], a.direct ? a.go : nullptr);
         DSRL_LAUNCH_CHECK();
         return DSRL_OK;
     };
