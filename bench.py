@@ -234,6 +234,13 @@ def bench_fa_train(args, rank, world, dev, peaks):
     ms = max_over_ranks(ms, world, dev)
     ms_hot = max_over_ranks(ms_hot, world, dev)
     loss_val = float(static_loss.item())
+    # the floor of this measurement: a graph holding ONE 4-byte memset node, timed the same way (event pair around a replay after
+    # an L2 flush) -- what a step costs before any arithmetic
+    z = torch.zeros(1, dtype=torch.float32, device=dev)
+    null_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(null_graph):
+        z.zero_()
+    floor_ms = max_over_ranks(timed_steps(null_graph.replay, args.steps, args.warmup, world, flush=flush), world, dev)
 
     # end to end through the public API from pinned host buffers
     p1 = torch.from_numpy(x1h).pin_memory()
@@ -321,6 +328,8 @@ def bench_fa_train(args, rank, world, dev, peaks):
                    "l2": "flushed before every step (256 MiB fill, outside the per-step event pair)",
                    "launch": f"CUDA graph replay of the step's {launches_per_step} kernels (FAPlan: fused forward + backward)", "parallelism": f"dp{world} (batch shard, no data-path collective)",
                    "ms_per_step_l2_warm": ms_hot / args.steps, "loss": loss_val,
+                   "measurement_floor_ms": floor_ms / args.steps,
+                   "measurement_floor_note": "a graph of one 4-byte memset node timed the same way: the launch + event cost inside ms_per_step",
                    "pytorch_eager_same_gpu_ms": eager_ms, "configs0_on_gpu": cfg0},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic().get("fa_train"),
@@ -1223,6 +1232,7 @@ def summarise_secondary(extra):
         "seg_counts_e2e_gpx_per_s": get("seg_counts", "e2e", "value"),
         "seg_logits_gpx_per_s": get("seg_logits", "value"), "seg_logits_hbm_frac": get("seg_logits", "roofline", "frac"),
         "fa_train_us_per_step": (get("fa_train", "ms_per_step") or 0) * 1e3 or None, "fa_train_gpairs_per_s": get("fa_train", "value"),
+        "fa_train_measurement_floor_us": (get("fa_train", "config", "measurement_floor_ms") or 0) * 1e3 or None,
         "fa_train_e2e_gpairs_per_s": get("fa_train", "e2e", "value"),
         "train_step_ms": get("train_step", "ms_per_step"), "train_step_images_per_s": get("train_step", "value"),
         "train_step_ms_with_stage3_loss": get("train_step", "with_dsrl_b200_stage3_loss", "ms_per_step"),
