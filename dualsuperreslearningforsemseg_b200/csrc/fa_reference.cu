@@ -399,8 +399,14 @@ __device__ __noinline__ double group_sum_d(double v, double *scratch, int gtid, 
     return scratch[32];
 }
 
+#ifdef DSRL_FUSED_TIMING
+__device__ long long g_fused_dbg[8];
+#endif
 __device__ __noinline__ float top_singular_warp(const float *sA, int rs, int cs, int m, int L, float *M0, float *M1,
                                                 float *xs, float *xl, int squarings) {
+#ifdef DSRL_FUSED_TIMING
+    const long long dbg_t0 = clock64();
+#endif
     // fp32 throughout: sigma only needs ~1e-6 relative (the loss tolerance is 1e-4, the reference itself is fp32) and
     // this single-warp dependent chain is the critical path of the whole forward -- fp64 shuffles/rsqrt tripled it.
     const int lane = threadIdx.x & 31;
@@ -472,8 +478,14 @@ __device__ __noinline__ float top_singular_warp(const float *sA, int rs, int cs,
         for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
         x = z;
         __syncwarp();
+#ifdef DSRL_FUSED_TIMING
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { g_fused_dbg[1] = it + 1; g_fused_dbg[2 + (it < 4 ? it : 4)] = __float_as_int(d); }
+#endif
         if (!(d > 1e-6f)) break;                                    // also leaves on NaN
     }
+#ifdef DSRL_FUSED_TIMING
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_fused_dbg[0] = clock64() - dbg_t0;
+#endif
     // consistent final pair: us = x/|x|, xl = V^T us, sigma = |xl|
     {
         const float nx = warp_sum(x * x);
@@ -1137,6 +1149,8 @@ struct FusedBranch {
     double pre[kFusedMaxW * kFusedMaxW + 1];   // their exclusive prefix sums
     float xs[32], xl[32];
     double scratch[34];
+    double keep[2];                            // max |P| (the scale of the unscaled Gram entries), sigma
+    unsigned wmax[8];                          // per-warp maxima of |P| (bit patterns)
 };
 inline bool fused_ok(const RefGeom &g) { return g.w <= kFusedMaxW && g.h <= kFusedMaxH; }
 
@@ -1173,24 +1187,30 @@ __device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, i
     return s / (float)(k * k);
 }
 
-__global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g,
+constexpr int kFusedThreads = 576, kFusedBranchThreads = 288;   // per branch: 256 workers + one solver warp
+__global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g,
                                                           RefSaved so, unsigned char *__restrict__ saved,
                                                           double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                           float g_scale, double loss_div, float *__restrict__ loss_out,
                                                           int need_grad, const float *__restrict__ grad_out,
                                                           float *__restrict__ dx1, float *__restrict__ dx2,
                                                           const float *__restrict__ bn) {
+    // Roles (round 2): S = P^T P / sigma^2, and sorting P^T P orders S, so nothing but the final scale needs sigma.  Per branch
+    // the 256 workers pool, form the unscaled Gram entries and sort / prefix-sum them WHILE one solver warp runs M = V V^T, the
+    // squarings and the power polish; both meet at one barrier.  The sigma solve (7.3 k cycles) and the Gram + sort (5.5 k) used
+    // to run one after the other.
     __shared__ FusedBranch sb[2];
-    __shared__ double red[34];
     __shared__ int is_last;
-    const int tid = threadIdx.x, br = tid >> 8, ht = tid & 255;
-    const Grp grp{ht, 256, 1 + br};
+    const int tid = threadIdx.x, br = tid / kFusedBranchThreads, ht = tid - br * kFusedBranchThreads;
+    const bool solver = ht >= 256;                       // warp 8 of the branch
+    const Grp grp{ht, 256, 1 + br};                      // the branch's workers
+    const Grp all{ht, kFusedBranchThreads, 3 + br};      // workers + solver warp
     FusedBranch &fb = sb[br];
     const int bc = blockIdx.x, h = g.h, w = g.w, n = g.n, lda = kFusedLda, hw = h * w;
     // every per-thread index decomposition is done once: ht = qw*w + rw (cell / S entry), ht + 256 = second cell
     const int qw = ht / w, rw = ht - qw * w;
     const int qw2 = (ht + 256) / w, rw2 = (ht + 256) - qw2 * w;
-    const bool c0 = ht < hw, c1 = ht + 256 < hw;
+    const bool c0 = !solver && ht < hw, c1 = !solver && ht + 256 < hw;
     const int a0 = qw * lda + rw, a1 = qw2 * lda + rw2;           // padded smem offsets of the thread's cells
 
 #ifdef DSRL_FUSED_TIMING
@@ -1200,89 +1220,108 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
 #define TSTAMP(i)
 #endif
     TSTAMP(0);
-    // 1. pool (FALoss.py:23-24)
+    // 1. pool (FALoss.py:23-24); the largest magnitude of the map rides along (one redux per warp): the Gram entries are formed
+    //    from P / max|P|, so they neither overflow nor underflow whatever the scale of the input
     const float *x = (br ? x2 : x1) + (size_t)bc * g.H * g.W;
     const bool vec4 = (g.k % 4 == 0) && (g.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const bool act = bn != nullptr;                          // {a, b, mean, invstd} per branch from ft_bn_forward_kernel
     const float bn_a = act ? __ldg(bn + 4 * br) : 1.f, bn_b = act ? __ldg(bn + 4 * br + 1) : 0.f;
-    if (c0) fb.P[a0] = pool_cell_rolled(x + (size_t)qw * g.k * g.W + (size_t)rw * g.k, g.W, g.k, vec4, act, bn_a, bn_b);
-    if (c1) fb.P[a1] = pool_cell_rolled(x + (size_t)qw2 * g.k * g.W + (size_t)rw2 * g.k, g.W, g.k, vec4, act, bn_a, bn_b);
-    grp.sync();
+    unsigned *wmax = fb.wmax;
+    if (!solver) {
+        float p0v = 0.f, p1v = 0.f;
+        if (c0) { p0v = pool_cell_rolled(x + (size_t)qw * g.k * g.W + (size_t)rw * g.k, g.W, g.k, vec4, act, bn_a, bn_b); fb.P[a0] = p0v; }
+        if (c1) { p1v = pool_cell_rolled(x + (size_t)qw2 * g.k * g.W + (size_t)rw2 * g.k, g.W, g.k, vec4, act, bn_a, bn_b); fb.P[a1] = p1v; }
+        // |x| bit patterns order like the values; a NaN (exponent all ones, mantissa non-zero) wins the maximum and poisons the scale
+        const unsigned mx = __reduce_max_sync(0xffffffffu, max(__float_as_uint(fabsf(p0v)), __float_as_uint(fabsf(p1v))));
+        if ((ht & 31) == 0) wmax[ht >> 5] = mx;
+    }
+    all.sync();                                              // barrier 1: P (and the maxima) visible to workers and solver
 
     TSTAMP(1);
-    // 2. sigma, u1, v1 (FALoss.py:10): M = V V^T by the whole group (m*m <= 256 entries), then one warp solves
     const int rs = g.transposed ? 1 : lda, cs = g.transposed ? lda : 1, m = g.m, L = g.L;
-    if (ht < m * m) {
-        const int i = ht / m, j = ht - i * m;
-        float s = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < L; ++c) s = fmaf(fb.P[i * rs + c * cs], fb.P[j * rs + c * cs], s);
-        fb.M[ht] = s;
-    }
-    grp.sync();
-    TSTAMP(2);
-    // six trace-normalised squarings of M by the whole group (one entry per thread, m*m <= 256): M^(64) is numerically
-    // rank one unless the spectral gap is tiny; one warp then polishes the vectors with power steps on V itself
-    float *mcur = fb.M, *mnxt = fb.M + m * m;
-    {
-        const int mi = ht / m, mj = ht - mi * m;
-#pragma unroll 1
-        for (int sq = 0; sq < 6; ++sq) {
-            float tr = 0.f;
-            for (int d = 0; d < m; ++d) tr += mcur[d * m + d];
-            if (!(tr > 0.f)) break;                              // zero / NaN matrix: same decision in every thread
-            const float inv = __frcp_rn(tr);
-            if (ht < m * m) {
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-                for (int k = 0; k + 1 < m; k += 2) {
-                    s0 = fmaf(mcur[mi * m + k], mcur[k * m + mj], s0);
-                    s1 = fmaf(mcur[mi * m + k + 1], mcur[(k + 1) * m + mj], s1);
-                }
-                if (m & 1) s0 = fmaf(mcur[mi * m + m - 1], mcur[(m - 1) * m + mj], s0);
-                mnxt[ht] = (s0 + s1) * inv * inv;
-            }
-            grp.sync();
-            float *t = mcur; mcur = mnxt; mnxt = t;
-        }
-    }
-    if (ht < 32) {
-        const double sg = top_singular_warp(fb.P, rs, cs, m, L, mcur, mnxt, fb.xs, fb.xl, 0);
-        if (ht == 0) fb.scratch[33] = sg;
-    }
-    grp.sync();
-    TSTAMP(3);
-#ifdef DSRL_FUSED_TIMING
-    if (bc == 0 && tid == 0) { for (int q = 0; q < 10; ++q) reinterpret_cast<double *>(partials + 80)[q] = (double)fb.xs[31 - q]; }
-#endif
-    const double sigma = fb.scratch[33];
-    const float *du = g.transposed ? fb.xl : fb.xs, *dv = g.transposed ? fb.xs : fb.xl;
-    const float sigf = (float)sigma;
-
-    // 3. S = A^^T A^ (FALoss.py:10-11); sigma == 0 -> 0/0 = NaN like the reference
-    if (c0) fb.A[a0] = fb.P[a0] / sigf;
-    if (c1) fb.A[a1] = fb.P[a1] / sigf;
-    grp.sync();
-    if (ht < n) {
-        float s = 0.f;
-#pragma unroll 4
-        for (int y = 0; y < h; ++y) s = fmaf(fb.A[y * lda + qw], fb.A[y * lda + rw], s);
-        fb.S[ht] = s;
-    }
-    __syncthreads();
-
-    TSTAMP(4);
-    // 4. all pairs (FALoss.py:27-34), exact in O(n log n) instead of n^2: each group sorts its own branch's values
-    //    (bitonic: shuffles inside a warp, 6 shared-memory exchanges across warps) and prefix-sums them in fp64; then
-    //    every value x of the OTHER branch is ranked with two binary searches:
-    //        lt = #{y < x}, le = #{y <= x}:   sum_j sign(x - y_j) = lt - (n - le)        (exact integer)
-    //                                         sum_j |x - y_j|     = x (lt - gt) - pre[lt] + (pre[n] - pre[le])
-    //    A NaN anywhere (dead channel, sigma = 0) makes the loss NaN and every sign 0, as torch's sign() does.
+    float sraw = 0.f;                                        // worker: its entry of (P/r)^T (P/r)
+    float rmax = 0.f;
     double local = 0.0;
-    {
+    if (solver) {
+        // 2. sigma, u1, v1 (FALoss.py:10) by the solver warp alone: M = V V^T, six trace-normalised squarings (M^64 is numerically
+        //    rank one unless the spectral gap is tiny), power steps on V itself until the vectors stand still
+        const int lane = ht - 256;
+        float sg;
+        if (m <= 8) {
+            // the model's shapes (pooled 8 x 16): M lives in registers, lane 8 i + j holds M[i][j] and M[i + 4][j] (rows / columns
+            // past m are zero); a squaring is 24 shuffles + 16 multiply-adds instead of a chain of shared-memory round trips
+            const int i = lane >> 3, j = lane & 7;
+            float a0 = 0.f, a1 = 0.f;
+            {
+                const bool v0 = i < m && j < m, v1 = i + 4 < m && j < m;
+                const float *ri = fb.P + (v0 ? i : 0) * rs, *ri4 = fb.P + (v1 ? i + 4 : 0) * rs, *rj = fb.P + (j < m ? j : 0) * rs;
+#pragma unroll 8
+                for (int c = 0; c < L; ++c) {
+                    const float vj = rj[c * cs];
+                    a0 = fmaf(ri[c * cs], vj, a0);
+                    a1 = fmaf(ri4[c * cs], vj, a1);
+                }
+                if (!v0) a0 = 0.f;
+                if (!v1) a1 = 0.f;
+            }
+#pragma unroll 1
+            for (int sq = 0; sq < 6; ++sq) {
+                const float tr = warp_sum((i == j ? a0 : 0.f) + (i + 4 == j ? a1 : 0.f));
+                if (!(tr > 0.f)) break;                          // zero / NaN matrix: same decision in every lane
+                const float inv = __frcp_rn(tr);
+                float n0 = 0.f, n1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float mik0 = __shfl_sync(0xffffffffu, a0, (i << 3) | k), mik1 = __shfl_sync(0xffffffffu, a1, (i << 3) | k);
+                    const float mkj = __shfl_sync(0xffffffffu, k < 4 ? a0 : a1, ((k & 3) << 3) | j);
+                    n0 = fmaf(mik0, mkj, n0);
+                    n1 = fmaf(mik1, mkj, n1);
+                }
+                a0 = n0 * inv * inv;
+                a1 = n1 * inv * inv;
+            }
+            if (i < m && j < m) fb.M[i * m + j] = a0;
+            if (i + 4 < m && j < m) fb.M[(i + 4) * m + j] = a1;
+            __syncwarp();
+            sg = top_singular_warp(fb.P, rs, cs, m, L, fb.M, fb.M + m * m, fb.xs, fb.xl, 0);
+        } else {
+            for (int o = lane; o < m * m; o += 32) {
+                const int i = o / m, j = o - i * m;
+                float s = 0.f;
+#pragma unroll 4
+                for (int c = 0; c < L; ++c) s = fmaf(fb.P[i * rs + c * cs], fb.P[j * rs + c * cs], s);
+                fb.M[o] = s;
+            }
+            __syncwarp();
+            sg = top_singular_warp(fb.P, rs, cs, m, L, fb.M, fb.M + m * m, fb.xs, fb.xl, 6);
+        }
+        if (lane == 0) fb.keep[1] = (double)sg;
+    } else {
+        // 3. unscaled Gram entries (FALoss.py:10-11 without the 1/sigma^2), then
+        // 4. all pairs (FALoss.py:27-34), exact in O(n log n) instead of n^2: the workers sort their own branch's values (bitonic:
+        //    shuffles inside a warp, 6 shared-memory exchanges across warps) and prefix-sum them in fp64; after the barrier
+        //    every value x of the OTHER branch is ranked with two binary searches:
+        //        lt = #{y < x}, le = #{y <= x}:   sum_j sign(x - y_j) = lt - (n - le)        (exact integer)
+        //                                         sum_j |x - y_j|     = x (lt - gt) - pre[lt] + (pre[n] - pre[le])
+        //    A NaN anywhere (dead channel, sigma = 0) makes the loss NaN and every sign 0, as torch's sign() does.
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rmax = fmaxf(rmax, __uint_as_float(wmax[i]));     // NaN patterns: fmaxf drops them ...
+        {
+            unsigned any = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) any = max(any, wmax[i]);
+            if (any > 0x7f800000u) rmax = NAN;                                          // ... so they are put back here
+        }
+        const float rinv = rmax > 0.f ? 1.f / rmax : 0.f;                              // NaN / inf scale: rinv = NaN / 0 -> NaN entries below
+        if (ht < n) {
+            float sacc = 0.f;
+#pragma unroll 4
+            for (int y = 0; y < h; ++y) sacc = fmaf(fb.P[y * lda + qw] * rinv, fb.P[y * lda + rw] * rinv, sacc);
+            sraw = rmax > 0.f ? sacc : (rmax == 0.f ? 0.f : NAN);
+        }
         const int lane = ht & 31;
-        float v = ht < n ? fb.S[ht] : INFINITY;
-        const bool has_nan = __syncthreads_or(ht < n && v != v) != 0;
+        float v = ht < n ? sraw : INFINITY;
+        if (v != v) v = INFINITY;                                // NaNs do not take part in the ordering (the result is NaN anyway)
         int xbuf = 0;
 #pragma unroll 1
         for (int k = 2; k <= 256; k <<= 1) {
@@ -1290,7 +1329,7 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
             for (int j = k >> 1; j > 0; j >>= 1) {
                 float o;
                 if (j >= 32) {                                   // partner in another warp: through shared memory, two buffers
-                    float *xb = xbuf ? fb.M : fb.sorted;         // in turn (M is free after the sigma solve): the barrier of the
+                    float *xb = xbuf ? fb.A : fb.sorted;         // in turn (A is written after barrier 2): the barrier of the
                     xbuf ^= 1;                                   // next exchange orders this one's reads before the buffer's reuse
                     xb[ht] = v;
                     grp.sync();
@@ -1302,7 +1341,7 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
                 v = keep_min ? fminf(v, o) : fmaxf(v, o);
             }
         }
-        fb.sorted[ht] = v;
+        fb.sorted[ht] = v;                                       // (the last exchange went through A, which is rebuilt after barrier 2)
         // exclusive prefix sums of the sorted values (the +inf padding sits at the end and is never read)
         double p = ht < n ? (double)v : 0.0;
 #pragma unroll
@@ -1315,24 +1354,38 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
         double base = 0.0;
         for (int wq = 0; wq < (ht >> 5); ++wq) base += fb.scratch[wq];
         fb.pre[ht + 1] = base + p;
-        if (ht == 0) fb.pre[0] = 0.0;
-        __syncthreads();                                         // both branches sorted and summed
-
-        if (ht < n && (br == 0 || need_grad)) {
-            const FusedBranch &ob = sb[1 - br];
-            const float x = fb.S[ht];
-            int lo = 0, hi = n;                                  // lt: first index with y >= x
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ob.sorted[mid] < x) lo = mid + 1; else hi = mid; }
-            const int lt = lo;
-            hi = n;                                              // le: first index with y > x
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ob.sorted[mid] <= x) lo = mid + 1; else hi = mid; }
-            const int le = lo, gt = n - le;
-            fb.cnt[ht] = has_nan ? 0 : lt - gt;
-            if (br == 0)
-                local = has_nan ? (double)NAN : (double)x * (double)(lt - gt) - ob.pre[lt] + (ob.pre[n] - ob.pre[le]);
-        }
+        if (ht == 0) { fb.pre[0] = 0.0; fb.keep[0] = (double)rmax; }
+    }
+    all.sync();                                              // barrier 2: sigma, u1, v1 <-> sorted values, prefix sums, scale
+    TSTAMP(2);
+    TSTAMP(3);
+    const double sigma = fb.keep[1];
+    const float *du = g.transposed ? fb.xl : fb.xs, *dv = g.transposed ? fb.xs : fb.xl;
+    const float sigf = (float)sigma;
+    if (c0) fb.A[a0] = fb.P[a0] / sigf;                      // A^ = P / sigma for the gradient (sigma == 0 -> NaN like the reference)
+    if (c1) fb.A[a1] = fb.P[a1] / sigf;
+    // both branches sorted and solved; S = (r / sigma)^2 * (P/r)^T (P/r) is NaN throughout for a dead (or non-finite) map
+    const bool bad = !(sigma > 0.0 && sigma < (double)INFINITY) || (!solver && ht < n && !(fabsf(sraw) < INFINITY));
+    const bool has_nan = __syncthreads_or(bad) != 0;
+    TSTAMP(4);
+    if (!solver && ht < n && (br == 0 || need_grad)) {
+        const FusedBranch &ob = sb[1 - br];
+        // values compared in double: x = sraw * (r/sigma)^2 on both sides, so both directions see the same numbers
+        const double ro = fb.keep[0] / sigma, oo = ob.keep[0] / ob.keep[1];
+        const double sc = ro * ro, osc = oo * oo;
+        const double xd = (double)sraw * sc;
+        int lo = 0, hi = n;                                  // lt: first index with y >= x
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)ob.sorted[mid] * osc < xd) lo = mid + 1; else hi = mid; }
+        const int lt = lo;
+        hi = n;                                              // le: first index with y > x
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)ob.sorted[mid] * osc <= xd) lo = mid + 1; else hi = mid; }
+        const int le = lo, gt = n - le;
+        fb.cnt[ht] = has_nan ? 0 : lt - gt;
+        if (br == 0)
+            local = has_nan ? (double)NAN : xd * (double)(lt - gt) - ob.pre[lt] * osc + (ob.pre[n] - ob.pre[le]) * osc;
     }
     TSTAMP(5);
+    if (solver) return;                                      // no block-wide barrier follows
     if (br == 0) {
         const double tot = group_sum_d(local, fb.scratch, ht, 256, 1 + br);
         if (ht == 0) {
@@ -1388,32 +1441,16 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
     }
 
     TSTAMP(7);
-    // 6. loss finish by the last CTA (fixed summation order -> deterministic).  Up to 1024 partials (every shape the model
-    //    produces: one per (b, c)) are summed by the ticket holder's own warp alone -- it wrote `is_last` itself, so the last CTA,
-    //    which is the critical path of the launch, skips a block-wide barrier and a 512-thread reduction (3.4 k -> 0.9 k cycles).
-    if (gridDim.x <= 1024) {
-        if (tid < 32) {
-            __syncwarp();
-            if (is_last) {
-                __threadfence();
-                double s = 0.0;
-#pragma unroll 1
-                for (int i = tid; i < (int)gridDim.x; i += 32) s += __ldcg(partials + i);
-                s = wsum_d(s);
-                if (tid == 0) {
-                    *reinterpret_cast<double *>(saved) = s;
-                    *loss_out = (float)(s / loss_div);
-                }
-            }
-        }
-    } else {
-        __syncthreads();
+    // 6. loss finish by the last CTA (fixed summation order -> deterministic): the ticket holder's own warp sums the partials -- it
+    //    wrote `is_last` itself, so the last CTA, which is the critical path of the launch, needs no block-wide barrier
+    if (tid < 32) {
+        __syncwarp();
         if (is_last) {
             __threadfence();
             double s = 0.0;
 #pragma unroll 1
-            for (int i = tid; i < (int)gridDim.x; i += 512) s += __ldcg(partials + i);
-            s = group_sum_d(s, red, tid, 512, 0);
+            for (int i = tid; i < (int)gridDim.x; i += 32) s += __ldcg(partials + i);
+            s = wsum_d(s);
             if (tid == 0) {
                 *reinterpret_cast<double *>(saved) = s;
                 *loss_out = (float)(s / loss_div);
@@ -1421,6 +1458,9 @@ __global__ void __launch_bounds__(512) fa_ref_fused_small(const float *__restric
         }
     }
     TSTAMP(8);
+#ifdef DSRL_FUSED_TIMING
+    if (bc == 0 && tid == 0) { for (int q = 0; q < 8; ++q) tm[9 + q] = g_fused_dbg[q]; }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1502,7 +1542,7 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
         unsigned *ticket = next_ticket_slot(st);
         if (!ticket) return DSRL_ERR_CUDA;
         const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
-        fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
+        fa_ref_fused_small<<<g.BC, kFusedThreads, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
                                                   loss_out, need_grad, nullptr, nullptr, nullptr, nullptr);
         DSRL_LAUNCH_CHECK();
         return DSRL_OK;
@@ -1575,7 +1615,7 @@ int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int 
     unsigned *ticket = next_ticket_slot(st);
     if (!ticket) return DSRL_ERR_CUDA;
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
-    fa_ref_fused_small<<<g.BC, 512, 0, st>>>(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket,
+    fa_ref_fused_small<<<g.BC, kFusedThreads, 0, st>>>(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket,
                                               (float)(1.0 / Z), Z, loss_out, 1, grad_out, dx1, dx2, bn);
     DSRL_LAUNCH_CHECK();
     return DSRL_OK;

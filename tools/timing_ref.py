@@ -9,4 +9,6 @@ plan = FAPlan((6, 1, 64, 128), subsample_factor=8)
 for _ in range(5):
     plan.forward(a, b, True); torch.cuda.synchronize()
     tm = plan.ws.view(torch.int64)[64:73].cpu().numpy()
-    print("phase cycles (pool, M, sigma, S, pairs, partial, grad, finish):", np.diff(tm), "total", tm[8] - tm[0])
+    dbg = plan.ws.view(torch.int64)[73:81].cpu().numpy()
+    print("  polish: cycles to loop end", dbg[0], "iterations", dbg[1], "d per iteration", [float(np.int32(v).view(np.float32)) for v in dbg[2:7]])
+    print("phase cycles (pool, Gram+sort || sigma solve, -, scale+vote, rank, partial, grad, finish):", np.diff(tm), "total", tm[8] - tm[0])
