@@ -1149,7 +1149,8 @@ struct FusedBranch {
     double pre[kFusedMaxW * kFusedMaxW + 1];   // their exclusive prefix sums
     float xs[32], xl[32];
     double scratch[34];
-    double keep[2];                            // max |P| (the scale of the unscaled Gram entries), sigma
+    double sd[kFusedMaxW * kFusedMaxW];        // the sorted values scaled to S (double), what the other branch's searches read
+    double keep[3];                            // max |P| (the scale of the unscaled Gram entries), sigma, (max|P| / sigma)^2
     unsigned wmax[8];                          // per-warp maxima of |P| (bit patterns)
 };
 inline bool fused_ok(const RefGeom &g) { return g.w <= kFusedMaxW && g.h <= kFusedMaxH; }
@@ -1264,6 +1265,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                 if (!v0) a0 = 0.f;
                 if (!v1) a1 = 0.f;
             }
+            const float o0 = a0, o1 = a1;                       // M itself, for the power steps below
 #pragma unroll 1
             for (int sq = 0; sq < 6; ++sq) {
                 const float tr = warp_sum((i == j ? a0 : 0.f) + (i + 4 == j ? a1 : 0.f));
@@ -1280,10 +1282,64 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                 a0 = n0 * inv * inv;
                 a1 = n1 * inv * inv;
             }
-            if (i < m && j < m) fb.M[i * m + j] = a0;
-            if (i + 4 < m && j < m) fb.M[(i + 4) * m + j] = a1;
-            __syncwarp();
-            sg = top_singular_warp(fb.P, rs, cs, m, L, fb.M, fb.M + m * m, fb.xs, fb.xl, 0);
+            // Power steps with everything in registers: every lane holds the whole vector x and row (lane & 7) of M, so a step
+            // is 8 multiply-adds, an all-gather of 8 shuffles and LOCAL norms / convergence test -- no warp reductions (the
+            // shared-memory form with V-steps spent 2.5 k cycles per step on them).  Start: column of the largest diagonal
+            // entry of M^64.  Same stopping rule as top_singular_warp: on the vector, because the gradient's rank-one term
+            // needs u1 v1^T to ~1e-5.
+            float xv[8], row[8];
+            {
+                float dg[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dg[k] = __shfl_sync(0xffffffffu, k < 4 ? a0 : a1, ((k & 3) << 3) | k);
+                int best = 0;
+#pragma unroll
+                for (int k = 1; k < 8; ++k) if (k < m && dg[k] > dg[best]) best = k;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xv[k] = __shfl_sync(0xffffffffu, k < 4 ? a0 : a1, ((k & 3) << 3) | best);
+                const int r = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float lo = __shfl_sync(0xffffffffu, o0, ((r & 3) << 3) | k), hi4 = __shfl_sync(0xffffffffu, o1, ((r & 3) << 3) | k);
+                    row[k] = r < 4 ? lo : hi4;
+                }
+            }
+#pragma unroll 1
+            for (int it = 0; it < 96; ++it) {
+                float nx = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nx = fmaf(xv[k], xv[k], nx);
+                const float rn = nx > 0.f ? rsqrtf(nx) : 0.f;
+                float z = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { xv[k] *= rn; z = fmaf(row[k], xv[k], z); }
+                float zk[8], s2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { zk[k] = __shfl_sync(0xffffffffu, z, k); s2 = fmaf(zk[k], zk[k], s2); }
+                const float rz = s2 > 0.f ? rsqrtf(s2) : 0.f;
+                float d = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { d = fmaxf(d, fabsf(zk[k] * rz - xv[k])); xv[k] = zk[k]; }
+                if (!(d > 1e-6f)) break;                         // also leaves on NaN (fmaxf drops it: checked below)
+                if (s2 != s2) break;
+            }
+            {   // consistent final pair: us = x/|x|, xl = V^T us / sigma, sigma = |V^T us|
+                float nx = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nx = fmaf(xv[k], xv[k], nx);
+                const float rn = nx > 0.f ? rsqrtf(nx) : (nx == 0.f ? 0.f : NAN);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (lane == k && k < m) fb.xs[k] = xv[k] * rn;
+                float y = 0.f;
+                if (lane < L) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) if (k < m) y = fmaf(fb.P[k * rs + lane * cs], xv[k] * rn, y);
+                }
+                const float s2 = warp_sum(y * y);
+                sg = sqrtf(s2);
+                if (lane < L) fb.xl[lane] = s2 > 0.f ? y / sg : 0.f;
+                __syncwarp();
+            }
         } else {
             for (int o = lane; o < m * m; o += 32) {
                 const int i = o / m, j = o - i * m;
@@ -1365,21 +1421,29 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
     if (c0) fb.A[a0] = fb.P[a0] / sigf;                      // A^ = P / sigma for the gradient (sigma == 0 -> NaN like the reference)
     if (c1) fb.A[a1] = fb.P[a1] / sigf;
     // both branches sorted and solved; S = (r / sigma)^2 * (P/r)^T (P/r) is NaN throughout for a dead (or non-finite) map
+    // values compared in double: float Gram entry * (r/sigma)^2, the same expression on both sides, so both directions of the
+    // ranking see the same numbers; every worker scales one sorted value of its own branch for the other branch's searches
+    const double ro = fb.keep[0] / sigma, sc = ro * ro;
+    if (!solver && ht < n) fb.sd[ht] = (double)fb.sorted[ht] * sc;
+    if (ht == 0) fb.keep[2] = sc;
     const bool bad = !(sigma > 0.0 && sigma < (double)INFINITY) || (!solver && ht < n && !(fabsf(sraw) < INFINITY));
     const bool has_nan = __syncthreads_or(bad) != 0;
     TSTAMP(4);
     if (!solver && ht < n && (br == 0 || need_grad)) {
         const FusedBranch &ob = sb[1 - br];
-        // values compared in double: x = sraw * (r/sigma)^2 on both sides, so both directions see the same numbers
-        const double ro = fb.keep[0] / sigma, oo = ob.keep[0] / ob.keep[1];
-        const double sc = ro * ro, osc = oo * oo;
+        const double osc = ob.keep[2];
         const double xd = (double)sraw * sc;
-        int lo = 0, hi = n;                                  // lt: first index with y >= x
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)ob.sorted[mid] * osc < xd) lo = mid + 1; else hi = mid; }
-        const int lt = lo;
-        hi = n;                                              // le: first index with y > x
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)ob.sorted[mid] * osc <= xd) lo = mid + 1; else hi = mid; }
-        const int le = lo, gt = n - le;
+        // lt = #{y < x}, le = #{y <= x}: two branch-free searches over the n <= 256 sorted values, interleaved (fixed 9 probes
+        // each; the divergent while-loops they replace took 2.6 k cycles)
+        int lt = 0, le = 0;
+#pragma unroll
+        for (int step = 256; step > 0; step >>= 1) {           // counts up to 256 = binary digits 256 .. 1
+            const int p1 = lt + step, p2 = le + step;
+            const double y1 = ob.sd[min(p1, n) - 1], y2 = ob.sd[min(p2, n) - 1];
+            if (p1 <= n && y1 < xd) lt = p1;
+            if (p2 <= n && y2 <= xd) le = p2;
+        }
+        const int gt = n - le;
         fb.cnt[ht] = has_nan ? 0 : lt - gt;
         if (br == 0)
             local = has_nan ? (double)NAN : xd * (double)(lt - gt) - ob.pre[lt] * osc + (ob.pre[n] - ob.pre[le]) * osc;
