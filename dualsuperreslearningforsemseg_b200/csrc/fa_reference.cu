@@ -1149,7 +1149,7 @@ struct FusedBranch {
     double pre[kFusedMaxW * kFusedMaxW + 1];   // their exclusive prefix sums
     float xs[32], xl[32];
     double scratch[34];
-    double sd[kFusedMaxW * kFusedMaxW];        // the sorted values scaled to S (double), what the other branch's searches read
+    float sf[kFusedMaxW * kFusedMaxW];         // the sorted values scaled to S, what the other branch's searches read
     double keep[3];                            // max |P| (the scale of the unscaled Gram entries), sigma, (max|P| / sigma)^2
     unsigned wmax[8];                          // per-warp maxima of |P| (bit patterns)
 };
@@ -1188,6 +1188,16 @@ __device__ __noinline__ float pool_cell_rolled(const float *__restrict__ base, i
     return s / (float)(k * k);
 }
 
+// Thread-block cluster plumbing of the fused kernel's loss reduction (B*C <= 8: the whole grid is one cluster).
+__device__ __forceinline__ uint32_t ref_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void ref_cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void ref_cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f64(double *own_smem, uint32_t rank, double v) {      // store into CTA `rank`'s copy
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(own_smem), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(r), "d"(v) : "memory");
+}
+
 constexpr int kFusedThreads = 576, kFusedBranchThreads = 288;   // per branch: 256 workers + one solver warp
 __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float *__restrict__ x1, const float *__restrict__ x2, RefGeom g,
                                                           RefSaved so, unsigned char *__restrict__ saved,
@@ -1195,13 +1205,14 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                                                           float g_scale, double loss_div, float *__restrict__ loss_out,
                                                           int need_grad, const float *__restrict__ grad_out,
                                                           float *__restrict__ dx1, float *__restrict__ dx2,
-                                                          const float *__restrict__ bn) {
+                                                          const float *__restrict__ bn, int use_cluster) {
     // Roles (round 2): S = P^T P / sigma^2, and sorting P^T P orders S, so nothing but the final scale needs sigma.  Per branch
     // the 256 workers pool, form the unscaled Gram entries and sort / prefix-sum them WHILE one solver warp runs M = V V^T, the
     // squarings and the power polish; both meet at one barrier.  The sigma solve (7.3 k cycles) and the Gram + sort (5.5 k) used
     // to run one after the other.
     __shared__ FusedBranch sb[2];
     __shared__ int is_last;
+    __shared__ double cl_part[8];                       // cluster form: CTA 0 collects the loss partials of the (<= 8) CTAs here
     const int tid = threadIdx.x, br = tid / kFusedBranchThreads, ht = tid - br * kFusedBranchThreads;
     const bool solver = ht >= 256;                       // warp 8 of the branch
     const Grp grp{ht, 256, 1 + br};                      // the branch's workers
@@ -1253,6 +1264,12 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
             // past m are zero); a squaring is 24 shuffles + 16 multiply-adds instead of a chain of shared-memory round trips
             const int i = lane >> 3, j = lane & 7;
             float a0 = 0.f, a1 = 0.f;
+#ifdef DSRL_FUSED_TIMING
+#define SSTAMP(q) do { if (bc == 0 && br == 0 && lane == 0) g_fused_dbg[q] = clock64(); } while (0)
+#else
+#define SSTAMP(q)
+#endif
+            SSTAMP(0);
             {
                 const bool v0 = i < m && j < m, v1 = i + 4 < m && j < m;
                 const float *ri = fb.P + (v0 ? i : 0) * rs, *ri4 = fb.P + (v1 ? i + 4 : 0) * rs, *rj = fb.P + (j < m ? j : 0) * rs;
@@ -1265,11 +1282,16 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                 if (!v0) a0 = 0.f;
                 if (!v1) a1 = 0.f;
             }
+            SSTAMP(1);
             const float o0 = a0, o1 = a1;                       // M itself, for the power steps below
 #pragma unroll 1
             for (int sq = 0; sq < 6; ++sq) {
                 const float tr = warp_sum((i == j ? a0 : 0.f) + (i + 4 == j ? a1 : 0.f));
                 if (!(tr > 0.f)) break;                          // zero / NaN matrix: same decision in every lane
+                // the matrix squared last time had trace 1, so tr = sum lambda^2 / (sum lambda)^2, which is 1 exactly when it has
+                // rank one: stop squaring as soon as that holds to rounding (three squarings for post-ReLU maps); the power
+                // steps below check the vector anyway
+                if (sq > 0 && tr > 1.f - 2e-6f) break;
                 const float inv = __frcp_rn(tr);
                 float n0 = 0.f, n1 = 0.f;
 #pragma unroll
@@ -1287,6 +1309,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
             // shared-memory form with V-steps spent 2.5 k cycles per step on them).  Start: column of the largest diagonal
             // entry of M^64.  Same stopping rule as top_singular_warp: on the vector, because the gradient's rank-one term
             // needs u1 v1^T to ~1e-5.
+            SSTAMP(2);
             float xv[8], row[8];
             {
                 float dg[8];
@@ -1304,6 +1327,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                     row[k] = r < 4 ? lo : hi4;
                 }
             }
+            SSTAMP(3);
 #pragma unroll 1
             for (int it = 0; it < 96; ++it) {
                 float nx = 0.f;
@@ -1323,6 +1347,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                 if (!(d > 1e-6f)) break;                         // also leaves on NaN (fmaxf drops it: checked below)
                 if (s2 != s2) break;
             }
+            SSTAMP(4);
             {   // consistent final pair: us = x/|x|, xl = V^T us / sigma, sigma = |V^T us|
                 float nx = 0.f;
 #pragma unroll
@@ -1340,6 +1365,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
                 if (lane < L) fb.xl[lane] = s2 > 0.f ? y / sg : 0.f;
                 __syncwarp();
             }
+            SSTAMP(5);
         } else {
             for (int o = lane; o < m * m; o += 32) {
                 const int i = o / m, j = o - i * m;
@@ -1379,9 +1405,9 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
         float v = ht < n ? sraw : INFINITY;
         if (v != v) v = INFINITY;                                // NaNs do not take part in the ordering (the result is NaN anyway)
         int xbuf = 0;
-#pragma unroll 1
+#pragma unroll
         for (int k = 2; k <= 256; k <<= 1) {
-#pragma unroll 1
+#pragma unroll
             for (int j = k >> 1; j > 0; j >>= 1) {
                 float o;
                 if (j >= 32) {                                   // partner in another warp: through shared memory, two buffers
@@ -1424,7 +1450,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
     // values compared in double: float Gram entry * (r/sigma)^2, the same expression on both sides, so both directions of the
     // ranking see the same numbers; every worker scales one sorted value of its own branch for the other branch's searches
     const double ro = fb.keep[0] / sigma, sc = ro * ro;
-    if (!solver && ht < n) fb.sd[ht] = (double)fb.sorted[ht] * sc;
+    if (!solver && ht < n) fb.sf[ht] = (float)((double)fb.sorted[ht] * sc);
     if (ht == 0) fb.keep[2] = sc;
     const bool bad = !(sigma > 0.0 && sigma < (double)INFINITY) || (!solver && ht < n && !(fabsf(sraw) < INFINITY));
     const bool has_nan = __syncthreads_or(bad) != 0;
@@ -1433,32 +1459,53 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
         const FusedBranch &ob = sb[1 - br];
         const double osc = ob.keep[2];
         const double xd = (double)sraw * sc;
+        const float xf = (float)xd;                          // the very float the other branch finds for this entry in fb.sf
+#ifdef DSRL_FUSED_TIMING
+        if (bc == 0 && tid == 0) g_fused_dbg[6] = clock64();
+#endif
         // lt = #{y < x}, le = #{y <= x}: two branch-free searches over the n <= 256 sorted values, interleaved (fixed 9 probes
-        // each; the divergent while-loops they replace took 2.6 k cycles)
+        // each).  Ordering is decided on the float values of S, like the reference's fp32 tensors (FP64 compares took 270
+        // cycles per probe here); the sums below use the doubles, so a pair within one float ulp counts as a tie with an error
+        // below that ulp.
         int lt = 0, le = 0;
 #pragma unroll
         for (int step = 256; step > 0; step >>= 1) {           // counts up to 256 = binary digits 256 .. 1
             const int p1 = lt + step, p2 = le + step;
-            const double y1 = ob.sd[min(p1, n) - 1], y2 = ob.sd[min(p2, n) - 1];
-            if (p1 <= n && y1 < xd) lt = p1;
-            if (p2 <= n && y2 <= xd) le = p2;
+            const float y1 = ob.sf[min(p1, n) - 1], y2 = ob.sf[min(p2, n) - 1];
+            if (p1 <= n && y1 < xf) lt = p1;
+            if (p2 <= n && y2 <= xf) le = p2;
         }
         const int gt = n - le;
+#ifdef DSRL_FUSED_TIMING
+        if (bc == 0 && tid == 0) g_fused_dbg[7] = clock64() + (lt & 0);
+#endif
         fb.cnt[ht] = has_nan ? 0 : lt - gt;
         if (br == 0)
             local = has_nan ? (double)NAN : xd * (double)(lt - gt) - ob.pre[lt] * osc + (ob.pre[n] - ob.pre[le]) * osc;
     }
     TSTAMP(5);
-    if (solver) return;                                      // no block-wide barrier follows
+    // Loss partial of this (b, c).  Grids of up to 8 CTAs are launched as ONE cluster: the partial goes into CTA 0's shared
+    // memory and every thread arrives (once, without waiting) at the cluster barrier; CTA 0 waits on it only at the very end, so
+    // the exchange overlaps the gradient phase.  The global ticket it replaces (fence + atomic round trip here, fence + L2 reads
+    // in the last CTA) cost 2 k + 2 k cycles on the critical path.  Larger grids keep the ticket.
+    if (solver) {
+        if (use_cluster) ref_cluster_arrive();
+        return;                                              // no block-wide barrier follows
+    }
     if (br == 0) {
         const double tot = group_sum_d(local, fb.scratch, ht, 256, 1 + br);
         if (ht == 0) {
-            partials[bc] = tot;
-            __threadfence();
-            const unsigned old = atomicInc(ticket, gridDim.x - 1);     // wraps to 0 after the last CTA: self-resetting
-            is_last = (old == gridDim.x - 1);
+            if (use_cluster) {
+                st_cluster_f64(&cl_part[ref_cluster_rank()], 0u, tot);
+            } else {
+                partials[bc] = tot;
+                __threadfence();
+                const unsigned old = atomicInc(ticket, gridDim.x - 1);     // wraps to 0 after the last CTA: self-resetting
+                is_last = (old == gridDim.x - 1);
+            }
         }
     }
+    if (use_cluster) ref_cluster_arrive();
 
     TSTAMP(6);
     // 5. pooled gradient for unit upstream gradient
@@ -1507,7 +1554,17 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
     TSTAMP(7);
     // 6. loss finish by the last CTA (fixed summation order -> deterministic): the ticket holder's own warp sums the partials -- it
     //    wrote `is_last` itself, so the last CTA, which is the critical path of the launch, needs no block-wide barrier
-    if (tid < 32) {
+    if (use_cluster) {
+        if (tid < 32 && ref_cluster_rank() == 0) {
+            ref_cluster_wait();                              // every thread of every CTA has arrived: all partials are in cl_part
+            if (tid == 0) {
+                double s = 0.0;
+                for (int i = 0; i < (int)gridDim.x; ++i) s += cl_part[i];
+                *reinterpret_cast<double *>(saved) = s;
+                *loss_out = (float)(s / loss_div);
+            }
+        }
+    } else if (tid < 32) {
         __syncwarp();
         if (is_last) {
             __threadfence();
@@ -1535,6 +1592,31 @@ constexpr size_t kSmemLimit = 220 * 1024;
 template <typename K>
 int opt_in_smem(K kern, size_t bytes) {
     if (bytes > 48 * 1024) DSRL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DSRL_OK;
+}
+
+// The fused kernel as one thread-block cluster when the grid has at most 8 CTAs (its loss reduction then runs over distributed
+// shared memory, see the kernel); a cluster size the device refuses falls back to the plain launch with the global ticket.
+int launch_fused(const float *x1, const float *x2, const RefGeom &g, const RefSaved &so, unsigned char *saved, double *partials,
+                 unsigned *ticket, float g_scale, double loss_div, float *loss_out, int need_grad, const float *grad_out, float *dx1,
+                 float *dx2, const float *bn, cudaStream_t st) {
+    static std::atomic<int> cluster_ok[9];                   // per cluster size: 0 untried, 1 works, -1 refused
+    if (g.BC <= 8 && cluster_ok[g.BC].load() >= 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(g.BC); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = g.BC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, fa_ref_fused_small, x1, x2, g, so, saved, partials, ticket, g_scale, loss_div, loss_out,
+                                                 need_grad, grad_out, dx1, dx2, bn, 1);
+        if (e == cudaSuccess) { cluster_ok[g.BC].store(1); ::dsrl::count_launch(); return DSRL_OK; }
+        (void)cudaGetLastError();
+        cluster_ok[g.BC].store(-1);
+    }
+    fa_ref_fused_small<<<g.BC, kFusedThreads, 0, st>>>(x1, x2, g, so, saved, partials, ticket, g_scale, loss_div, loss_out, need_grad, grad_out,
+                                                       dx1, dx2, bn, 0);
+    DSRL_LAUNCH_CHECK();
     return DSRL_OK;
 }
 
@@ -1606,10 +1688,8 @@ int fa_ref_forward(const float *x1, const float *x2, int B, int C, int H, int W,
         unsigned *ticket = next_ticket_slot(st);
         if (!ticket) return DSRL_ERR_CUDA;
         const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
-        fa_ref_fused_small<<<g.BC, kFusedThreads, 0, st>>>(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z,
-                                                  loss_out, need_grad, nullptr, nullptr, nullptr, nullptr);
-        DSRL_LAUNCH_CHECK();
-        return DSRL_OK;
+        return launch_fused(x1, x2, g, so, saved, static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z, loss_out, need_grad, nullptr,
+                            nullptr, nullptr, nullptr, st);
     }
 
     PrepSmem ps = make_prep_smem(g, kSmemLimit);
@@ -1679,10 +1759,8 @@ int fa_ref_forward_backward(const float *x1, const float *x2, int B, int C, int 
     unsigned *ticket = next_ticket_slot(st);
     if (!ticket) return DSRL_ERR_CUDA;
     const double Z = reduction == DSRL_REDUCE_MEAN ? (double)g.BC * (double)g.n * (double)g.n : 1.0;
-    fa_ref_fused_small<<<g.BC, kFusedThreads, 0, st>>>(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket,
-                                              (float)(1.0 / Z), Z, loss_out, 1, grad_out, dx1, dx2, bn);
-    DSRL_LAUNCH_CHECK();
-    return DSRL_OK;
+    return launch_fused(x1, x2, g, so, static_cast<unsigned char *>(saved_v), static_cast<double *>(ws), ticket, (float)(1.0 / Z), Z, loss_out,
+                        1, grad_out, dx1, dx2, bn, st);
 }
 
 int fa_ref_backward(const void *saved_v, size_t saved_bytes, const float *grad_out, float *dx1, float *dx2, int B, int C,

@@ -10,5 +10,5 @@ for _ in range(5):
     plan.forward(a, b, True); torch.cuda.synchronize()
     tm = plan.ws.view(torch.int64)[64:73].cpu().numpy()
     dbg = plan.ws.view(torch.int64)[73:81].cpu().numpy()
-    print("  polish: cycles to loop end", dbg[0], "iterations", dbg[1], "d per iteration", [float(np.int32(v).view(np.float32)) for v in dbg[2:7]])
+    print("  solver warp (m <= 8): M, squarings, start, power steps, final pair:", np.diff(dbg[:6]), " start after kernel begin:", dbg[0] - tm[0], " rank: setup", dbg[6] - tm[4], "searches", dbg[7] - dbg[6], "rest", tm[5] - dbg[7])
     print("phase cycles (pool, Gram+sort || sigma solve, -, scale+vote, rank, partial, grad, finish):", np.diff(tm), "total", tm[8] - tm[0])
