@@ -1212,7 +1212,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
     // to run one after the other.
     __shared__ FusedBranch sb[2];
     __shared__ int is_last;
-    __shared__ double cl_part[8];                       // cluster form: CTA 0 collects the loss partials of the (<= 8) CTAs here
+    __shared__ double cl_part[64];                      // cluster form: CTA 0 collects the per-warp loss partials of the (<= 8) CTAs here
     const int tid = threadIdx.x, br = tid / kFusedBranchThreads, ht = tid - br * kFusedBranchThreads;
     const bool solver = ht >= 256;                       // warp 8 of the branch
     const Grp grp{ht, 256, 1 + br};                      // the branch's workers
@@ -1455,6 +1455,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
     const bool bad = !(sigma > 0.0 && sigma < (double)INFINITY) || (!solver && ht < n && !(fabsf(sraw) < INFINITY));
     const bool has_nan = __syncthreads_or(bad) != 0;
     TSTAMP(4);
+    double gs_term = 0.0;                                    // cnt_i * S_i: its sum is <G, S> = <G^, P> / (2 sigma g_scale)
     if (!solver && ht < n && (br == 0 || need_grad)) {
         const FusedBranch &ob = sb[1 - br];
         const double osc = ob.keep[2];
@@ -1480,6 +1481,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
         if (bc == 0 && tid == 0) g_fused_dbg[7] = clock64() + (lt & 0);
 #endif
         fb.cnt[ht] = has_nan ? 0 : lt - gt;
+        gs_term = (double)(has_nan ? 0 : lt - gt) * xd;
         if (br == 0)
             local = has_nan ? (double)NAN : xd * (double)(lt - gt) - ob.pre[lt] * osc + (ob.pre[n] - ob.pre[le]) * osc;
     }
@@ -1492,25 +1494,40 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
         if (use_cluster) ref_cluster_arrive();
         return;                                              // no block-wide barrier follows
     }
-    if (br == 0) {
-        const double tot = group_sum_d(local, fb.scratch, ht, 256, 1 + br);
-        if (ht == 0) {
-            if (use_cluster) {
-                st_cluster_f64(&cl_part[ref_cluster_rank()], 0u, tot);
-            } else {
-                partials[bc] = tot;
-                __threadfence();
-                const unsigned old = atomicInc(ticket, gridDim.x - 1);     // wraps to 0 after the last CTA: self-resetting
-                is_last = (old == gridDim.x - 1);
+    // One reduction pass for both sums a branch needs: the loss terms (branch 0) and cnt_i * S_i (the gradient's <G^, P>, which
+    // equals 2 sigma <G, S> because S is symmetric -- so the gradient phase needs no reduction of its own).  Warp sums only: the
+    // eight per-warp loss partials go straight into CTA 0's shared memory (cluster form) and are added there in a fixed order.
+    {
+        const int lane = ht & 31, wid = ht >> 5;
+        const double tg = wsum_d(gs_term);
+        if (lane == 0) fb.scratch[wid] = tg;
+        if (br == 0) {
+            const double tl = wsum_d(local);
+            if (lane == 0) {
+                if (use_cluster) st_cluster_f64(&cl_part[ref_cluster_rank() * 8 + wid], 0u, tl);
+                else fb.scratch[8 + wid] = tl;
             }
         }
     }
-    if (use_cluster) ref_cluster_arrive();
+    grp.sync();                                              // also orders the cnt writes before the G + G^T build below
+    double gs_sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gs_sum += fb.scratch[i];
+    if (use_cluster) {
+        ref_cluster_arrive();
+    } else if (br == 0 && ht == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += fb.scratch[8 + i];
+        partials[bc] = tot;
+        __threadfence();
+        const unsigned old = atomicInc(ticket, gridDim.x - 1);     // wraps to 0 after the last CTA: self-resetting
+        is_last = (old == gridDim.x - 1);
+    }
 
     TSTAMP(6);
     // 5. pooled gradient for unit upstream gradient
     if (need_grad) {
-        grp.sync();
         if (ht < n) fb.Gs[qw * lda + rw] = (float)(fb.cnt[ht] + fb.cnt[rw * w + qw]) * g_scale;     // G + G^T
         grp.sync();
         float gh0 = 0.f, gh1 = 0.f;
@@ -1522,9 +1539,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
 #pragma unroll 4
             for (int xp = 0; xp < w; ++xp) gh1 = fmaf(fb.A[qw2 * lda + xp], fb.Gs[xp * lda + rw2], gh1);
         }
-        double inner = (c0 ? (double)gh0 * (double)fb.P[a0] : 0.0) + (c1 ? (double)gh1 * (double)fb.P[a1] : 0.0);
-        inner = group_sum_d(inner, fb.scratch, ht, 256, 1 + br);
-        const float coef = (float)(inner / (sigma * sigma));
+        const float coef = (float)(2.0 * (double)g_scale * gs_sum / sigma);      // <G^, P> / sigma^2
         float *gdA = reinterpret_cast<float *>(saved + so.dA) + ((size_t)br * g.BC + bc) * hw;
         const float ga0 = gh0 / sigf - coef * du[qw] * dv[rw];
         const float ga1 = c1 ? gh1 / sigf - coef * du[qw2] * dv[rw2] : 0.f;
@@ -1559,7 +1574,7 @@ __global__ void __launch_bounds__(kFusedThreads) fa_ref_fused_small(const float 
             ref_cluster_wait();                              // every thread of every CTA has arrived: all partials are in cl_part
             if (tid == 0) {
                 double s = 0.0;
-                for (int i = 0; i < (int)gridDim.x; ++i) s += cl_part[i];
+                for (int i = 0; i < 8 * (int)gridDim.x; ++i) s += cl_part[i];
                 *reinterpret_cast<double *>(saved) = s;
                 *loss_out = (float)(s / loss_div);
             }
