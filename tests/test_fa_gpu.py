@@ -106,6 +106,27 @@ def test_wide_map_reduction_none():
     assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
 
 
+@pytest.mark.parametrize("shape,dist", [((3, 1, 64, 128), "relu"), ((5, 1, 64, 128), "randn"), ((7, 1, 64, 128), "relu"),
+                                        ((8, 1, 64, 128), "relu"), ((3, 4, 64, 128), "relu"), ((2, 8, 64, 128), "randn"),
+                                        ((2, 1, 128, 128), "relu"), ((1, 2, 256, 128), "randn"), ((1, 3, 96, 104), "relu")])
+def test_fused_kernel_grid_and_solver_paths(shape, dist):
+    """The single-launch kernel of the training shapes: every cluster size 1..8 of its loss reduction (B*C CTAs as one thread-block
+    cluster, partials over distributed shared memory), the global-ticket form of larger grids (B*C = 12, 16), and the solver
+    warp's two forms -- register-resident for a short side <= 8, shared-memory squarings for 9..16 (pooled 16 x 16, 32 x 16,
+    12 x 13).  Against the float64 oracle; forward + backward through autograd and as the one-call form."""
+    from dualsuperreslearningforsemseg_b200.functional import FAPlan
+    x1, x2 = fa_inputs(shape, dist, 31)
+    loss, d1, d2 = run(x1, x2, 8, "mean")
+    ol, o1, o2 = fa_oracle.fa_reference(x1, x2, 8, "mean")
+    assert abs(float(loss) - ol) <= LOSS_RTOL * abs(ol), (float(loss), ol)
+    assert relnorm(d1, o1) <= GRAD_RTOL and relnorm(d2, o2) <= GRAD_RTOL, (relnorm(d1, o1), relnorm(d2, o2))
+    if shape[2] % 8 == 0 and shape[3] % 8 == 0:
+        plan = FAPlan(shape, subsample_factor=8)
+        l2, e1, e2 = plan.forward_backward(torch.from_numpy(x1).cuda(), torch.from_numpy(x2).cuda(), torch.ones((), device="cuda"))
+        torch.cuda.synchronize()
+        assert float(l2) == float(loss) and np.array_equal(e1.cpu().numpy(), d1) and np.array_equal(e2.cpu().numpy(), d2)
+
+
 @pytest.mark.parametrize("shape", [(2, 1, 256, 512), (2, 1, 1024, 1024), (2, 1, 512, 1152)])
 def test_dead_channel_on_every_all_pairs_path(shape):
     """sigma = 0 (an all-zero pooled map) must give a NaN loss, NaN gradient for the dead (b, c) of the dead branch and an
