@@ -532,7 +532,7 @@ __global__ void fa_ref_prepare(const float *__restrict__ x1, const float *__rest
         const int py = cell / w, px = cell - py * w;
         float v;
         if (pooled) v = gP[cell];                              // fa_ref_pool ran first
-        else { v = pool_cell(x, g.W, g.k, py, px, vec4); gP[cell] = v; }
+        else { v = pool_cell_rolled(x + (size_t)py * g.k * g.W + (size_t)px * g.k, g.W, g.k, vec4, false, 1.f, 0.f); gP[cell] = v; }   // all loads of a window in flight
         if (ps.sepW || mid) sA[py * lda + px] = v;
         if (!small && !mid) { if (g.transposed) sW[(size_t)px * g.L + py] = v; else sW[(size_t)py * g.L + px] = v; }
     }
