@@ -1637,7 +1637,7 @@ int launch_fused(const float *x1, const float *x2, const RefGeom &g, const RefSa
 
 int launch_grad(const RefGeom &g, const RefSaved &so, unsigned char *saved, const float *gfl, float g_scale,
                 const double *partials, int num_partials, double loss_div, float *loss_out, int do_grad, cudaStream_t st) {
-    if (do_grad && g.w > 64) {
+    if (do_grad && g.w > 32) {                 // (w = 64: 18.4 us in the single-CTA kernel below, 15.5 us here)
         const size_t smem = grad_rows_smem(g);
         if (smem > kSmemLimit) DSRL_FAIL(DSRL_ERR_UNSUPPORTED, "FA(reference): pooled map %dx%d too wide for shared memory", g.h, g.w);
         int rc = opt_in_smem(fa_ref_grad_rows, smem);
